@@ -1,0 +1,167 @@
+/* include/mh_gpu.h — C ABI of the B200-native Markov-Huffman codec (libmh_gpu.so).
+ *
+ * This is the drop-in boundary for the reference's hot path (jeremy-rifkin/Markov-Huffman-Coding). The reference
+ * has no FFI; its seam is the abstract class i_coding_provider (src/coding.h:18-35) plus the free function
+ * construct_table (src/main.cpp:29). Each entry point below names the reference interface it replaces.
+ * Plain pointers and sizes only: no CUDA, torch or C++ types cross this boundary (a CUDA stream is passed as
+ * void*). Every function returns MH_OK (0) or a negative mh_status; nothing exits or throws.
+ *
+ * There is no CPU fallback: every mh_gpu_* / mh_session_* call runs hand-written sm_100a kernels and fails with
+ * MH_ERR_CUDA / MH_ERR_NO_DEVICE when no device is usable.
+ */
+#ifndef MH_GPU_H
+#define MH_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mh_status {
+	MH_OK = 0,
+	MH_ERR_INVALID_ARG = -1,
+	MH_ERR_CUDA = -2,              /* a CUDA runtime call failed; see mh_last_error() */
+	MH_ERR_NO_DEVICE = -3,
+	MH_ERR_CAPACITY = -4,          /* an output buffer is too small */
+	MH_ERR_BAD_TABLE = -5,         /* table file truncated / malformed */
+	MH_ERR_CODE_TOO_LONG = -6,     /* a codeword exceeds MH_MAX_CODE_BITS (device tables only) */
+	MH_ERR_BAD_HEADER = -7,        /* "Input appears corrupt"                      (src/coding.cpp:103-106) */
+	MH_ERR_TYPE_MISMATCH = -8,     /* "File encoding method does not match ..."    (src/coding.cpp:107-110) */
+	MH_ERR_CORRUPT_STREAM = -9,    /* decode reached a null table entry / ran past the payload */
+	MH_ERR_COUNT_WRAPPED = -10,    /* a live count is a multiple of 2^32: the reference's int counter is 0 (F3) */
+	MH_ERR_NOT_CONVERGED = -11,    /* decode seam fix-up needs more iterations (device API only) */
+	MH_ERR_WORKSPACE = -12         /* workspace too small for this call */
+} mh_status;
+
+#define MH_MAX_CODE_BITS 56        /* device codebook entry: 8-bit length + 56-bit right-aligned code */
+#define MH_ORDER_HUFFMAN 0         /* -h : one tree, get_type() == 0 (src/huffman.cpp:48-50) */
+#define MH_ORDER_MARKOV 1          /* default: 256 trees indexed by the previous byte, get_type() == 1 */
+#define MH_PREV0 0x20              /* the reference seeds prev with ' ' (src/main.cpp:32, src/coding.cpp:67,118) */
+
+typedef void* mh_stream_t;         /* a cudaStream_t, or NULL for the default stream */
+
+const char* mh_status_string(int status);
+const char* mh_last_error(void);   /* thread-local detail of the last MH_ERR_CUDA */
+int mh_device_count(void);
+int mh_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Host side: the coding tables. Replaces huffman_table / markov_huffman_table (src/huffman.{h,cpp},
+ * src/markov_huffman.{h,cpp}), tree_node (src/tree.h) and min_pq (src/min_pq.tpp). Microsecond work that
+ * stays on the host and reproduces the reference's heap tie-breaking and int32 weight arithmetic exactly.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct mh_table mh_table;
+
+/* huffman_table(int*) (src/huffman.cpp:18-20) / markov_huffman_table(int*) (src/markov_huffman.cpp:9-13).
+ * counts: 256 (order 0) or 65536 (order 1, index 256*prev + c) 64-bit counts as mh_gpu_histogram produces them;
+ * they are truncated to the reference's int32 before use. */
+int mh_table_from_counts(const uint64_t* counts, int order, mh_table** out);
+/* huffman_table(bitbuffer&) / markov_huffman_table(bitbuffer&) (src/huffman.cpp:22-25, src/markov_huffman.cpp:15-25):
+ * load an encoding-table file image. The first bit selects the kind (src/main.cpp:147-161). */
+int mh_table_from_bytes(const uint8_t* bytes, size_t n, mh_table** out);
+/* write_coding_tree (src/coding.h:23; src/huffman.cpp:83-85,174-188; src/markov_huffman.cpp:80-88). */
+int mh_table_serialize(const mh_table* t, uint8_t* out, size_t cap, size_t* n_out);
+/* get_type() (src/coding.h:32). */
+int mh_table_order(const mh_table* t);
+/* huffman_table::empty() for context prev (src/huffman.cpp:44-46); prev is ignored for order 0. */
+int mh_table_context_empty(const mh_table* t, int prev);
+/* get_encoding(prev, c) (src/coding.h:33): *len = bit length (0: no codeword), bits = MSB-first bytes. */
+int mh_table_code(const mh_table* t, int prev, int c, uint8_t bits[32], int* len);
+int mh_table_max_code_bits(const mh_table* t);
+/* decoding_lookup(prev, w) (src/coding.h:34): kind 0 null, 1 leaf (value, depth), 2 internal node at depth 8. */
+int mh_table_lookup(const mh_table* t, int prev, int window, int* kind, int* value, int* depth);
+/* print_table() + print_tree() (src/coding.h:21-22): the `-g` dump, written to the caller's buffer. */
+int mh_table_debug_dump(const mh_table* t, char* out, size_t cap, size_t* n_out);
+void mh_table_destroy(mh_table* t);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Device side: the three hot loops on device-resident buffers (caller owns all buffers and the stream).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct mh_codebook mh_codebook;     /* flat (prev, c) -> (code, length) table in device memory */
+typedef struct mh_dectable mh_dectable;     /* 8-bit LUTs + flattened trees for the > 8-bit walk, in device memory */
+typedef struct mh_workspace mh_workspace;   /* device scratch: scan descriptors, subsequence states */
+
+int mh_codebook_create(const mh_table* t, mh_codebook** out);
+void mh_codebook_destroy(mh_codebook* cb);
+int mh_dectable_create(const mh_table* t, mh_dectable** out);
+void mh_dectable_destroy(mh_dectable* dt);
+/* Scratch for inputs up to max_input_bytes and payloads up to max_payload_bytes (either may be 0). */
+int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh_workspace** out);
+void mh_workspace_destroy(mh_workspace* ws);
+
+/* Replaces construct_table + its two lambdas (src/main.cpp:29-39, :168-170, :176-178).
+ * d_counts[256] (order 0) or d_counts[65536] (order 1) is OVERWRITTEN with the counts of d_in[0..n) where the
+ * byte before d_in[0] is prev0 (MH_PREV0 for a whole file; the previous shard's last byte when sharding). */
+int mh_gpu_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, uint64_t* d_counts,
+                     mh_workspace* ws, mh_stream_t stream);
+
+/* Replaces the loop of i_coding_provider::compress (src/coding.cpp:61-94) and the bit packer
+ * (src/bitbuffer.cpp:21-73,170-180). Writes the payload (no header byte) to d_out, MSB-first. The first payload
+ * bit lands at bit (bit_base & 7) of d_out[0] so that byte-range shards concatenate: shard g passes the global
+ * bit offset of its first codeword and the caller ORs the seam byte. d_out needs 4-byte alignment and
+ * out_capacity >= ceil(((bit_base & 7) + total_bits) / 32) * 4 bytes; bytes past the payload end inside the last
+ * 32-bit word are written as zero. d_result is 4 x uint64: [0] = payload bits produced, [1] = symbols that had no
+ * codeword and were dropped like the reference does (assert compiled out, src/coding.cpp:72), [2] = 1 if
+ * out_capacity was too small (nothing useful was written), [3] reserved. */
+int mh_gpu_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
+                  uint8_t* d_out, uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream);
+
+/* Replaces the loop of i_coding_provider::decompress (src/coding.cpp:118-157) and the bit reader
+ * (src/bitbuffer.cpp:75-140). d_bits: payload (no header byte), 4-byte aligned, n_bits payload bits starting at
+ * bit 0 of d_bits[0]; bits past the payload read as zero (pop_rest pads, src/bitbuffer.cpp:129-140).
+ * d_result is 4 x uint64: [0] = bytes decoded, [1] = 0 or a negative mh_status that stopped the write pass
+ * (MH_ERR_CAPACITY, MH_ERR_NOT_CONVERGED), [2] = 0 or MH_ERR_CORRUPT_STREAM (bytes were still written, as the
+ * reference would), [3] reserved. */
+int mh_gpu_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt,
+                  uint8_t* d_out, uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Host-buffer calls: what a maintainer binds in place of compress(FILE*, FILE*) / decompress(FILE*, FILE*)
+ * (src/coding.h:26-27) and of the table construction in main (src/main.cpp:164-183). A session owns a stream,
+ * pinned staging and device buffers sized at creation; calls are synchronous and include the H2D / D2H copies.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct mh_session mh_session;
+
+int mh_session_create(int device, uint64_t max_input_bytes, mh_session** out);
+void mh_session_destroy(mh_session* s);
+
+/* `markovhuffman in -o out [-h] -d table` minus the file I/O: histogram -> tables -> encode.
+ * in[0..n) host bytes. out receives header byte + payload (the exact compressed file image).
+ * *table_out (optional) receives the table that was built; the caller destroys it. */
+int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
+                        uint8_t* out, uint64_t out_capacity, uint64_t* out_len, mh_table** table_out);
+/* `markovhuffman in -o out -e table`: encode with a given table (src/main.cpp:137-162 then :211).
+ * *dropped (optional) = symbols without a codeword. */
+int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n,
+                                   uint8_t* out, uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped);
+/* `markovhuffman in -o out -x -e table`: header checks (src/coding.cpp:100-116) then decode.
+ * Call with out == NULL to get the decoded size in *out_len without writing. */
+int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* stream, uint64_t stream_len,
+                          uint8_t* out, uint64_t out_capacity, uint64_t* out_len);
+/* Histogram only (host buffer in, host counts out): construct_table on the device. */
+int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order, uint64_t* counts);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Synthetic workloads of the benchmark configs; not part of the reference. Byte-identical to
+ * the oracle's generators (oracle/mh_oracle.c) so the CPU baseline can be fed the same data.
+ * ------------------------------------------------------------------------------------------------------- */
+int mh_synth_markov(const uint32_t* trans_counts /* host [65536] */, uint64_t seed, uint64_t seg_bytes,
+                    uint64_t first_seg, uint8_t* d_out, uint64_t n, mh_stream_t stream);
+int mh_synth_fibonacci(int k_symbols, uint8_t base, uint64_t seed, uint64_t first_index,
+                       uint8_t* d_out, uint64_t n, mh_stream_t stream);
+
+/* Launch counter: number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t mh_kernel_launches(void);
+
+/* Per-kernel device timing for bench.py's roofline: while enabled, every launch is bracketed by CUDA events on the
+ * stream it is launched on. mh_profile_report synchronises those events and writes a JSON object
+ * {"kernel": {"launches": n, "ms": total}, ...} (NUL-terminated) and clears the record. */
+int mh_profile_enable(int on);
+int mh_profile_report(char* out, size_t cap, size_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

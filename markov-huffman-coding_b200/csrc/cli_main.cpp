@@ -1,0 +1,267 @@
+// cli_main.cpp — `markovhuffman`, the C++ host driver behind the reference's command line
+//   markov-huffman <input> [-o output] [-h] [-e encoding_file] [-d output_encoding_file] [-g] [-x]
+// (reference src/main.cpp:17-27, :41-217). The flag grammar, validation errors, exit codes and stderr progress
+// lines follow the reference; all coding work goes through the C ABI of libmh_gpu.so (include/mh_gpu.h) and runs
+// on the GPU. There is no CPU path: without a usable device the tool reports the error and exits 1.
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <unistd.h>
+
+#include "../../include/mh_gpu.h"
+
+#define eprintf(...) fprintf(stderr, __VA_ARGS__)
+
+namespace {
+
+void usage() {   // src/main.cpp:17-27
+	eprintf("markov-huffman <input> [-o output] [options]\n");
+	eprintf("\t-o output_file\n");
+	eprintf("\t-h use simple huffman coding\n");
+	eprintf("\n");
+	eprintf("\t-e encoding_file\n");
+	eprintf("\t-d output_encoding_file\n");
+	eprintf("\n");
+	eprintf("\t-g print huffman trees and tables\n");
+	eprintf("\t-x extract\n");
+}
+
+// src/utils.cpp:44-56: only warns, and without a trailing newline
+void probe_access(const char* path, bool write) {
+	if(access(path, write ? W_OK : R_OK) == -1)
+		eprintf("Error: Unable to open \"%s\" for %s; %s.", path, write ? "writing" : "reading", strerror(errno));
+}
+
+bool slurp(FILE* f, std::vector<uint8_t>& out) {
+	uint8_t buf[1 << 16];
+	size_t got;
+	while((got = fread(buf, 1, sizeof buf, f)) > 0) out.insert(out.end(), buf, buf + got);
+	return !ferror(f);
+}
+
+[[noreturn]] void die_status(const char* what, int rc) {
+	if(rc == MH_ERR_BAD_HEADER) eprintf("Error while decoding file: Input appears corrupt.\n");                        // src/coding.cpp:104
+	else if(rc == MH_ERR_TYPE_MISMATCH) eprintf("Error: File encoding method does not match provided encoding table.\n");   // src/coding.cpp:108
+	else if(rc == MH_ERR_CUDA || rc == MH_ERR_NO_DEVICE) eprintf("Error: %s: %s (%s). This build has no CPU path.\n", what, mh_status_string(rc), mh_last_error());
+	else eprintf("Error: %s: %s.\n", what, mh_status_string(rc));
+	exit(1);
+}
+
+const char* shown(const char* s) { return s ? s : "(null)"; }   // what glibc prints for a null %s
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+	if(argc < 2) {
+		usage();
+		return 1;
+	}
+	bool extract = false, debug = false, simple_huffman = false;
+	const char* input = nullptr;
+	const char* output = nullptr;
+	const char* encoding_input = nullptr;
+	const char* encoding_output = nullptr;
+	// src/main.cpp:55-101: short flags may be combined ("-xh"); every value flag inside one argument consumes the
+	// next unused argv entry in order; a bare "-" is a no-op; unknown flags warn and continue.
+	for(int i = 1; i < argc; i++) {
+		if(argv[i][0] != '-') {
+			if(!input) input = argv[i];
+			else eprintf("Warning: Unexpected positional argument %s.\n", argv[i]);
+			continue;
+		}
+		int taken = 0;
+		auto value = [&]() -> const char* {
+			const int at = i + taken + 1;
+			++taken;
+			return at <= argc ? argv[at] : nullptr;   // argv[argc] is the null terminator, as the reference would read
+		};
+		for(const char* f = argv[i] + 1; *f; ++f) {
+			switch(*f) {
+				case 'o':
+					if(i + 1 < argc) output = value();
+					else eprintf("Error: Expected output file following -o.\n");
+					break;
+				case 'e':
+					if(i + 1 < argc) encoding_input = value();
+					else eprintf("Error: Expected encoding file following -e.\n");
+					break;
+				case 'd':
+					if(i + 1 < argc) encoding_output = value();
+					else eprintf("Error: Expected encoding output file following -d.\n");
+					break;
+				case 'x': extract = true; break;
+				case 'h': simple_huffman = true; break;
+				case 'g': debug = true; break;
+				default: eprintf("Warning: Unknown option %c.\n", *f);
+			}
+		}
+		i += taken;
+	}
+
+	// src/main.cpp:104-115
+	if(!input) {
+		eprintf("Error: Must provide input file.\n");
+		exit(1);
+	}
+	if(encoding_input && encoding_output) {
+		eprintf("Error: Don't provide an encoding input and an encoding output. Just use cp.\n");
+		exit(1);
+	}
+	if(extract && !encoding_input) {
+		eprintf("Error: Must provide encoding file input while in decompress mode.\n");
+		exit(1);
+	}
+	// src/main.cpp:118-121
+	probe_access(input, false);
+	if(output) probe_access(output, true);
+	if(encoding_input) probe_access(encoding_input, false);
+	if(encoding_output) probe_access(encoding_output, false);
+
+	FILE* input_fd = fopen(input, "rb");
+	if(!input_fd) {
+		eprintf("Error while opening input; %s.\n", strerror(errno));
+		exit(1);
+	}
+	FILE* output_fd = output ? fopen(output, "wb") : stdout;   // opened early to catch errors (src/main.cpp:129-134)
+	if(!output_fd) {
+		eprintf("Error while opening output; %s.\n", strerror(errno));
+		exit(1);
+	}
+
+	std::vector<uint8_t> in_bytes;
+	if(!slurp(input_fd, in_bytes)) {
+		eprintf("Error occurred while reading file.\n");   // src/utils.cpp:62-65
+		exit(1);
+	}
+	fclose(input_fd);
+
+	const int order = simple_huffman ? MH_ORDER_HUFFMAN : MH_ORDER_MARKOV;
+	mh_table* table = nullptr;
+	mh_session* session = nullptr;
+	std::vector<uint8_t> result;
+
+	if(encoding_input) {
+		eprintf("Loading encoding table from file...\n");
+		FILE* tf = fopen(encoding_input, "rb");
+		if(!tf) {
+			eprintf("Error while opening encoding input; %s.\n", strerror(errno));
+			exit(1);
+		}
+		std::vector<uint8_t> tbytes;
+		if(!slurp(tf, tbytes)) {
+			eprintf("Error occurred while reading file.\n");
+			exit(1);
+		}
+		fclose(tf);
+		if(tbytes.empty()) {   // the reference peeks a bit of an empty buffer here (undefined); refuse instead
+			eprintf("Error: Encoding table file is empty.\n");
+			exit(1);
+		}
+		const bool file_is_markov = (tbytes[0] & 0x80) != 0;   // src/main.cpp:147-154
+		if(file_is_markov != !simple_huffman) {
+			eprintf("Error: Incorrect encoding table provided for current operation; expected %s, found %s.\n",
+			        simple_huffman ? "simple Huffman" : "Markov-Huffman", file_is_markov ? "Markov-Huffman" : "simple Huffman");
+			exit(1);
+		}
+		int rc = mh_table_from_bytes(tbytes.data(), tbytes.size(), &table);
+		if(rc != MH_OK) die_status("loading the encoding table", rc);
+	}
+
+	// device buffers: the uncompressed side bounds the session. For -x the decoded size is unknown until the count
+	// pass; every symbol costs at least one bit, so 8x the payload is a safe bound and the usual ratio needs far less.
+	uint64_t raw_bound = in_bytes.size();
+	if(extract) raw_bound = in_bytes.size() * 8 + 64;
+	int rc = mh_session_create(0, raw_bound + 64, &session);
+	if(rc != MH_OK) die_status("creating the GPU session", rc);
+
+	bool built_here = false;
+	if(!encoding_input) {
+		eprintf(simple_huffman ? "Building simple Huffman encoding table from input...\n"
+		                       : "Building Markov-Huffman encoding table from input...\n");
+		built_here = true;
+	}
+
+	if(built_here) {
+		// histogram -> trees -> encode, all in one session call; the table comes back for -g / -d
+		result.resize(in_bytes.size() + in_bytes.size() / 8 + 4200);
+		uint64_t out_len = 0;
+		rc = mh_session_compress(session, in_bytes.data(), in_bytes.size(), order, result.data(), result.size(), &out_len, &table);
+		if(rc != MH_OK) die_status("compressing", rc);
+		result.resize(out_len);
+	}
+
+	if(debug) {   // src/main.cpp:187-190
+		size_t n = 0;
+		mh_table_debug_dump(table, nullptr, 0, &n);
+		std::string text(n, '\0');
+		if(n && mh_table_debug_dump(table, &text[0], n, &n) == MH_OK) fwrite(text.data(), 1, n, stdout);
+	}
+
+	if(encoding_output) {   // src/main.cpp:193-202
+		FILE* ef = fopen(encoding_output, "wb");
+		eprintf("Writing encoding table to %s...\n", encoding_output);
+		if(!ef) {
+			eprintf("Error while opening encoding file output; %s.\n", strerror(errno));
+			exit(1);
+		}
+		size_t n = 0;
+		mh_table_serialize(table, nullptr, 0, &n);
+		std::vector<uint8_t> tb(n ? n : 1);
+		if(mh_table_serialize(table, tb.data(), tb.size(), &n) != MH_OK || (n && fwrite(tb.data(), 1, n, ef) != n)) {
+			eprintf("Error occurred while writing file.\n");
+			exit(1);
+		}
+		fclose(ef);
+	}
+
+	if(extract) {
+		eprintf("Extracting %s ===> %s...\n", input, shown(output));
+		uint64_t n_out = 0;
+		rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), nullptr, 0, &n_out);
+		if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
+		result.resize(n_out ? n_out : 1);
+		rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), result.data(), result.size(), &n_out);
+		if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
+		result.resize(n_out);
+		if(n_out && fwrite(result.data(), 1, n_out, output_fd) != n_out) {
+			eprintf("Error occurred while writing file.\n");
+			exit(1);
+		}
+	} else {
+		eprintf("Compressing %s ===> %s...\n", input, shown(output));
+		if(!built_here) {
+			result.resize(in_bytes.size() + in_bytes.size() / 8 + 4200);
+			uint64_t out_len = 0, dropped = 0;
+			rc = mh_session_compress_with_table(session, table, in_bytes.data(), in_bytes.size(), result.data(), result.size(), &out_len, &dropped);
+			if(rc != MH_OK) die_status("compressing", rc);
+			result.resize(out_len);
+		}
+		// The reference writes a 0x80 placeholder first and seeks back to patch the header (src/coding.cpp:66, :85-89).
+		// On a non-seekable sink the seek fails and the header byte lands after the payload; keep that behaviour.
+		const bool seekable = fseek(output_fd, 0, SEEK_CUR) == 0;
+		bool ok;
+		if(seekable) {
+			ok = fwrite(result.data(), 1, result.size(), output_fd) == result.size();
+		} else {
+			const uint8_t placeholder = 0x80;
+			ok = fwrite(&placeholder, 1, 1, output_fd) == 1 &&
+			     (result.size() == 1 || fwrite(result.data() + 1, 1, result.size() - 1, output_fd) == result.size() - 1) &&
+			     fwrite(result.data(), 1, 1, output_fd) == 1;
+		}
+		if(!ok) {
+			eprintf("Error occurred while writing file.\n");
+			exit(1);
+		}
+	}
+	if(output_fd != stdout) fclose(output_fd);
+	else fflush(stdout);
+
+	mh_table_destroy(table);
+	mh_session_destroy(session);
+	eprintf("Done.\n");
+	return 0;
+}

@@ -1,0 +1,509 @@
+// mh_api.cu — the C ABI of libmh_gpu.so (include/mh_gpu.h): handles, workspaces, the device entry points and the
+// host-buffer session that stands in for i_coding_provider::compress / decompress (reference src/coding.cpp:61-160)
+// and for the table construction in main (src/main.cpp:164-183).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mh_host.hpp"
+#include "mh_internal.hpp"
+
+struct mh_table {
+	mh::CodingTable impl;
+};
+
+namespace mh {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+static thread_local std::string t_last_error;
+
+int cuda_fail(cudaError_t e, const char* what) {
+	t_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+	cudaGetLastError();   // clear the sticky-free error state
+	return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? MH_ERR_NO_DEVICE : MH_ERR_CUDA;
+}
+
+namespace {
+struct ProfRecord { const char* name; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof;
+}  // namespace
+
+ProfScope::ProfScope(const char* name, cudaStream_t s) : slot(-1), st(s) {
+	if(!g_prof_on) return;
+	ProfRecord r{name, nullptr, nullptr};
+	if(cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+	cudaEventRecord(r.a, st);
+	g_prof.push_back(r);
+	slot = int(g_prof.size()) - 1;
+}
+ProfScope::~ProfScope() {
+	if(slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+}
+
+int sm_count() {
+	static int cached = 0;
+	if(!cached) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cached <= 0) cached = 148;
+	}
+	return cached;
+}
+
+int max_smem_optin() {
+	static int cached = 0;
+	if(!cached) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if(cudaDeviceGetAttribute(&cached, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) cached = 48 * 1024;
+	}
+	return cached;
+}
+
+}  // namespace mh
+
+using namespace mh;
+
+extern "C" {
+
+const char* mh_status_string(int status) {
+	switch(status) {
+		case MH_OK: return "ok";
+		case MH_ERR_INVALID_ARG: return "invalid argument";
+		case MH_ERR_CUDA: return "CUDA error";
+		case MH_ERR_NO_DEVICE: return "no CUDA device";
+		case MH_ERR_CAPACITY: return "output buffer too small";
+		case MH_ERR_BAD_TABLE: return "encoding table is truncated or malformed";
+		case MH_ERR_CODE_TOO_LONG: return "a codeword exceeds 56 bits";
+		case MH_ERR_BAD_HEADER: return "Input appears corrupt";
+		case MH_ERR_TYPE_MISMATCH: return "File encoding method does not match provided encoding table";
+		case MH_ERR_CORRUPT_STREAM: return "compressed stream is corrupt";
+		case MH_ERR_COUNT_WRAPPED: return "a symbol count is a non-zero multiple of 2^32";
+		case MH_ERR_NOT_CONVERGED: return "decoder seams did not converge";
+		case MH_ERR_WORKSPACE: return "workspace too small";
+	}
+	return "unknown status";
+}
+
+const char* mh_last_error(void) { return t_last_error.c_str(); }
+
+int mh_device_count(void) {
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+int mh_version(void) { return 100; }
+
+uint64_t mh_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int mh_profile_enable(int on) {
+	for(auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+	g_prof.clear();
+	g_prof_on = on != 0;
+	return MH_OK;
+}
+
+int mh_profile_report(char* out, size_t cap, size_t* n_out) {
+	if(!n_out) return MH_ERR_INVALID_ARG;
+	struct Agg { const char* name; uint64_t launches; double ms; };
+	std::vector<Agg> agg;
+	for(auto& r : g_prof) {
+		float ms = 0.f;
+		if(cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+		size_t k = 0;
+		while(k < agg.size() && strcmp(agg[k].name, r.name) != 0) ++k;
+		if(k == agg.size()) agg.push_back({r.name, 0, 0.0});
+		agg[k].launches += 1;
+		agg[k].ms += ms;
+	}
+	std::string js = "{";
+	for(size_t k = 0; k < agg.size(); ++k) {
+		char buf[256];
+		snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f}", k ? ", " : "", agg[k].name,
+		         (unsigned long long) agg[k].launches, agg[k].ms);
+		js += buf;
+	}
+	js += "}";
+	*n_out = js.size() + 1;
+	if(js.size() + 1 > cap) return MH_ERR_CAPACITY;
+	memcpy(out, js.c_str(), js.size() + 1);
+	const bool keep = g_prof_on;
+	mh_profile_enable(keep ? 1 : 0);
+	return MH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host tables
+// ---------------------------------------------------------------------------------------------------------
+int mh_table_from_counts(const uint64_t* counts, int order, mh_table** out) {
+	if(!counts || !out) return MH_ERR_INVALID_ARG;
+	mh_table* t = new(std::nothrow) mh_table;
+	if(!t) return MH_ERR_INVALID_ARG;
+	int rc = CodingTable::from_counts(counts, order, t->impl);
+	if(rc != MH_OK) { delete t; return rc; }
+	*out = t;
+	return MH_OK;
+}
+
+int mh_table_from_bytes(const uint8_t* bytes, size_t n, mh_table** out) {
+	if(!out) return MH_ERR_INVALID_ARG;
+	mh_table* t = new(std::nothrow) mh_table;
+	if(!t) return MH_ERR_INVALID_ARG;
+	int rc = CodingTable::from_bytes(bytes, n, t->impl);
+	if(rc != MH_OK) { delete t; return rc; }
+	*out = t;
+	return MH_OK;
+}
+
+int mh_table_serialize(const mh_table* t, uint8_t* out, size_t cap, size_t* n_out) {
+	if(!t || !n_out) return MH_ERR_INVALID_ARG;
+	std::vector<uint8_t> v = t->impl.serialize();
+	*n_out = v.size();
+	if(v.size() > cap) return MH_ERR_CAPACITY;
+	if(!v.empty()) memcpy(out, v.data(), v.size());
+	return MH_OK;
+}
+
+int mh_table_order(const mh_table* t) { return t ? t->impl.order : MH_ERR_INVALID_ARG; }
+
+int mh_table_context_empty(const mh_table* t, int prev) {
+	if(!t || prev < 0 || prev > 255) return MH_ERR_INVALID_ARG;
+	return t->impl.tree_for(prev).empty() ? 1 : 0;
+}
+
+int mh_table_code(const mh_table* t, int prev, int c, uint8_t bits[32], int* len) {
+	if(!t || !len || prev < 0 || prev > 255 || c < 0 || c > 255) return MH_ERR_INVALID_ARG;
+	const Codeword& cw = t->impl.tree_for(prev).code[c];
+	*len = cw.length;
+	if(bits) memcpy(bits, cw.bytes.data(), 32);
+	return MH_OK;
+}
+
+int mh_table_max_code_bits(const mh_table* t) { return t ? t->impl.max_code_bits() : MH_ERR_INVALID_ARG; }
+
+int mh_table_lookup(const mh_table* t, int prev, int window, int* kind, int* value, int* depth) {
+	if(!t || prev < 0 || prev > 255 || window < 0 || window > 255 || !kind || !value || !depth) return MH_ERR_INVALID_ARG;
+	const CodeTree& tr = t->impl.tree_for(prev);
+	const int n = tr.lut[window];
+	if(n == kNoChild) { *kind = 0; *value = 0; *depth = 0; return MH_OK; }
+	*kind = tr.nodes[n].internal ? 2 : 1;
+	*value = tr.nodes[n].symbol;
+	*depth = tr.nodes[n].depth;
+	return MH_OK;
+}
+
+int mh_table_debug_dump(const mh_table* t, char* out, size_t cap, size_t* n_out) {
+	if(!t || !n_out) return MH_ERR_INVALID_ARG;
+	std::string s = t->impl.debug_dump();
+	*n_out = s.size();
+	if(s.size() > cap) return MH_ERR_CAPACITY;
+	if(!s.empty()) memcpy(out, s.data(), s.size());
+	return MH_OK;
+}
+
+void mh_table_destroy(mh_table* t) { delete t; }
+
+// ---------------------------------------------------------------------------------------------------------
+// device tables and scratch
+// ---------------------------------------------------------------------------------------------------------
+static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st, bool sync) {
+	std::vector<uint64_t> enc;
+	int rc = t->impl.flatten_codebook(enc);
+	if(rc != MH_OK) return rc;
+	if(!cb->d_enc) MH_CUDA(cudaMalloc(&cb->d_enc, 65536 * sizeof(uint64_t)));
+	MH_CUDA(cudaMemcpyAsync(cb->d_enc, enc.data(), enc.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	if(sync) MH_CUDA(cudaStreamSynchronize(st));   // pageable source: the copy has consumed `enc` once the stream drains
+	cb->order = t->impl.order;
+	cb->max_bits = t->impl.max_code_bits();
+	return MH_OK;
+}
+
+static int upload_dectable(const mh_table* t, mh_dectable* dt, cudaStream_t st, bool sync) {
+	std::vector<uint16_t> lut;
+	std::vector<uint32_t> walk;
+	t->impl.flatten_dectable(lut, walk);
+	if(!dt->d_lut) MH_CUDA(cudaMalloc(&dt->d_lut, 65536 * sizeof(uint16_t)));
+	if(!dt->d_walk) MH_CUDA(cudaMalloc(&dt->d_walk, 256 * 512 * sizeof(uint32_t)));
+	MH_CUDA(cudaMemcpyAsync(dt->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+	MH_CUDA(cudaMemcpyAsync(dt->d_walk, walk.data(), walk.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	if(sync) MH_CUDA(cudaStreamSynchronize(st));
+	dt->order = t->impl.order;
+	dt->max_bits = t->impl.max_code_bits();
+	return MH_OK;
+}
+
+int mh_codebook_create(const mh_table* t, mh_codebook** out) {
+	if(!t || !out) return MH_ERR_INVALID_ARG;
+	mh_codebook* cb = new(std::nothrow) mh_codebook;
+	if(!cb) return MH_ERR_INVALID_ARG;
+	int rc = upload_codebook(t, cb, nullptr, true);
+	if(rc != MH_OK) { mh_codebook_destroy(cb); return rc; }
+	*out = cb;
+	return MH_OK;
+}
+
+void mh_codebook_destroy(mh_codebook* cb) {
+	if(!cb) return;
+	if(cb->d_enc) cudaFree(cb->d_enc);
+	delete cb;
+}
+
+int mh_dectable_create(const mh_table* t, mh_dectable** out) {
+	if(!t || !out) return MH_ERR_INVALID_ARG;
+	mh_dectable* dt = new(std::nothrow) mh_dectable;
+	if(!dt) return MH_ERR_INVALID_ARG;
+	int rc = upload_dectable(t, dt, nullptr, true);
+	if(rc != MH_OK) { mh_dectable_destroy(dt); return rc; }
+	*out = dt;
+	return MH_OK;
+}
+
+void mh_dectable_destroy(mh_dectable* dt) {
+	if(!dt) return;
+	if(dt->d_lut) cudaFree(dt->d_lut);
+	if(dt->d_walk) cudaFree(dt->d_walk);
+	delete dt;
+}
+
+int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh_workspace** out) {
+	if(!out) return MH_ERR_INVALID_ARG;
+	mh_workspace* ws = new(std::nothrow) mh_workspace;
+	if(!ws) return MH_ERR_INVALID_ARG;
+	auto fail = [&](int rc) { mh_workspace_destroy(ws); return rc; };
+#define WS_CUDA(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(cuda_fail(e_, #call)); } while(0)
+	WS_CUDA(cudaMalloc(&ws->counters, 16 * sizeof(uint32_t)));
+	WS_CUDA(cudaMalloc(&ws->hist_params, 8 * sizeof(uint32_t)));
+	WS_CUDA(cudaMemset(ws->counters, 0, 16 * sizeof(uint32_t)));
+	WS_CUDA(cudaMemset(ws->hist_params, 0, 8 * sizeof(uint32_t)));
+	ws->enc_tiles_cap = encode_tiles_for(max_input_bytes) + 1;
+	WS_CUDA(cudaMalloc(&ws->enc_desc, ws->enc_tiles_cap * sizeof(uint64_t)));
+	WS_CUDA(cudaMalloc(&ws->enc_tail_agg, ws->enc_tiles_cap * sizeof(uint32_t)));
+	WS_CUDA(cudaMalloc(&ws->enc_tail_inc, ws->enc_tiles_cap * sizeof(uint32_t)));
+	const uint64_t min_sub = decode_sub_bits(0) < decode_sub_bits(1) ? decode_sub_bits(0) : decode_sub_bits(1);
+	ws->dec_subs_cap = (max_payload_bytes * 8 + min_sub - 1) / min_sub + 1;
+	ws->dec_chunks_cap = ws->dec_subs_cap / (kDecThreads - kDecWarmSubs) + 2;
+	WS_CUDA(cudaMalloc(&ws->dec_state, ws->dec_subs_cap * sizeof(uint32_t)));
+	WS_CUDA(cudaMalloc(&ws->dec_count, ws->dec_subs_cap * sizeof(uint32_t)));
+	WS_CUDA(cudaMalloc(&ws->dec_seam, ws->dec_chunks_cap * sizeof(uint32_t)));
+	WS_CUDA(cudaMalloc(&ws->dec_chunk_total, ws->dec_chunks_cap * sizeof(uint64_t)));
+	WS_CUDA(cudaMalloc(&ws->dec_chunk_base, (ws->dec_chunks_cap + 1) * sizeof(uint64_t)));
+	WS_CUDA(cudaMalloc(&ws->dec_flags, 8 * sizeof(uint32_t)));
+#undef WS_CUDA
+	*out = ws;
+	return MH_OK;
+}
+
+void mh_workspace_destroy(mh_workspace* ws) {
+	if(!ws) return;
+	void* ptrs[] = {ws->enc_desc, ws->enc_tail_agg, ws->enc_tail_inc, ws->counters, ws->hist_params, ws->dec_state,
+	                ws->dec_count, ws->dec_seam, ws->dec_chunk_total, ws->dec_chunk_base, ws->dec_flags};
+	for(void* p : ptrs)
+		if(p) cudaFree(p);
+	delete ws;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the three device entry points
+// ---------------------------------------------------------------------------------------------------------
+int mh_gpu_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, uint64_t* d_counts, mh_workspace* ws,
+                     mh_stream_t stream) {
+	return launch_histogram(d_in, n, prev0, order, reinterpret_cast<unsigned long long*>(d_counts), ws, static_cast<cudaStream_t>(stream));
+}
+
+int mh_gpu_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base, uint8_t* d_out,
+                  uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream) {
+	return launch_encode(d_in, n, prev0, cb, bit_base, d_out, out_capacity, reinterpret_cast<unsigned long long*>(d_result), ws,
+	                     static_cast<cudaStream_t>(stream));
+}
+
+int mh_gpu_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+                  uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream) {
+	return launch_decode(d_bits, n_bits, prev0, dt, d_out, out_capacity, reinterpret_cast<unsigned long long*>(d_result), ws,
+	                     static_cast<cudaStream_t>(stream), 2);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer session
+// ---------------------------------------------------------------------------------------------------------
+struct mh_session {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	uint64_t max_input = 0;
+	uint64_t payload_cap = 0;
+	uint8_t* d_raw = nullptr;       // uncompressed side
+	uint8_t* d_payload = nullptr;   // compressed side (no header byte)
+	uint64_t* d_counts = nullptr;   // [65536]
+	uint64_t* d_result = nullptr;   // [4]
+	uint64_t* h_counts = nullptr;   // pinned [65536]
+	uint64_t* h_result = nullptr;   // pinned [4]
+	mh_workspace* ws = nullptr;
+	mh_codebook book;
+	mh_dectable dec;
+};
+
+extern "C" {
+
+int mh_session_create(int device, uint64_t max_input_bytes, mh_session** out) {
+	if(!out) return MH_ERR_INVALID_ARG;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if(e != cudaSuccess || ndev == 0) { cudaGetLastError(); t_last_error = "no usable CUDA device"; return MH_ERR_NO_DEVICE; }
+	if(device < 0 || device >= ndev) return MH_ERR_INVALID_ARG;
+	MH_CUDA(cudaSetDevice(device));
+	mh_session* s = new(std::nothrow) mh_session;
+	if(!s) return MH_ERR_INVALID_ARG;
+	s->device = device;
+	s->max_input = max_input_bytes;
+	// An optimal prefix code built from the data's own counts never averages more than 8 bits per byte; a foreign
+	// -e table can expand, which is reported as MH_ERR_CAPACITY rather than silently truncated.
+	s->payload_cap = ((max_input_bytes + (max_input_bytes >> 3) + 4096 + 15) / 16) * 16;
+	auto fail = [&](int rc) { mh_session_destroy(s); return rc; };
+#define S_CUDA(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(cuda_fail(e_, #call)); } while(0)
+	S_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	S_CUDA(cudaMalloc(&s->d_raw, max_input_bytes + 64));
+	S_CUDA(cudaMalloc(&s->d_payload, s->payload_cap));
+	S_CUDA(cudaMalloc(&s->d_counts, 65536 * sizeof(uint64_t)));
+	S_CUDA(cudaMalloc(&s->d_result, 4 * sizeof(uint64_t)));
+	S_CUDA(cudaMallocHost(&s->h_counts, 65536 * sizeof(uint64_t)));
+	S_CUDA(cudaMallocHost(&s->h_result, 4 * sizeof(uint64_t)));
+#undef S_CUDA
+	int rc = mh_workspace_create(max_input_bytes, s->payload_cap, &s->ws);
+	if(rc != MH_OK) return fail(rc);
+	*out = s;
+	return MH_OK;
+}
+
+void mh_session_destroy(mh_session* s) {
+	if(!s) return;
+	cudaSetDevice(s->device);
+	if(s->stream) cudaStreamSynchronize(s->stream);
+	if(s->d_raw) cudaFree(s->d_raw);
+	if(s->d_payload) cudaFree(s->d_payload);
+	if(s->d_counts) cudaFree(s->d_counts);
+	if(s->d_result) cudaFree(s->d_result);
+	if(s->h_counts) cudaFreeHost(s->h_counts);
+	if(s->h_result) cudaFreeHost(s->h_result);
+	if(s->book.d_enc) cudaFree(s->book.d_enc);
+	if(s->dec.d_lut) cudaFree(s->dec.d_lut);
+	if(s->dec.d_walk) cudaFree(s->dec.d_walk);
+	mh_workspace_destroy(s->ws);
+	if(s->stream) cudaStreamDestroy(s->stream);
+	delete s;
+}
+
+int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order, uint64_t* counts) {
+	if(!s || !counts || (!in && n)) return MH_ERR_INVALID_ARG;
+	if(n > s->max_input) return MH_ERR_CAPACITY;
+	MH_CUDA(cudaSetDevice(s->device));
+	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
+	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
+	if(rc != MH_OK) return rc;
+	const size_t bins = order ? 65536 : 256;
+	MH_CUDA(cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+	MH_CUDA(cudaStreamSynchronize(s->stream));
+	memcpy(counts, s->h_counts, bins * sizeof(uint64_t));
+	return MH_OK;
+}
+
+// encode d_raw[0..n) with `t`, fetch header + payload into out
+static int session_encode(mh_session* s, const mh_table* t, uint64_t n, uint8_t* out, uint64_t out_capacity,
+                          uint64_t* out_len, uint64_t* dropped) {
+	if(out_capacity < 1) return MH_ERR_CAPACITY;
+	int rc = upload_codebook(t, &s->book, s->stream, true);
+	if(rc != MH_OK) return rc;
+	rc = launch_encode(s->d_raw, n, MH_PREV0, &s->book, 0, s->d_payload, s->payload_cap,
+	                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
+	if(rc != MH_OK) return rc;
+	MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+	MH_CUDA(cudaStreamSynchronize(s->stream));
+	if(s->h_result[2]) return MH_ERR_CAPACITY;
+	const uint64_t bits = s->h_result[0];
+	const uint64_t bytes = (bits + 7) / 8;
+	if(dropped) *dropped = s->h_result[1];
+	*out_len = 1 + bytes;
+	if(1 + bytes > out_capacity) return MH_ERR_CAPACITY;
+	// header: 0 0 1 1 E R R R, E = inverse of the coder type, RRR = unused bits of the last byte (src/coding.cpp:88)
+	out[0] = uint8_t(0x30 | ((~t->impl.order & 1) << 3) | ((8 - bits % 8) % 8));
+	if(bytes) {
+		MH_CUDA(cudaMemcpyAsync(out + 1, s->d_payload, bytes, cudaMemcpyDeviceToHost, s->stream));
+		MH_CUDA(cudaStreamSynchronize(s->stream));
+	}
+	return MH_OK;
+}
+
+int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order, uint8_t* out, uint64_t out_capacity,
+                        uint64_t* out_len, mh_table** table_out) {
+	if(!s || !out || !out_len || (!in && n) || (order != 0 && order != 1)) return MH_ERR_INVALID_ARG;
+	if(n > s->max_input) return MH_ERR_CAPACITY;
+	MH_CUDA(cudaSetDevice(s->device));
+	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
+	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
+	if(rc != MH_OK) return rc;
+	const size_t bins = order ? 65536 : 256;
+	MH_CUDA(cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+	MH_CUDA(cudaStreamSynchronize(s->stream));
+	mh_table* t = nullptr;
+	rc = mh_table_from_counts(s->h_counts, order, &t);
+	if(rc != MH_OK) return rc;
+	rc = session_encode(s, t, n, out, out_capacity, out_len, nullptr);
+	if(rc == MH_OK && table_out) *table_out = t;
+	else mh_table_destroy(t);
+	return rc;
+}
+
+int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n, uint8_t* out,
+                                   uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped) {
+	if(!s || !t || !out || !out_len || (!in && n)) return MH_ERR_INVALID_ARG;
+	if(n > s->max_input) return MH_ERR_CAPACITY;
+	MH_CUDA(cudaSetDevice(s->device));
+	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
+	return session_encode(s, t, n, out, out_capacity, out_len, dropped);
+}
+
+int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* stream, uint64_t stream_len, uint8_t* out,
+                          uint64_t out_capacity, uint64_t* out_len) {
+	if(!s || !t || !stream || !out_len) return MH_ERR_INVALID_ARG;
+	if(stream_len < 1) return MH_ERR_BAD_HEADER;
+	const uint8_t header = stream[0];
+	if((header & 0xF0) != 0x30) return MH_ERR_BAD_HEADER;                       // src/coding.cpp:103-106
+	if(((~header >> 3) & 1) != t->impl.order) return MH_ERR_TYPE_MISMATCH;      // src/coding.cpp:107-110
+	const uint64_t payload_bytes = stream_len - 1;
+	const uint64_t remainder = header & 7;
+	// src/coding.cpp:115 in 64-bit; a negative length makes the reference's loop (:124) decode nothing
+	const uint64_t n_bits = payload_bytes * 8 < remainder ? 0 : payload_bytes * 8 - remainder;
+	if(payload_bytes > s->payload_cap) return MH_ERR_CAPACITY;
+	MH_CUDA(cudaSetDevice(s->device));
+	int rc = upload_dectable(t, &s->dec, s->stream, true);
+	if(rc != MH_OK) return rc;
+	if(payload_bytes) MH_CUDA(cudaMemcpyAsync(s->d_payload, stream + 1, payload_bytes, cudaMemcpyHostToDevice, s->stream));
+	const uint64_t dev_cap = s->max_input;
+	int iters = 2;
+	for(;;) {
+		rc = launch_decode(s->d_payload, n_bits, MH_PREV0, &s->dec, s->d_raw, dev_cap,
+		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
+		if(rc != MH_OK) return rc;
+		MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+		MH_CUDA(cudaStreamSynchronize(s->stream));
+		if(int64_t(s->h_result[1]) == MH_ERR_NOT_CONVERGED && iters < 8) { iters = 8; continue; }
+		break;
+	}
+	*out_len = s->h_result[0];
+	if(int64_t(s->h_result[1]) != 0) return int(int64_t(s->h_result[1]));
+	if(!out) return MH_OK;
+	if(s->h_result[0] > out_capacity) return MH_ERR_CAPACITY;
+	if(s->h_result[0]) {
+		MH_CUDA(cudaMemcpyAsync(out, s->d_raw, s->h_result[0], cudaMemcpyDeviceToHost, s->stream));
+		MH_CUDA(cudaStreamSynchronize(s->stream));
+	}
+	if(int64_t(s->h_result[2]) != 0) return int(int64_t(s->h_result[2]));   // bytes are delivered, like the reference, but flagged
+	return MH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+// mh_decode.cu — kernel 3: self-synchronising speculative parallel decoder.
+//
+// Replaces the loop of i_coding_provider::decompress (reference src/coding.cpp:118-157) and the bit reader it
+// drives (bitbuffer::pop_rest / try_pop_bit / pop_bit, src/bitbuffer.cpp:82-90, :116-140): take the next 8
+// stream bits (zero padded past the end), look them up in the previous symbol's 256-entry table
+// (decoding_lookup, src/markov_huffman.cpp:56-58); a leaf gives (symbol, length <= 8); an internal node at
+// depth 8 consumes 8 bits and is walked bit by bit to a leaf (src/coding.cpp:129-149).
+//
+// The stream has no symbol count and no block index, so decoding is sequential by construction. Decode state is
+// (bit position, previous symbol). The payload is cut into subsequences of S bits; Huffman streams
+// self-synchronise, so a decoder started at a wrong state converges onto the true parse.
+//   D1 sync     one thread per subsequence decodes it from a guessed state, then keeps decoding its successors
+//               until the end state it produces equals the one already recorded there (Weißenberger & Schmidt's
+//               scheme, extended to compare the context as well as the bit position). Each CTA also re-decodes
+//               the last kDecWarmSubs subsequences of the previous chunk as warm-up, so its own first
+//               subsequence normally starts from a converged state.
+//   D2 seams    one thread per chunk boundary checks that the previous chunk's recorded end state equals what
+//               this chunk's warm-up produced; only on a mismatch does it re-decode from the recorded state until
+//               it merges. Repeats until no chunk end state changes (normally zero re-decodes).
+//   D3 offsets  per-chunk symbol totals, exclusive scan -> output offset of every chunk, total output size.
+//   D4 write    one thread per subsequence decodes from its verified start state and writes its symbols at its
+//               output offset (block scan of the per-subsequence counts inside the chunk).
+// D1 and D4 are persistent CTAs that stage the decode LUT (128 KiB in Markov mode) in shared memory once.
+#include "mh_internal.hpp"
+
+namespace mh {
+
+namespace {
+
+constexpr int kWarm = kDecWarmSubs;
+constexpr int kChunkSubs = kDecThreads - kWarm;   // subsequences owned by one chunk
+
+struct Tables {
+	const uint16_t* lut;    // shared or global; row = context (order 1) or 0
+	const uint32_t* walk;   // global
+};
+
+// MSB-first bit window over 32-bit words of the payload. `avail` valid bits are left-aligned in `buf`.
+struct Cursor {
+	const uint32_t* words;
+	uint64_t n_bytes;
+	uint64_t next;   // index of the next word to fetch
+	uint64_t buf;
+	int avail;
+
+	__device__ __forceinline__ uint32_t fetch(uint64_t w) const {
+		const uint64_t o = w << 2;
+		if(o + 4 <= n_bytes) return __byte_perm(__ldg(words + w), 0, 0x0123);
+		uint32_t v = 0;   // ragged end: bytes past the payload read as zero (pop_rest pads, src/bitbuffer.cpp:129-140)
+		const uint8_t* b = reinterpret_cast<const uint8_t*>(words);
+		for(int i = 0; i < 4; ++i)
+			if(o + i < n_bytes) v |= uint32_t(b[o + i]) << (24 - 8 * i);
+		return v;
+	}
+	__device__ __forceinline__ void seek(uint64_t bit) {
+		const uint64_t w = bit >> 5;
+		const int off = int(bit & 31);
+		buf = ((uint64_t(fetch(w)) << 32) | fetch(w + 1)) << off;
+		avail = 64 - off;
+		next = w + 2;
+	}
+	__device__ __forceinline__ void take(int nbits) { buf <<= nbits; avail -= nbits; }
+	__device__ __forceinline__ void top_up() {
+		if(avail <= 32) {
+			buf |= uint64_t(fetch(next)) << (32 - avail);
+			++next;
+			avail += 32;
+		}
+	}
+};
+
+// 8-byte packed output writer: single bytes until the address is 8-aligned, then whole 64-bit stores.
+struct Emitter {
+	uint8_t* out;
+	uint64_t at;
+	uint64_t pack;
+	int held;
+	__device__ __forceinline__ void init(uint8_t* o, uint64_t start) { out = o; at = start; pack = 0; held = 0; }
+	__device__ __forceinline__ void put(uint32_t sym) {
+		if(held == 0 && ((reinterpret_cast<uint64_t>(out) + at) & 7)) { out[at++] = uint8_t(sym); return; }
+		pack |= uint64_t(sym) << (8 * held);
+		if(++held == 8) {
+			*reinterpret_cast<uint64_t*>(out + at) = pack;
+			at += 8; held = 0; pack = 0;
+		}
+	}
+	__device__ __forceinline__ void finish() {
+		for(int i = 0; i < held; ++i) out[at + i] = uint8_t(pack >> (8 * i));
+	}
+};
+
+// Decode every symbol whose first bit lies in [pos, limit). pos/limit are bit offsets from the cursor's origin
+// (the caller seeks the cursor to origin + pos). Returns false if a null table entry was hit.
+template <int ORDER, bool WRITE>
+__device__ __forceinline__ bool decode_span(Cursor& cur, const Tables& tb, uint32_t& pos, uint32_t limit, uint32_t& ctx,
+                                            uint32_t& count, Emitter* em) {
+	bool clean = true;
+	while(pos < limit) {
+		const uint32_t row = ORDER ? ctx : 0u;
+		const uint32_t e = tb.lut[(row << 8) + uint32_t(cur.buf >> 56)];
+		uint32_t sym;
+		if(!(e & 0x8000u)) {
+			const int len = int((e >> 8) & 15u);
+			sym = e & 255u;
+			if(e & 0x4000u) clean = false;
+			cur.take(len);
+			pos += len;
+		} else {
+			cur.take(8);
+			pos += 8;
+			uint32_t node = e & 0x1ffu;
+			sym = ' ';
+			for(int guard = 0; guard < 256; ++guard) {
+				cur.top_up();
+				const uint32_t bit = uint32_t(cur.buf >> 63);
+				cur.take(1);
+				++pos;
+				const uint32_t w = __ldg(tb.walk + (row << 9) + node);
+				const uint32_t child = bit ? (w & 0xffffu) : (w >> 16);
+				if(child & 0x8000u) { sym = child & 255u; break; }
+				node = child;
+				if(guard == 255) clean = false;
+			}
+		}
+		ctx = sym;
+		++count;
+		if(WRITE) em->put(sym);
+		cur.top_up();
+	}
+	return clean;
+}
+
+__device__ __forceinline__ uint32_t pack_state(uint32_t rel_bits, uint32_t ctx) { return (rel_bits << 8) | ctx; }
+
+// ---------------------------------------------------------------------------------------------------------
+// D1: speculative decode + intra-chunk synchronisation
+// ---------------------------------------------------------------------------------------------------------
+template <int ORDER>
+__global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
+    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t prev0, const uint16_t* __restrict__ lut_g,
+    const uint32_t* __restrict__ walk, uint32_t* __restrict__ state, uint32_t* __restrict__ count,
+    uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks) {
+	extern __shared__ uint16_t lut_s[];
+	__shared__ uint32_t st_s[kDecThreads];
+	__shared__ uint32_t cnt_s[kDecThreads];
+	const uint32_t tid = threadIdx.x;
+	{
+		const uint32_t n16 = ORDER ? 65536u : 256u;
+		const uint4* src = reinterpret_cast<const uint4*>(lut_g);
+		uint4* dst = reinterpret_cast<uint4*>(lut_s);
+		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
+	}
+	__syncthreads();
+	Tables tb{lut_s, walk};
+	Cursor cur;
+	cur.words = words;
+	cur.n_bytes = (n_bits + 7) >> 3;
+
+	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+		// thread t handles subsequence first_sub + t where first_sub may be negative for chunk 0
+		const int64_t first_sub = int64_t(chunk) * kChunkSubs - kWarm;
+		const int64_t my_sub = first_sub + tid;
+		const int64_t end_sub = int64_t(chunk + 1) * kChunkSubs < int64_t(n_subs) ? int64_t(chunk + 1) * kChunkSubs : int64_t(n_subs);
+		const uint64_t origin = first_sub < 0 ? 0 : uint64_t(first_sub) * sub_bits;   // bit origin of this CTA's window
+		const int64_t origin_sub = first_sub < 0 ? 0 : first_sub;
+		bool active = my_sub >= 0 && my_sub < end_sub;
+
+		auto limit_of = [&](int64_t k) -> uint32_t {   // end of subsequence k relative to origin
+			uint64_t e = uint64_t(k + 1) * sub_bits;
+			if(e > n_bits) e = n_bits;
+			return uint32_t(e - origin);
+		};
+
+		uint32_t pos = 0, ctx = ' ', cnt = 0;
+		int64_t k = my_sub;
+		if(active) {
+			pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
+			ctx = my_sub == 0 ? prev0 : uint32_t(' ');
+			cur.seek(origin + pos);
+			const uint32_t lim = limit_of(k);
+			decode_span<ORDER, false>(cur, tb, pos, lim, ctx, cnt, nullptr);
+			st_s[tid] = pack_state(pos - lim, ctx);
+			cnt_s[tid] = cnt;
+		}
+		__syncthreads();
+		// rounds: take over the next subsequence until my end state matches what is recorded there
+		for(;;) {
+			++k;
+			if(active && k >= end_sub) active = false;
+			if(active) {
+				const uint32_t lim = limit_of(k);
+				cnt = 0;
+				decode_span<ORDER, false>(cur, tb, pos, lim, ctx, cnt, nullptr);
+				const uint32_t st = pack_state(pos - lim, ctx);
+				const uint32_t slot = uint32_t(k - first_sub);
+				cnt_s[slot] = cnt;
+				if(st_s[slot] == st) active = false;
+				else st_s[slot] = st;
+			}
+			if(!__syncthreads_or(active ? 1 : 0)) break;
+		}
+		if(my_sub >= 0 && my_sub < end_sub) {
+			if(tid >= uint32_t(kWarm)) { state[my_sub] = st_s[tid]; count[my_sub] = cnt_s[tid]; }
+			else if(tid == uint32_t(kWarm - 1)) seam[chunk] = st_s[tid];   // boundary state as this chunk saw it
+		}
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// D2: chunk seams. flags[slot] is raised when some chunk's END state changed (the next pass must re-check).
+// ---------------------------------------------------------------------------------------------------------
+template <int ORDER>
+__global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_bits, const uint16_t* __restrict__ lut_g,
+                                const uint32_t* __restrict__ walk, uint32_t* state, uint32_t* count, uint32_t* seam,
+                                uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t* flag) {
+	const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x + 1;
+	if(chunk >= n_chunks) return;
+	const uint64_t first = uint64_t(chunk) * kChunkSubs;
+	const uint32_t recorded = *(volatile uint32_t*) (state + first - 1);
+	if(seam[chunk] == recorded) return;
+	seam[chunk] = recorded;
+	const uint64_t last = first + kChunkSubs < n_subs ? first + kChunkSubs : n_subs;
+	const uint64_t origin = first * sub_bits;
+	Tables tb{lut_g, walk};
+	Cursor cur;
+	cur.words = words;
+	cur.n_bytes = (n_bits + 7) >> 3;
+	uint32_t pos = recorded >> 8, ctx = recorded & 255u;
+	cur.seek(origin + pos);
+	bool merged = false;
+	for(uint64_t k = first; k < last; ++k) {
+		uint64_t e = (k + 1) * sub_bits;
+		if(e > n_bits) e = n_bits;
+		const uint32_t lim = uint32_t(e - origin);
+		uint32_t cnt = 0;
+		decode_span<ORDER, false>(cur, tb, pos, lim, ctx, cnt, nullptr);
+		const uint32_t st = pack_state(pos - lim, ctx);
+		count[k] = cnt;
+		if(state[k] == st) { merged = true; break; }
+		state[k] = st;
+	}
+	if(!merged) *flag = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// D3: per-chunk totals and their exclusive scan
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_total_kernel(const uint32_t* __restrict__ count, uint64_t n_subs,
+                                                         unsigned long long* __restrict__ chunk_total) {
+	__shared__ unsigned long long part[8];
+	const uint64_t first = uint64_t(blockIdx.x) * kChunkSubs;
+	const uint64_t last = first + kChunkSubs < n_subs ? first + kChunkSubs : n_subs;
+	unsigned long long s = 0;
+	for(uint64_t k = first + threadIdx.x; k < last; k += 256) s += count[k];
+	for(int d = 16; d; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+	if((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if(threadIdx.x == 0) {
+		unsigned long long t = 0;
+		for(int i = 0; i < 8; ++i) t += part[i];
+		chunk_total[blockIdx.x] = t;
+	}
+}
+
+__global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long* __restrict__ chunk_total,
+                                                         unsigned long long* __restrict__ chunk_base, uint32_t n_chunks,
+                                                         uint64_t out_capacity, const uint32_t* __restrict__ flags, int last_flag,
+                                                         unsigned long long* __restrict__ result) {
+	__shared__ unsigned long long warp_tot[32];
+	__shared__ unsigned long long carry_s;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if(tid == 0) carry_s = 0;
+	__syncthreads();
+	for(uint32_t base = 0; base < n_chunks; base += 1024) {
+		const uint32_t i = base + tid;
+		const unsigned long long v = i < n_chunks ? chunk_total[i] : 0ull;
+		unsigned long long incl = v;
+		for(int d = 1; d < 32; d <<= 1) {
+			const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+			if(lane >= uint32_t(d)) incl += t;
+		}
+		if(lane == 31) warp_tot[warp] = incl;
+		__syncthreads();
+		unsigned long long before = carry_s;
+		for(uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
+		if(i < n_chunks) chunk_base[i] = before + incl - v;
+		__syncthreads();
+		if(tid == 1023) carry_s = before + incl;
+		__syncthreads();
+	}
+	if(tid == 0) {
+		const unsigned long long total = carry_s;
+		chunk_base[n_chunks] = total;
+		result[0] = total;
+		long long status = 0;
+		if(last_flag >= 0 && flags[last_flag]) status = MH_ERR_NOT_CONVERGED;
+		else if(total > out_capacity) status = MH_ERR_CAPACITY;
+		result[1] = (unsigned long long) status;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// D4: final decode + write
+// ---------------------------------------------------------------------------------------------------------
+template <int ORDER>
+__global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
+    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t prev0, const uint16_t* __restrict__ lut_g,
+    const uint32_t* __restrict__ walk, const uint32_t* __restrict__ state, const uint32_t* __restrict__ count,
+    const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits, uint64_t n_subs,
+    uint32_t n_chunks, unsigned long long* result) {
+	extern __shared__ uint16_t lut_s[];
+	__shared__ uint32_t warp_tot[32];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if(result[1] != 0) return;   // capacity / convergence error decided by D3: write nothing
+	{
+		const uint32_t n16 = ORDER ? 65536u : 256u;
+		const uint4* src = reinterpret_cast<const uint4*>(lut_g);
+		uint4* dst = reinterpret_cast<uint4*>(lut_s);
+		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
+	}
+	__syncthreads();
+	Tables tb{lut_s, walk};
+	Cursor cur;
+	cur.words = words;
+	cur.n_bytes = (n_bits + 7) >> 3;
+	bool clean = true;
+	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+		const uint64_t k = uint64_t(chunk) * kChunkSubs + tid;
+		const bool mine = tid < uint32_t(kChunkSubs) && k < n_subs;
+		const uint32_t c = mine ? count[k] : 0u;
+		uint32_t incl = c;
+		for(int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+			if(lane >= uint32_t(d)) incl += t;
+		}
+		if(lane == 31) warp_tot[warp] = incl;
+		__syncthreads();
+		uint32_t before = 0;
+		for(uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
+		__syncthreads();
+		if(mine) {
+			const uint32_t start = k == 0 ? pack_state(0, prev0) : state[k - 1];
+			const uint64_t origin = k * sub_bits;
+			uint64_t e = (k + 1) * sub_bits;
+			if(e > n_bits) e = n_bits;
+			uint32_t pos = start >> 8, ctx = start & 255u, cnt = 0;
+			const uint32_t lim = uint32_t(e - origin);
+			Emitter em;
+			em.init(out, chunk_base[chunk] + before + incl - c);
+			if(pos < lim) {
+				cur.seek(origin + pos);
+				clean &= decode_span<ORDER, true>(cur, tb, pos, lim, ctx, cnt, &em);
+			}
+			em.finish();
+			if(cnt != c) clean = false;
+			if(k == n_subs - 1 && origin + pos != n_bits) clean = false;   // the last codeword runs past the payload
+		}
+	}
+	if(!clean) result[2] = (unsigned long long) (long long) MH_ERR_CORRUPT_STREAM;
+}
+
+}  // namespace
+
+uint32_t decode_sub_bits(int order) {
+	static int cached[2] = {0, 0};
+	int& c = cached[order ? 1 : 0];
+	if(c == 0) {
+		c = order ? 1024 : 256;
+		const char* env = getenv(order ? "MH_DEC_SUB_BITS_MARKOV" : "MH_DEC_SUB_BITS_HUFFMAN");
+		if(env) {
+			int v = atoi(env);
+			if(v >= kDecMinSubBits && v % 32 == 0 && v <= (1 << 20)) c = v;
+		}
+	}
+	return uint32_t(c);
+}
+
+namespace {
+
+template <int ORDER>
+int run_decode(const uint32_t* words, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+               uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
+	const uint32_t sub_bits = decode_sub_bits(ORDER);
+	const uint64_t n_subs = (n_bits + sub_bits - 1) / sub_bits;
+	const uint64_t chunks64 = (n_subs + kChunkSubs - 1) / kChunkSubs;
+	if(n_subs > ws->dec_subs_cap || chunks64 > ws->dec_chunks_cap) return MH_ERR_WORKSPACE;
+	const uint32_t n_chunks = uint32_t(chunks64);
+	const size_t lut_bytes = ORDER ? 65536 * 2 : 256 * 2;
+	static bool attr_done = false;
+	if(!attr_done) {
+		MH_CUDA(cudaFuncSetAttribute(dec_sync_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lut_bytes)));
+		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lut_bytes)));
+		attr_done = true;
+	}
+	const int sms = sm_count();
+	const uint32_t grid = n_chunks < uint32_t(sms) ? n_chunks : uint32_t(sms);
+	MH_CUDA(cudaMemsetAsync(ws->dec_flags, 0, 8 * sizeof(uint32_t), st));
+	{
+		ProfScope p("dec_sync_kernel", st);
+		dec_sync_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, prev0, dt->d_lut, dt->d_walk, ws->dec_state,
+		    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks);
+	}
+	count_launch(1);
+	int last_flag = -1;
+	if(n_chunks > 1) {
+		if(fix_iters < 1) fix_iters = 1;
+		if(fix_iters > 8) fix_iters = 8;
+		for(int it = 0; it < fix_iters; ++it) {
+			ProfScope p("dec_seam_kernel", st);
+			dec_seam_kernel<ORDER><<<(n_chunks - 1 + 127) / 128, 128, 0, st>>>(words, n_bits, dt->d_lut, dt->d_walk, ws->dec_state,
+			    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, ws->dec_flags + it);
+			count_launch(1);
+			last_flag = it;
+		}
+	}
+	{
+		ProfScope p("dec_total_kernel", st);
+		dec_total_kernel<<<n_chunks, 256, 0, st>>>(ws->dec_count, n_subs, (unsigned long long*) ws->dec_chunk_total);
+	}
+	{
+		ProfScope p("dec_scan_kernel", st);
+		dec_scan_kernel<<<1, 1024, 0, st>>>((const unsigned long long*) ws->dec_chunk_total, (unsigned long long*) ws->dec_chunk_base,
+		    n_chunks, out_capacity, ws->dec_flags, last_flag, d_result);
+	}
+	{
+		ProfScope p("dec_write_kernel", st);
+		dec_write_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, prev0, dt->d_lut, dt->d_walk, ws->dec_state,
+		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, d_result);
+	}
+	count_launch(3);
+	MH_CUDA(cudaGetLastError());
+	return MH_OK;
+}
+
+}  // namespace
+
+int launch_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+                  uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
+	if(!dt || !dt->d_lut || !d_result || (!d_bits && n_bits)) return MH_ERR_INVALID_ARG;
+	if(reinterpret_cast<uint64_t>(d_bits) & 3) return MH_ERR_INVALID_ARG;
+	if(!ws || !ws->dec_state) return MH_ERR_WORKSPACE;
+	MH_CUDA(cudaMemsetAsync(d_result, 0, 4 * sizeof(unsigned long long), st));
+	if(n_bits == 0) return MH_OK;
+	const uint32_t* words = reinterpret_cast<const uint32_t*>(d_bits);
+	if(dt->order) return run_decode<1>(words, n_bits, prev0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	return run_decode<0>(words, n_bits, prev0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+}
+
+}  // namespace mh

@@ -1,0 +1,88 @@
+// mh_host.hpp — host-side coding tables for the B200 Markov-Huffman codec.
+//
+// The 256 tiny Huffman trees stay on the CPU (microsecond work) but must come out bit-identical to the
+// reference's: same heap tie-breaking (src/min_pq.tpp), same int32 weight arithmetic (src/tree.h:14,20),
+// same "shallower subtree goes left" swap (src/huffman.cpp:147-149), same single-symbol fake root
+// (src/huffman.cpp:154-162), same pre-order code assignment (src/huffman.cpp:97-123).
+// Trees are index-based arenas (no pointers) so they flatten directly into the device tables.
+#pragma once
+
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mh {
+
+constexpr int kNoChild = -1;
+constexpr int kMaxCodeBitsDevice = 56;
+
+struct TreeNode {
+	int left = kNoChild;
+	int right = kNoChild;
+	bool internal = false;
+	uint8_t symbol = 0;
+	int32_t weight = 0;   // int32 on purpose: wraps like the reference's `int weight`
+	int32_t height = 0;
+	int32_t depth = -1;
+};
+
+// A codeword of up to 255 bits, MSB-first (bit i of the codeword is bit 7 - i%8 of bytes[i/8]).
+struct Codeword {
+	int length = 0;
+	std::array<uint8_t, 32> bytes{};
+	void append(int bit);
+	void drop_last();
+	int bit(int i) const { return (bytes[i >> 3] >> (7 - (i & 7))) & 1; }
+};
+
+// One Huffman tree with its derived encode table and 8-bit decode LUT.
+class CodeTree {
+public:
+	std::vector<TreeNode> nodes;
+	int root = kNoChild;
+	std::array<Codeword, 256> code;     // code[c].length == 0: no codeword
+	std::array<int, 256> lut;           // node index per 8-bit window, kNoChild = null
+
+	CodeTree() { lut.fill(kNoChild); }
+	bool empty() const { return root == kNoChild; }
+	int max_code_bits() const;
+
+	// counts are the reference's ints (already truncated to int32 by the caller)
+	void build_from_counts(const int32_t* counts256);
+	// called after the shape exists (built or loaded): assigns depths, codewords and the LUT
+	void derive_codes();
+};
+
+class BitSink;    // MSB-first bit writer
+class BitSource;  // MSB-first bit reader
+
+// The reference's i_coding_provider state: one tree (-h) or 256 trees (Markov).
+class CodingTable {
+public:
+	int order = 1;                  // get_type()
+	std::vector<CodeTree> trees;    // size 1 or 256
+
+	static int from_counts(const uint64_t* counts, int order, CodingTable& out);       // returns mh_status
+	static int from_bytes(const uint8_t* bytes, size_t n, CodingTable& out);           // returns mh_status
+	std::vector<uint8_t> serialize() const;
+	const CodeTree& tree_for(int prev) const { return trees[order ? (prev & 255) : 0]; }
+	int max_code_bits() const;
+	std::string debug_dump() const;   // -g: print_table() + print_tree()
+
+	// ---- flat device images -------------------------------------------------------------------------
+	// enc[ctx*256 + c] = (len << 56) | code (right-aligned); returns MH_ERR_CODE_TOO_LONG if any len > 56
+	int flatten_codebook(std::vector<uint64_t>& enc) const;
+	// lut[ctx*256 + w]: leaf   : 0x0000 | len << 8 | symbol           (len 1..8)
+	//                  deep   : 0x8000 | node index within the context (internal node at depth 8)
+	//                  null   : 0x4000 | 1 << 8 | ' '                  (speculation-safe; an error if verified)
+	// walk[ctx*512 + node] = left << 16 | right, child = 0x8000|symbol for a leaf, else node index
+	void flatten_dectable(std::vector<uint16_t>& lut, std::vector<uint32_t>& walk) const;
+};
+
+constexpr uint16_t kLutDeep = 0x8000;
+constexpr uint16_t kLutNull = 0x4000;
+constexpr uint32_t kWalkLeaf = 0x8000;
+
+}  // namespace mh

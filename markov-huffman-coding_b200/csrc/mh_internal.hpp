@@ -1,0 +1,97 @@
+// mh_internal.hpp — shared declarations between the C-ABI glue (mh_api.cu) and the kernel files.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/mh_gpu.h"
+
+namespace mh {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+inline void count_launch(uint64_t n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Brackets one kernel launch with CUDA events on its stream while profiling is enabled (mh_profile_enable).
+struct ProfScope {
+	ProfScope(const char* name, cudaStream_t st);
+	~ProfScope();
+	int slot;
+	cudaStream_t st;
+};
+
+int cuda_fail(cudaError_t e, const char* what);   // records mh_last_error(), returns MH_ERR_CUDA
+#define MH_CUDA(call)                                              \
+	do {                                                           \
+		cudaError_t e_ = (call);                                   \
+		if(e_ != cudaSuccess) return ::mh::cuda_fail(e_, #call);   \
+	} while(0)
+
+int sm_count();          // multiprocessors of the current device (cached)
+int max_smem_optin();    // bytes of opt-in dynamic shared memory per block (cached)
+
+// ---- tunables (env overrides exist for experiments; defaults are what DESIGN.md documents) ------------
+constexpr int kEncThreads = 256;
+constexpr int kEncRoundBytes = kEncThreads * 16;      // one 128-bit load per thread per round
+constexpr int kEncStageWords = 8192;                  // 32 KiB of staged output bits per tile
+constexpr int kDecThreads = 1024;                     // subsequences per chunk (one thread each)
+constexpr int kDecMinSubBits = 256;
+constexpr int kDecWarmSubs = 8;                       // overlap subsequences re-decoded by the next chunk
+
+// ---- encode look-back descriptors -----------------------------------------------------------------------
+// status word: [63:62] 0 = empty, 1 = aggregate (this tile only), 2 = inclusive (all tiles up to this one);
+//              [61:0]  bit count. The matching tail word holds the last min(bits, 31) bits, right-aligned.
+constexpr uint64_t kDescAggregate = 1ull << 62;
+constexpr uint64_t kDescInclusive = 2ull << 62;
+constexpr uint64_t kDescValueMask = (1ull << 62) - 1;
+
+}  // namespace mh
+
+// Device scratch. All pointers are device memory owned by the workspace.
+struct mh_workspace {
+	// encode
+	uint64_t* enc_desc = nullptr;         // [enc_tiles_cap]
+	uint32_t* enc_tail_agg = nullptr;     // [enc_tiles_cap]
+	uint32_t* enc_tail_inc = nullptr;     // [enc_tiles_cap]
+	uint64_t enc_tiles_cap = 0;
+	uint32_t* counters = nullptr;         // [16] dynamic tile counters / flags
+	// histogram
+	uint32_t* hist_params = nullptr;      // [8] lo, range, replicas, ...
+	// decode
+	uint32_t* dec_state = nullptr;        // [dec_subs_cap] end state of each subsequence: rel_bits << 8 | context
+	uint32_t* dec_count = nullptr;        // [dec_subs_cap] symbols that start in each subsequence
+	uint64_t dec_subs_cap = 0;
+	uint32_t* dec_seam = nullptr;         // [dec_chunks_cap] boundary state as seen by the next chunk's warm-up
+	uint64_t* dec_chunk_total = nullptr;  // [dec_chunks_cap]
+	uint64_t* dec_chunk_base = nullptr;   // [dec_chunks_cap + 1]
+	uint64_t dec_chunks_cap = 0;
+	uint32_t* dec_flags = nullptr;        // [8] 0: seam mismatch pending, 1: error status, ...
+};
+
+struct mh_codebook {
+	uint64_t* d_enc = nullptr;   // [ntab * 256] len << 56 | code
+	int order = 1;
+	int max_bits = 0;
+};
+
+struct mh_dectable {
+	uint16_t* d_lut = nullptr;   // [ntab * 256]
+	uint32_t* d_walk = nullptr;  // [ntab * 512]
+	int order = 1;
+	int max_bits = 0;
+};
+
+namespace mh {
+
+int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, unsigned long long* d_counts,
+                     mh_workspace* ws, cudaStream_t st);
+int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
+                  uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st);
+int launch_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+                  uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
+uint32_t decode_sub_bits(int order);                 // subsequence size in bits used for this coder type
+uint64_t encode_tiles_for(uint64_t n);               // worst-case tile count for n input bytes
+
+}  // namespace mh

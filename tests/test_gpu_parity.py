@@ -1,0 +1,169 @@
+"""Parity of the CUDA path against the oracle and the reference-built golden vectors. Everything goes through the
+C ABI (include/mh_gpu.h) via the ctypes mirror. Bit-exact: integer / byte work has no tolerance."""
+import base64
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle_py as o
+from conftest import golden_input, load_golden
+from mhlib import load
+
+pytestmark = pytest.mark.gpu
+
+mh = load()
+CASES = load_golden()
+IDS = ["%s-%s" % (c["input"], c["mode"]) for c in CASES]
+
+
+@pytest.fixture(scope="module")
+def session():
+    s = mh.Session(72 << 20)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def ipsum_counts():
+    return o.histogram(golden_input("input_ipsum.txt"), True).astype(np.uint32)
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+# ---- config 1: the reference's own corpus, -d then -x, both modes ---------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_corpus_compress_matches_reference_bytes(session, case):
+    data = golden_input(case["input"])
+    order = int(case["mode"] == "markov")
+    stream, provider = session.compress(data, order)
+    table = provider.write_coding_tree()
+    assert len(table) == case["table_bytes"] and sha(table) == case["table_sha256"]
+    assert len(stream) == case["stream_bytes"]
+    assert "%02x" % stream[0] == case["header"]
+    assert sha(stream) == case["stream_sha256"]
+    if "stream_b64" in case:
+        assert stream == base64.b64decode(case["stream_b64"])
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_corpus_extract_restores_input(session, case):
+    data = golden_input(case["input"])
+    table = base64.b64decode(case["table_b64"])
+    if not table:
+        pytest.skip("empty -h table cannot be loaded (neither can the reference)")
+    markov = case["mode"] == "markov"
+    stream = o.Table.from_bytes(table).compress(data)           # reference-identical stream (pinned by test_oracle)
+    assert sha(stream) == case["stream_sha256"]
+    provider = mh.CodingProvider.from_table_file(table)          # the -e path
+    assert session.decompress(provider, stream) == data
+    assert session.compress_with_table(provider, data)[0] == stream
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_histogram_matches_oracle(session, order):
+    rng = np.random.default_rng(5)
+    for data in (golden_input("input_wiki_cpp.html"), golden_input("edge_random_64k.bin"), b"", b"x",
+                 bytes(rng.integers(0, 256, 1 << 20, dtype=np.uint8)), bytes(rng.integers(97, 101, 300001, dtype=np.uint8))):
+        got = session.histogram(data, order)
+        want = o.histogram(data, bool(order)).astype(np.int64).astype(np.uint64)
+        assert np.array_equal(got, want)
+
+
+# ---- sizes around every internal boundary (16-byte loads, 4 KiB rounds, tiles, subsequences, chunks) -----
+SIZES = [1, 2, 15, 16, 17, 31, 33, 255, 4095, 4096, 4097, 8191, 8192, 16383, 16384, 16385, 65536 + 3, 262144 + 17, 1048576 + 5]
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_ragged_sizes_roundtrip_and_match_oracle(session, ipsum_counts, order):
+    text = o.synth_markov(ipsum_counts, 77, 4096, 0, max(SIZES))
+    for n in SIZES:
+        data = text[:n]
+        stream, provider = session.compress(data, order)
+        want_stream, want_table = o.compress_from_input(data, bool(order))
+        assert stream == want_stream, "n=%d" % n
+        assert provider.write_coding_tree() == want_table
+        assert session.decompress(provider, stream) == data, "n=%d" % n
+
+
+# ---- configs 2-4 at sizes the oracle finishes in seconds --------------------------------------------------
+@pytest.mark.parametrize("order", [0, 1])
+def test_markov_text_8mib(session, ipsum_counts, order):
+    data = o.synth_markov(ipsum_counts, 20261018, 65536, 0, 8 << 20)
+    stream, provider = session.compress(data, order)
+    want_stream, want_table = o.compress_from_input(data, bool(order))
+    assert provider.write_coding_tree() == want_table
+    assert sha(stream) == sha(want_stream)
+    assert session.decompress(provider, stream) == data
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_fibonacci_long_codewords_4mib(session, order):
+    """Codewords beyond 8 bits: depth-8 LUT entries + tree walk in the decoder, 2-word pushes in the encoder."""
+    data = o.synth_fibonacci(40, 48, 1234, 0, 4 << 20)
+    stream, provider = session.compress(data, order)
+    assert provider.max_code_bits() > 16
+    want_stream, want_table = o.compress_from_input(data, bool(order))
+    assert provider.write_coding_tree() == want_table
+    assert sha(stream) == sha(want_stream)
+    assert session.decompress(provider, stream) == data
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_binary_data_all_256_symbols(session, order):
+    rng = np.random.default_rng(99)
+    skew = (rng.integers(0, 256, 3 << 20) * rng.integers(0, 256, 3 << 20) >> 8).astype(np.uint8)   # skewed, K = 256
+    data = bytes(skew)
+    stream, provider = session.compress(data, order)
+    want_stream, want_table = o.compress_from_input(data, bool(order))
+    assert provider.write_coding_tree() == want_table
+    assert sha(stream) == sha(want_stream)
+    assert session.decompress(provider, stream) == data
+
+
+def test_codewords_longer_than_32_bits(session):
+    """A foreign (-e) table with 44-deep Fibonacci codes: the encoder's long-code path, the decoder's deep walk."""
+    fib = np.zeros(256, dtype=np.uint64); a, b = 1, 1
+    for i in range(44):
+        fib[60 + i] = a; a, b = b, a + b
+    provider = mh.CodingProvider.from_counts_array(fib, 0)
+    assert provider.max_code_bits() == 43
+    rng = np.random.default_rng(1)
+    data = bytes((60 + rng.integers(0, 44, 200000)).astype(np.uint8))      # uniform over symbols: long codes are common
+    ot = o.Table.from_counts(fib.astype(np.int64), False)
+    stream, dropped = session.compress_with_table(provider, data)
+    assert dropped == 0
+    assert stream == ot.compress(data)
+    assert session.decompress(provider, stream) == data
+
+
+def test_symbols_missing_from_a_foreign_table_are_dropped_like_the_reference(session):
+    provider = mh.CodingProvider.from_counts_array(o.histogram(b"abracadabra" * 50, True).astype(np.uint64), 1)
+    ot = o.Table.from_counts(o.histogram(b"abracadabra" * 50, True), True)
+    data = b"abraXcadabra" * 3000 + b"ZZZZ" * 5000 + b"abra"
+    stream, dropped = session.compress_with_table(provider, data)
+    want, want_dropped = ot.compress(data, return_dropped=True)
+    assert dropped == want_dropped > 0
+    assert stream == want
+
+
+def test_header_checks(session):
+    data = golden_input("input_b.txt")
+    sm, pm = session.compress(data, 1)
+    sh_, ph = session.compress(data, 0)
+    with pytest.raises(mh.MhError) as e:
+        session.decompress(pm, sh_)
+    assert e.value.status == mh.MH_ERR_TYPE_MISMATCH
+    with pytest.raises(mh.MhError) as e:
+        session.decompress(pm, b"\x80" + sm[1:])
+    assert e.value.status == mh.MH_ERR_BAD_HEADER
+
+
+def test_single_symbol_contexts(session):
+    for data in (b"q" * 100000, b"ab" * 70000, b"Z"):
+        for order in (0, 1):
+            stream, provider = session.compress(data, order)
+            assert stream == o.compress_from_input(data, bool(order))[0]
+            assert session.decompress(provider, stream) == data

@@ -1,0 +1,142 @@
+"""Host logic of the product (tree building, code assignment, table file format) against the oracle and the
+reference-built golden vectors. CPU only: no kernel is launched."""
+import base64
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_py as o
+from conftest import ROOT, golden_input, load_golden
+from mhlib import load
+
+mh = load()
+CASES = load_golden()
+IDS = ["%s-%s" % (c["input"], c["mode"]) for c in CASES]
+
+
+def _counts(data, markov):
+    return o.histogram(data, markov).astype(np.int64).astype(np.uint64)   # oracle counts are only the INPUT here
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_table_file_matches_reference_golden(case):
+    data = golden_input(case["input"])
+    markov = case["mode"] == "markov"
+    p = mh.CodingProvider.from_counts_array(np.ascontiguousarray(_counts(data, markov)), int(markov))
+    table = p.write_coding_tree()
+    assert hashlib.sha256(table).hexdigest() == case["table_sha256"]
+    assert table == base64.b64decode(case["table_b64"])
+    assert p.get_type() == int(markov)
+    if table:
+        q = mh.CodingProvider.from_table_file(table)          # loader is the writer's mirror (left subtree first)
+        assert q.get_type() == int(markov)
+        assert q.write_coding_tree() == table
+        ot = o.Table.from_counts(o.histogram(data, markov), markov)
+        for prev in ([0x20, data[0]] if markov and data else [0]):
+            for c in range(256):
+                assert q.get_encoding(prev, c) == p.get_encoding(prev, c) == ot.code(prev, c)
+    else:
+        with pytest.raises(mh.MhError):
+            mh.CodingProvider.from_table_file(table)
+
+
+def _count_vectors():
+    rng = np.random.default_rng(3)
+    vs = [("all_equal", np.full(256, 7)), ("two", np.bincount([1, 255], minlength=256)), ("one", np.bincount([9], minlength=256) * 3)]
+    fib = np.zeros(256, dtype=np.int64); a, b = 1, 1
+    for i in range(44):
+        fib[100 + i] = a; a, b = b, a + b
+    vs.append(("fib44", fib))
+    big = rng.integers(1, 1 << 28, 256); big[32] = (1 << 31) - 5
+    vs.append(("sum_wraps_int32", big))
+    neg = rng.integers(0, 1 << 20, 256).astype(np.int64); neg[101] = (1 << 31) + 12345
+    vs.append(("count_wraps_negative", neg))
+    wide = rng.integers(0, 1 << 40, 256)
+    wide[wide % (1 << 32) == 0] += 1
+    vs.append(("counts_beyond_32_bits", wide))
+    for k in range(8):
+        vs.append(("rand%d" % k, rng.integers(0, 1 << rng.integers(1, 24), 256) * (rng.random(256) < rng.random())))
+    return vs
+
+
+@pytest.mark.parametrize("name,counts", _count_vectors(), ids=[n for n, _ in _count_vectors()])
+def test_single_tree_vs_oracle(name, counts):
+    """Tie-breaking, int32 wrap, LUT semantics: product host code == oracle (itself pinned to the reference)."""
+    cu = np.ascontiguousarray(np.asarray(counts, dtype=np.int64).astype(np.uint64))
+    p = mh.CodingProvider.from_counts_array(cu, 0)
+    ot = o.Table.from_counts(counts, False)
+    assert p.write_coding_tree() == ot.serialize()
+    for c in range(256):
+        assert p.get_encoding(0, c) == ot.code(0, c)
+    for w, (kind, value, depth) in enumerate(ot.lut(0)):
+        k2, v2, d2 = p.decoding_lookup(0, w)
+        assert k2 == kind
+        if kind:
+            assert d2 == depth
+        if kind == 1:
+            assert v2 == value
+    if o.ref() is not None:
+        assert p.write_coding_tree() == o.ref_table_from_counts(counts, False)
+
+
+def test_count_that_wraps_to_zero_is_refused():
+    counts = np.zeros(256, dtype=np.uint64)
+    counts[65] = 1 << 32
+    counts[66] = 5
+    with pytest.raises(mh.MhError) as e:
+        mh.CodingProvider.from_counts_array(counts, 0)
+    assert e.value.status == mh.MH_ERR_COUNT_WRAPPED
+
+
+def test_malformed_table_files():
+    good = base64.b64decode(next(c for c in CASES if c["input"] == "input_ipsum.txt" and c["mode"] == "markov")["table_b64"])
+    for cut in (1, 5, 33, len(good) // 2):
+        with pytest.raises(mh.MhError) as e:
+            mh.CodingProvider.from_table_file(good[:cut])
+        assert e.value.status == mh.MH_ERR_BAD_TABLE
+    with pytest.raises(mh.MhError):
+        mh.CodingProvider.from_table_file(b"\x40\x80")      # -h file whose root is a bare leaf: the writer never emits it
+    with pytest.raises(mh.MhError):
+        mh.CodingProvider.from_table_file(b"\x00" * 64)     # internal nodes forever: depth limit
+
+
+def test_debug_dump_matches_reference_cli(tmp_path):
+    """-g output (print_table + print_tree) byte for byte, when the reference binary is available."""
+    import subprocess
+    if not os.path.exists(o.REF_STOCK):
+        pytest.skip("oracle/_ref not built")
+    for name in ("input_b.txt", "input_ipsum.txt"):
+        for markov in (True, False):
+            src = os.path.join(ROOT, "tests/golden/inputs", name)
+            out = subprocess.run([o.REF_STOCK, src, "-o", str(tmp_path / "o"), "-g"] + ([] if markov else ["-h"]),
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE).stdout
+            p = mh.CodingProvider.from_counts_array(np.ascontiguousarray(_counts(golden_input(name), markov)), int(markov))
+            assert p.debug_dump() == out
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads and exports exactly what include/mh_gpu.h declares (no compute call is made)."""
+    header = open(os.path.join(ROOT, "include/mh_gpu.h")).read()
+    declared = set(re.findall(r"\b(mh_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mh_status"}
+    import ctypes
+    lib = ctypes.CDLL(mh.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libmh_gpu.so does not export %s" % name
+    assert declared == set(mh._SIGNATURES), declared ^ set(mh._SIGNATURES)
+    assert mh._lib.mh_status_string(mh.MH_ERR_BAD_HEADER) == b"Input appears corrupt"
+    assert mh._lib.mh_version() >= 100
+
+
+def test_no_device_fails_loudly():
+    """Without a usable GPU every compute entry point must raise, never fall back to the CPU."""
+    if mh.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(mh.MhError) as e:
+        mh.Session(1 << 20)
+    assert e.value.status in (mh.MH_ERR_NO_DEVICE, mh.MH_ERR_CUDA)
+    with pytest.raises(mh.MhError):
+        mh.compress(b"hello")
