@@ -70,6 +70,9 @@ int mh_table_context_empty(const mh_table* t, int prev);
 /* get_encoding(prev, c) (src/coding.h:33): *len = bit length (0: no codeword), bits = MSB-first bytes. */
 int mh_table_code(const mh_table* t, int prev, int c, uint8_t bits[32], int* len);
 int mh_table_max_code_bits(const mh_table* t);
+/* All code lengths at once: lens[256*prev + c] for order 1 (65536 entries), lens[c] for order 0 (256 entries).
+ * With the local histogram this gives a shard's payload size without touching the data (sum of count x length). */
+int mh_table_code_lengths(const mh_table* t, uint8_t* lens, size_t cap);
 /* decoding_lookup(prev, w) (src/coding.h:34): kind 0 null, 1 leaf (value, depth), 2 internal node at depth 8. */
 int mh_table_lookup(const mh_table* t, int prev, int window, int* kind, int* value, int* depth);
 /* print_table() + print_tree() (src/coding.h:21-22): the `-g` dump, written to the caller's buffer. */
@@ -84,8 +87,11 @@ typedef struct mh_dectable mh_dectable;     /* 8-bit LUTs + flattened trees for 
 typedef struct mh_workspace mh_workspace;   /* device scratch: scan descriptors, subsequence states */
 
 int mh_codebook_create(const mh_table* t, mh_codebook** out);
+/* Re-upload another table into an existing handle, stream-ordered, without allocating or blocking the host. */
+int mh_codebook_update(mh_codebook* cb, const mh_table* t, mh_stream_t stream);
 void mh_codebook_destroy(mh_codebook* cb);
 int mh_dectable_create(const mh_table* t, mh_dectable** out);
+int mh_dectable_update(mh_dectable* dt, const mh_table* t, mh_stream_t stream);
 void mh_dectable_destroy(mh_dectable* dt);
 /* Scratch for inputs up to max_input_bytes and payloads up to max_payload_bytes (either may be 0). */
 int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh_workspace** out);
@@ -110,11 +116,13 @@ int mh_gpu_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 
 /* Replaces the loop of i_coding_provider::decompress (src/coding.cpp:118-157) and the bit reader
  * (src/bitbuffer.cpp:75-140). d_bits: payload (no header byte), 4-byte aligned, n_bits payload bits starting at
- * bit 0 of d_bits[0]; bits past the payload read as zero (pop_rest pads, src/bitbuffer.cpp:129-140).
+ * bit (bit_base & 7) of d_bits[0] (0 for a whole stream; a byte-range shard passes the global bit offset of its
+ * first codeword, as in mh_gpu_encode); prev0 is the byte decoded just before. Bits past the payload read as
+ * zero (pop_rest pads, src/bitbuffer.cpp:129-140).
  * d_result is 4 x uint64: [0] = bytes decoded, [1] = 0 or a negative mh_status that stopped the write pass
  * (MH_ERR_CAPACITY, MH_ERR_NOT_CONVERGED), [2] = 0 or MH_ERR_CORRUPT_STREAM (bytes were still written, as the
  * reference would), [3] reserved. */
-int mh_gpu_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt,
+int mh_gpu_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt,
                   uint8_t* d_out, uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -67,18 +67,21 @@ _SIGNATURES = {
     "mh_table_context_empty": (_i, [_vp, _i]),
     "mh_table_code": (_i, [_vp, _i, _i, _vp, _pi]),
     "mh_table_max_code_bits": (_i, [_vp]),
+    "mh_table_code_lengths": (_i, [_vp, _vp, _sz]),
     "mh_table_lookup": (_i, [_vp, _i, _i, _pi, _pi, _pi]),
     "mh_table_debug_dump": (_i, [_vp, _vp, _sz, _psz]),
     "mh_table_destroy": (None, [_vp]),
     "mh_codebook_create": (_i, [_vp, _pp]),
+    "mh_codebook_update": (_i, [_vp, _vp, _vp]),
     "mh_codebook_destroy": (None, [_vp]),
     "mh_dectable_create": (_i, [_vp, _pp]),
+    "mh_dectable_update": (_i, [_vp, _vp, _vp]),
     "mh_dectable_destroy": (None, [_vp]),
     "mh_workspace_create": (_i, [_u64, _u64, _pp]),
     "mh_workspace_destroy": (None, [_vp]),
     "mh_gpu_histogram": (_i, [_vp, _u64, _u8, _i, _vp, _vp, _vp]),
     "mh_gpu_encode": (_i, [_vp, _u64, _u8, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
-    "mh_gpu_decode": (_i, [_vp, _u64, _u8, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "mh_gpu_decode": (_i, [_vp, _u64, _u64, _u8, _vp, _vp, _u64, _vp, _vp, _vp]),
     "mh_session_create": (_i, [_i, _u64, _pp]),
     "mh_session_destroy": (None, [_vp]),
     "mh_session_compress": (_i, [_vp, _vp, _u64, _i, _vp, _u64, _pu64, _pp]),
@@ -205,6 +208,14 @@ class CodingProvider:
     def max_code_bits(self):
         return _lib.mh_table_max_code_bits(self._h)
 
+    def code_lengths(self):
+        """numpy uint64 array of all code lengths: [65536] indexed 256*prev + c (order 1) or [256] (order 0)."""
+        import numpy as np
+        n = 65536 if self.get_type() else 256
+        lens = np.zeros(n, dtype=np.uint8)
+        _check(_lib.mh_table_code_lengths(self._h, lens.ctypes.data, n), "mh_table_code_lengths")
+        return lens.astype(np.uint64)
+
     def decoding_lookup(self, prev, window):
         """(kind, value, depth): kind 0 null, 1 leaf, 2 internal node at depth 8."""
         k, v, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -267,7 +278,8 @@ class Session:
     def compress_with_table(self, provider, data):
         import numpy as np
         keep, addr, n = _as_buffer(data)
-        cap = n + (n >> 3) + 4160
+        # a foreign table can expand the input: size for its longest codeword
+        cap = max(n + (n >> 3), (n * max(8, provider.max_code_bits()) + 7) // 8) + 4160
         buf = np.empty(cap, dtype=np.uint8)
         out_len, dropped = ctypes.c_uint64(0), ctypes.c_uint64(0)
         _check(_lib.mh_session_compress_with_table(self._h, provider._h, addr, n, buf.ctypes.data, buf.size, ctypes.byref(out_len), ctypes.byref(dropped)),
@@ -331,6 +343,9 @@ class Codebook:
         _check(_lib.mh_codebook_create(provider._h, ctypes.byref(out)), "mh_codebook_create")
         self._h = out
 
+    def update(self, provider, stream=0):
+        _check(_lib.mh_codebook_update(self._h, provider._h, stream or None), "mh_codebook_update")
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.mh_codebook_destroy(self._h)
@@ -344,6 +359,9 @@ class DecodeTable:
         out = ctypes.c_void_p()
         _check(_lib.mh_dectable_create(provider._h, ctypes.byref(out)), "mh_dectable_create")
         self._h = out
+
+    def update(self, provider, stream=0):
+        _check(_lib.mh_dectable_update(self._h, provider._h, stream or None), "mh_dectable_update")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -361,8 +379,8 @@ def gpu_encode(d_in, n, prev0, codebook, bit_base, d_out, out_capacity, d_result
     _check(_lib.mh_gpu_encode(d_in, n, prev0, codebook._h, bit_base, d_out, out_capacity, d_result, ws._h, stream or None), "mh_gpu_encode")
 
 
-def gpu_decode(d_bits, n_bits, prev0, dectable, d_out, out_capacity, d_result, ws, stream=0):
-    _check(_lib.mh_gpu_decode(d_bits, n_bits, prev0, dectable._h, d_out, out_capacity, d_result, ws._h, stream or None), "mh_gpu_decode")
+def gpu_decode(d_bits, bit_base, n_bits, prev0, dectable, d_out, out_capacity, d_result, ws, stream=0):
+    _check(_lib.mh_gpu_decode(d_bits, bit_base, n_bits, prev0, dectable._h, d_out, out_capacity, d_result, ws._h, stream or None), "mh_gpu_decode")
 
 
 def synth_markov(trans_counts_u32, seed, seg_bytes, first_seg, d_out, n, stream=0):

@@ -186,6 +186,15 @@ int mh_table_code(const mh_table* t, int prev, int c, uint8_t bits[32], int* len
 
 int mh_table_max_code_bits(const mh_table* t) { return t ? t->impl.max_code_bits() : MH_ERR_INVALID_ARG; }
 
+int mh_table_code_lengths(const mh_table* t, uint8_t* lens, size_t cap) {
+	if(!t || !lens) return MH_ERR_INVALID_ARG;
+	const size_t ntab = t->impl.trees.size();
+	if(cap < ntab * 256) return MH_ERR_CAPACITY;
+	for(size_t k = 0; k < ntab; ++k)
+		for(int c = 0; c < 256; ++c) lens[k * 256 + c] = uint8_t(t->impl.trees[k].code[c].length);
+	return MH_OK;
+}
+
 int mh_table_lookup(const mh_table* t, int prev, int window, int* kind, int* value, int* depth) {
 	if(!t || prev < 0 || prev > 255 || window < 0 || window > 255 || !kind || !value || !depth) return MH_ERR_INVALID_ARG;
 	const CodeTree& tr = t->impl.tree_for(prev);
@@ -211,45 +220,73 @@ void mh_table_destroy(mh_table* t) { delete t; }
 // ---------------------------------------------------------------------------------------------------------
 // device tables and scratch
 // ---------------------------------------------------------------------------------------------------------
-static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st, bool sync) {
-	std::vector<uint64_t> enc;
-	int rc = t->impl.flatten_codebook(enc);
-	if(rc != MH_OK) return rc;
+// Uploads are stream-ordered and never block the host: the flat image is built in a pinned buffer owned by the
+// handle; an event guards that buffer against being rewritten while a previous copy is still reading it.
+static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st) {
 	if(!cb->d_enc) MH_CUDA(cudaMalloc(&cb->d_enc, 65536 * sizeof(uint64_t)));
-	MH_CUDA(cudaMemcpyAsync(cb->d_enc, enc.data(), enc.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-	if(sync) MH_CUDA(cudaStreamSynchronize(st));   // pageable source: the copy has consumed `enc` once the stream drains
+	if(!cb->h_stage) MH_CUDA(cudaMallocHost(&cb->h_stage, 65536 * sizeof(uint64_t)));
+	if(!cb->uploaded) MH_CUDA(cudaEventCreateWithFlags(&cb->uploaded, cudaEventDisableTiming));
+	else MH_CUDA(cudaEventSynchronize(cb->uploaded));
+	int rc = t->impl.flatten_codebook(cb->h_stage);
+	if(rc != MH_OK) return rc;
+	MH_CUDA(cudaMemcpyAsync(cb->d_enc, cb->h_stage, t->impl.trees.size() * 256 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	MH_CUDA(cudaEventRecord(cb->uploaded, st));
 	cb->order = t->impl.order;
 	cb->max_bits = t->impl.max_code_bits();
 	return MH_OK;
 }
 
-static int upload_dectable(const mh_table* t, mh_dectable* dt, cudaStream_t st, bool sync) {
-	std::vector<uint16_t> lut;
-	std::vector<uint32_t> walk;
-	t->impl.flatten_dectable(lut, walk);
+static int upload_dectable(const mh_table* t, mh_dectable* dt, cudaStream_t st) {
 	if(!dt->d_lut) MH_CUDA(cudaMalloc(&dt->d_lut, 65536 * sizeof(uint16_t)));
 	if(!dt->d_walk) MH_CUDA(cudaMalloc(&dt->d_walk, 256 * 512 * sizeof(uint32_t)));
-	MH_CUDA(cudaMemcpyAsync(dt->d_lut, lut.data(), lut.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-	MH_CUDA(cudaMemcpyAsync(dt->d_walk, walk.data(), walk.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-	if(sync) MH_CUDA(cudaStreamSynchronize(st));
+	if(!dt->h_lut) MH_CUDA(cudaMallocHost(&dt->h_lut, 65536 * sizeof(uint16_t)));
+	if(!dt->h_walk) MH_CUDA(cudaMallocHost(&dt->h_walk, 256 * 512 * sizeof(uint32_t)));
+	if(!dt->uploaded) MH_CUDA(cudaEventCreateWithFlags(&dt->uploaded, cudaEventDisableTiming));
+	else MH_CUDA(cudaEventSynchronize(dt->uploaded));
+	t->impl.flatten_dectable(dt->h_lut, dt->h_walk);
+	const size_t ntab = t->impl.trees.size();
+	MH_CUDA(cudaMemcpyAsync(dt->d_lut, dt->h_lut, ntab * 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+	MH_CUDA(cudaMemcpyAsync(dt->d_walk, dt->h_walk, ntab * 512 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	MH_CUDA(cudaEventRecord(dt->uploaded, st));
 	dt->order = t->impl.order;
 	dt->max_bits = t->impl.max_code_bits();
 	return MH_OK;
+}
+
+static void release_book(mh_codebook* cb) {
+	if(cb->uploaded) { cudaEventSynchronize(cb->uploaded); cudaEventDestroy(cb->uploaded); }
+	if(cb->d_enc) cudaFree(cb->d_enc);
+	if(cb->h_stage) cudaFreeHost(cb->h_stage);
+	*cb = mh_codebook();
+}
+
+static void release_dec(mh_dectable* dt) {
+	if(dt->uploaded) { cudaEventSynchronize(dt->uploaded); cudaEventDestroy(dt->uploaded); }
+	if(dt->d_lut) cudaFree(dt->d_lut);
+	if(dt->d_walk) cudaFree(dt->d_walk);
+	if(dt->h_lut) cudaFreeHost(dt->h_lut);
+	if(dt->h_walk) cudaFreeHost(dt->h_walk);
+	*dt = mh_dectable();
 }
 
 int mh_codebook_create(const mh_table* t, mh_codebook** out) {
 	if(!t || !out) return MH_ERR_INVALID_ARG;
 	mh_codebook* cb = new(std::nothrow) mh_codebook;
 	if(!cb) return MH_ERR_INVALID_ARG;
-	int rc = upload_codebook(t, cb, nullptr, true);
+	int rc = upload_codebook(t, cb, nullptr);
 	if(rc != MH_OK) { mh_codebook_destroy(cb); return rc; }
 	*out = cb;
 	return MH_OK;
 }
 
+int mh_codebook_update(mh_codebook* cb, const mh_table* t, mh_stream_t stream) {
+	if(!cb || !t) return MH_ERR_INVALID_ARG;
+	return upload_codebook(t, cb, static_cast<cudaStream_t>(stream));
+}
+
 void mh_codebook_destroy(mh_codebook* cb) {
 	if(!cb) return;
-	if(cb->d_enc) cudaFree(cb->d_enc);
+	release_book(cb);
 	delete cb;
 }
 
@@ -257,16 +294,20 @@ int mh_dectable_create(const mh_table* t, mh_dectable** out) {
 	if(!t || !out) return MH_ERR_INVALID_ARG;
 	mh_dectable* dt = new(std::nothrow) mh_dectable;
 	if(!dt) return MH_ERR_INVALID_ARG;
-	int rc = upload_dectable(t, dt, nullptr, true);
+	int rc = upload_dectable(t, dt, nullptr);
 	if(rc != MH_OK) { mh_dectable_destroy(dt); return rc; }
 	*out = dt;
 	return MH_OK;
 }
 
+int mh_dectable_update(mh_dectable* dt, const mh_table* t, mh_stream_t stream) {
+	if(!dt || !t) return MH_ERR_INVALID_ARG;
+	return upload_dectable(t, dt, static_cast<cudaStream_t>(stream));
+}
+
 void mh_dectable_destroy(mh_dectable* dt) {
 	if(!dt) return;
-	if(dt->d_lut) cudaFree(dt->d_lut);
-	if(dt->d_walk) cudaFree(dt->d_walk);
+	release_dec(dt);
 	delete dt;
 }
 
@@ -321,9 +362,9 @@ int mh_gpu_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	                     static_cast<cudaStream_t>(stream));
 }
 
-int mh_gpu_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+int mh_gpu_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
                   uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream) {
-	return launch_decode(d_bits, n_bits, prev0, dt, d_out, out_capacity, reinterpret_cast<unsigned long long*>(d_result), ws,
+	return launch_decode(d_bits, bit_base, n_bits, prev0, dt, d_out, out_capacity, reinterpret_cast<unsigned long long*>(d_result), ws,
 	                     static_cast<cudaStream_t>(stream), 2);
 }
 
@@ -390,9 +431,8 @@ void mh_session_destroy(mh_session* s) {
 	if(s->d_result) cudaFree(s->d_result);
 	if(s->h_counts) cudaFreeHost(s->h_counts);
 	if(s->h_result) cudaFreeHost(s->h_result);
-	if(s->book.d_enc) cudaFree(s->book.d_enc);
-	if(s->dec.d_lut) cudaFree(s->dec.d_lut);
-	if(s->dec.d_walk) cudaFree(s->dec.d_walk);
+	release_book(&s->book);
+	release_dec(&s->dec);
 	mh_workspace_destroy(s->ws);
 	if(s->stream) cudaStreamDestroy(s->stream);
 	delete s;
@@ -416,7 +456,7 @@ int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order
 static int session_encode(mh_session* s, const mh_table* t, uint64_t n, uint8_t* out, uint64_t out_capacity,
                           uint64_t* out_len, uint64_t* dropped) {
 	if(out_capacity < 1) return MH_ERR_CAPACITY;
-	int rc = upload_codebook(t, &s->book, s->stream, true);
+	int rc = upload_codebook(t, &s->book, s->stream);
 	if(rc != MH_OK) return rc;
 	rc = launch_encode(s->d_raw, n, MH_PREV0, &s->book, 0, s->d_payload, s->payload_cap,
 	                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
@@ -480,13 +520,13 @@ int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* strea
 	const uint64_t n_bits = payload_bytes * 8 < remainder ? 0 : payload_bytes * 8 - remainder;
 	if(payload_bytes > s->payload_cap) return MH_ERR_CAPACITY;
 	MH_CUDA(cudaSetDevice(s->device));
-	int rc = upload_dectable(t, &s->dec, s->stream, true);
+	int rc = upload_dectable(t, &s->dec, s->stream);
 	if(rc != MH_OK) return rc;
 	if(payload_bytes) MH_CUDA(cudaMemcpyAsync(s->d_payload, stream + 1, payload_bytes, cudaMemcpyHostToDevice, s->stream));
 	const uint64_t dev_cap = s->max_input;
 	int iters = 2;
 	for(;;) {
-		rc = launch_decode(s->d_payload, n_bits, MH_PREV0, &s->dec, s->d_raw, dev_cap,
+		rc = launch_decode(s->d_payload, 0, n_bits, MH_PREV0, &s->dec, s->d_raw, dev_cap,
 		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
 		if(rc != MH_OK) return rc;
 		MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));

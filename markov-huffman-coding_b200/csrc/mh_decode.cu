@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t pack_state(uint32_t rel_bits, uint32_t ctx) 
 // ---------------------------------------------------------------------------------------------------------
 template <int ORDER>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
-    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t prev0, const uint16_t* __restrict__ lut_g,
+    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, uint32_t* __restrict__ state, uint32_t* __restrict__ count,
     uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks) {
 	extern __shared__ uint16_t lut_s[];
@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		int64_t k = my_sub;
 		if(active) {
 			pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
-			ctx = my_sub == 0 ? prev0 : uint32_t(' ');
+			ctx = ' ';
+			if(my_sub == 0) { pos = start0 >> 8; ctx = start0 & 255u; }   // the one exactly known state
 			cur.seek(origin + pos);
 			const uint32_t lim = limit_of(k);
 			decode_span<ORDER, false>(cur, tb, pos, lim, ctx, cnt, nullptr);
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long
 // ---------------------------------------------------------------------------------------------------------
 template <int ORDER>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
-    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t prev0, const uint16_t* __restrict__ lut_g,
+    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ state, const uint32_t* __restrict__ count,
     const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits, uint64_t n_subs,
     uint32_t n_chunks, unsigned long long* result) {
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 		for(uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
 		__syncthreads();
 		if(mine) {
-			const uint32_t start = k == 0 ? pack_state(0, prev0) : state[k - 1];
+			const uint32_t start = k == 0 ? start0 : state[k - 1];
 			const uint64_t origin = k * sub_bits;
 			uint64_t e = (k + 1) * sub_bits;
 			if(e > n_bits) e = n_bits;
@@ -379,7 +380,7 @@ uint32_t decode_sub_bits(int order) {
 namespace {
 
 template <int ORDER>
-int run_decode(const uint32_t* words, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh_dectable* dt, uint8_t* d_out,
                uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
 	const uint32_t sub_bits = decode_sub_bits(ORDER);
 	const uint64_t n_subs = (n_bits + sub_bits - 1) / sub_bits;
@@ -398,7 +399,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint8_t prev0, const mh_d
 	MH_CUDA(cudaMemsetAsync(ws->dec_flags, 0, 8 * sizeof(uint32_t), st));
 	{
 		ProfScope p("dec_sync_kernel", st);
-		dec_sync_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, prev0, dt->d_lut, dt->d_walk, ws->dec_state,
+		dec_sync_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, start0, dt->d_lut, dt->d_walk, ws->dec_state,
 		    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks);
 	}
 	count_launch(1);
@@ -425,7 +426,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint8_t prev0, const mh_d
 	}
 	{
 		ProfScope p("dec_write_kernel", st);
-		dec_write_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, prev0, dt->d_lut, dt->d_walk, ws->dec_state,
+		dec_write_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, start0, dt->d_lut, dt->d_walk, ws->dec_state,
 		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, d_result);
 	}
 	count_launch(3);
@@ -435,7 +436,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint8_t prev0, const mh_d
 
 }  // namespace
 
-int launch_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
                   uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
 	if(!dt || !dt->d_lut || !d_result || (!d_bits && n_bits)) return MH_ERR_INVALID_ARG;
 	if(reinterpret_cast<uint64_t>(d_bits) & 3) return MH_ERR_INVALID_ARG;
@@ -443,8 +444,13 @@ int launch_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const m
 	MH_CUDA(cudaMemsetAsync(d_result, 0, 4 * sizeof(unsigned long long), st));
 	if(n_bits == 0) return MH_OK;
 	const uint32_t* words = reinterpret_cast<const uint32_t*>(d_bits);
-	if(dt->order) return run_decode<1>(words, n_bits, prev0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
-	return run_decode<0>(words, n_bits, prev0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	// the payload starts at bit (bit_base & 7) of d_bits[0]: the kernels see a stream that ends at bit0 + n_bits and
+	// whose first subsequence starts, exactly known, at (bit0, prev0)
+	const uint32_t bit0 = uint32_t(bit_base & 7);
+	const uint32_t start0 = (bit0 << 8) | prev0;
+	const uint64_t end_bit = n_bits + bit0;
+	if(dt->order) return run_decode<1>(words, end_bit, start0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	return run_decode<0>(words, end_bit, start0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
 }
 
 }  // namespace mh

@@ -321,8 +321,8 @@ int CodingTable::max_code_bits() const {
 	return m;
 }
 
-int CodingTable::flatten_codebook(std::vector<uint64_t>& enc) const {
-	enc.assign(trees.size() * 256, 0);
+int CodingTable::flatten_codebook(uint64_t* enc) const {
+	std::fill(enc, enc + trees.size() * 256, uint64_t(0));
 	for(size_t t = 0; t < trees.size(); ++t)
 		for(int c = 0; c < 256; ++c) {
 			const Codeword& cw = trees[t].code[c];
@@ -335,9 +335,9 @@ int CodingTable::flatten_codebook(std::vector<uint64_t>& enc) const {
 	return MH_OK;
 }
 
-void CodingTable::flatten_dectable(std::vector<uint16_t>& lut, std::vector<uint32_t>& walk) const {
-	lut.assign(trees.size() * 256, uint16_t(kLutNull | (1u << 8) | ' '));
-	walk.assign(trees.size() * 512, 0);
+void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
+	std::fill(lut, lut + trees.size() * 256, uint16_t(kLutNull | (1u << 8) | ' '));
+	std::fill(walk, walk + trees.size() * 512, uint32_t(0));
 	for(size_t t = 0; t < trees.size(); ++t) {
 		const CodeTree& tr = trees[t];
 		if(tr.empty()) continue;

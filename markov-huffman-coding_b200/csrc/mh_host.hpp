@@ -73,12 +73,12 @@ public:
 
 	// ---- flat device images -------------------------------------------------------------------------
 	// enc[ctx*256 + c] = (len << 56) | code (right-aligned); returns MH_ERR_CODE_TOO_LONG if any len > 56
-	int flatten_codebook(std::vector<uint64_t>& enc) const;
+	int flatten_codebook(uint64_t* enc /* [trees.size() * 256] */) const;
 	// lut[ctx*256 + w]: leaf   : 0x0000 | len << 8 | symbol           (len 1..8)
 	//                  deep   : 0x8000 | node index within the context (internal node at depth 8)
 	//                  null   : 0x4000 | 1 << 8 | ' '                  (speculation-safe; an error if verified)
 	// walk[ctx*512 + node] = left << 16 | right, child = 0x8000|symbol for a leaf, else node index
-	void flatten_dectable(std::vector<uint16_t>& lut, std::vector<uint32_t>& walk) const;
+	void flatten_dectable(uint16_t* lut /* [trees.size() * 256] */, uint32_t* walk /* [trees.size() * 512] */) const;
 };
 
 constexpr uint16_t kLutDeep = 0x8000;

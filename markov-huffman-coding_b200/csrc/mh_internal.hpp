@@ -71,14 +71,19 @@ struct mh_workspace {
 };
 
 struct mh_codebook {
-	uint64_t* d_enc = nullptr;   // [ntab * 256] len << 56 | code
+	uint64_t* d_enc = nullptr;     // [ntab * 256] len << 56 | code
+	uint64_t* h_stage = nullptr;   // pinned image the async upload reads from
+	cudaEvent_t uploaded = nullptr;
 	int order = 1;
 	int max_bits = 0;
 };
 
 struct mh_dectable {
-	uint16_t* d_lut = nullptr;   // [ntab * 256]
-	uint32_t* d_walk = nullptr;  // [ntab * 512]
+	uint16_t* d_lut = nullptr;     // [ntab * 256]
+	uint32_t* d_walk = nullptr;    // [ntab * 512]
+	uint16_t* h_lut = nullptr;     // pinned
+	uint32_t* h_walk = nullptr;    // pinned
+	cudaEvent_t uploaded = nullptr;
 	int order = 1;
 	int max_bits = 0;
 };
@@ -89,7 +94,7 @@ int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, 
                      mh_workspace* ws, cudaStream_t st);
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
                   uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st);
-int launch_decode(const uint8_t* d_bits, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
+int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
                   uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
 uint32_t decode_sub_bits(int order);                 // subsequence size in bits used for this coder type
 uint64_t encode_tiles_for(uint64_t n);               // worst-case tile count for n input bytes
