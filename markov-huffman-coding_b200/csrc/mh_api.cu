@@ -230,9 +230,18 @@ static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st) 
 	int rc = t->impl.flatten_codebook(cb->h_stage);
 	if(rc != MH_OK) return rc;
 	MH_CUDA(cudaMemcpyAsync(cb->d_enc, cb->h_stage, t->impl.trees.size() * 256 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-	MH_CUDA(cudaEventRecord(cb->uploaded, st));
 	cb->order = t->impl.order;
 	cb->max_bits = t->impl.max_code_bits();
+	cb->has_box = cb->max_bits <= kEncBoxMaxBits;
+	if(cb->has_box) {
+		if(!cb->d_box) MH_CUDA(cudaMalloc(&cb->d_box, 257 * 257 * sizeof(uint32_t)));
+		if(!cb->h_box) MH_CUDA(cudaMallocHost(&cb->h_box, 257 * 257 * sizeof(uint32_t)));
+		t->impl.live_range(cb->box_lo, cb->box_r);
+		t->impl.flatten_box(cb->box_lo, cb->box_r, cb->h_box);
+		const size_t entries = cb->order ? size_t(cb->box_r + 1) * (cb->box_r + 1) : 256;
+		MH_CUDA(cudaMemcpyAsync(cb->d_box, cb->h_box, entries * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	}
+	MH_CUDA(cudaEventRecord(cb->uploaded, st));
 	return MH_OK;
 }
 
@@ -257,6 +266,8 @@ static void release_book(mh_codebook* cb) {
 	if(cb->uploaded) { cudaEventSynchronize(cb->uploaded); cudaEventDestroy(cb->uploaded); }
 	if(cb->d_enc) cudaFree(cb->d_enc);
 	if(cb->h_stage) cudaFreeHost(cb->h_stage);
+	if(cb->d_box) cudaFree(cb->d_box);
+	if(cb->h_box) cudaFreeHost(cb->h_box);
 	*cb = mh_codebook();
 }
 
@@ -322,9 +333,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 	WS_CUDA(cudaMemset(ws->counters, 0, 16 * sizeof(uint32_t)));
 	WS_CUDA(cudaMemset(ws->hist_params, 0, 8 * sizeof(uint32_t)));
 	ws->enc_tiles_cap = encode_tiles_for(max_input_bytes) + 1;
-	WS_CUDA(cudaMalloc(&ws->enc_desc, ws->enc_tiles_cap * sizeof(uint64_t)));
-	WS_CUDA(cudaMalloc(&ws->enc_tail_agg, ws->enc_tiles_cap * sizeof(uint32_t)));
-	WS_CUDA(cudaMalloc(&ws->enc_tail_inc, ws->enc_tiles_cap * sizeof(uint32_t)));
+	WS_CUDA(cudaMalloc(&ws->enc_desc, 2 * ws->enc_tiles_cap * sizeof(uint64_t)));
 	const uint64_t min_sub = decode_sub_bits(0) < decode_sub_bits(1) ? decode_sub_bits(0) : decode_sub_bits(1);
 	ws->dec_subs_cap = (max_payload_bytes * 8 + min_sub - 1) / min_sub + 1;
 	ws->dec_chunks_cap = ws->dec_subs_cap / (kDecThreads - kDecWarmSubs) + 2;
@@ -341,7 +350,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 
 void mh_workspace_destroy(mh_workspace* ws) {
 	if(!ws) return;
-	void* ptrs[] = {ws->enc_desc, ws->enc_tail_agg, ws->enc_tail_inc, ws->counters, ws->hist_params, ws->dec_state,
+	void* ptrs[] = {ws->enc_desc, ws->counters, ws->hist_params, ws->dec_state,
 	                ws->dec_count, ws->dec_seam, ws->dec_chunk_total, ws->dec_chunk_base, ws->dec_flags};
 	for(void* p : ptrs)
 		if(p) cudaFree(p);

@@ -335,6 +335,36 @@ int CodingTable::flatten_codebook(uint64_t* enc) const {
 	return MH_OK;
 }
 
+void CodingTable::live_range(uint32_t& lo, uint32_t& r) const {
+	int first = 256, last = -1;
+	auto touch = [&](int s) { first = std::min(first, s); last = std::max(last, s); };
+	for(size_t t = 0; t < trees.size(); ++t) {
+		if(order && !trees[t].empty()) touch(int(t));
+		for(int c = 0; c < 256; ++c)
+			if(trees[t].code[c].length) touch(c);
+	}
+	if(last < 0) { lo = 0; r = 1; return; }
+	lo = uint32_t(first);
+	r = uint32_t(last - first + 1);
+}
+
+void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
+	auto entry = [](const Codeword& cw) -> uint32_t {
+		if(cw.length == 0) return 0u;
+		uint32_t v = 0;
+		for(int i = 0; i < cw.length; ++i) v = (v << 1) | uint32_t(cw.bit(i));
+		return (v << (32 - cw.length)) | uint32_t(cw.length);
+	};
+	if(!order) {
+		for(int c = 0; c < 256; ++c) box[c] = entry(trees[0].code[c]);
+		return;
+	}
+	const uint32_t pitch = r + 1;
+	std::fill(box, box + size_t(pitch) * pitch, 0u);
+	for(uint32_t p = 0; p < r; ++p)
+		for(uint32_t c = 0; c < r; ++c) box[p * pitch + c] = entry(trees[lo + p].code[lo + c]);
+}
+
 void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
 	std::fill(lut, lut + trees.size() * 256, uint16_t(kLutNull | (1u << 8) | ' '));
 	std::fill(walk, walk + trees.size() * 512, uint32_t(0));

@@ -74,6 +74,12 @@ public:
 	// ---- flat device images -------------------------------------------------------------------------
 	// enc[ctx*256 + c] = (len << 56) | code (right-aligned); returns MH_ERR_CODE_TOO_LONG if any len > 56
 	int flatten_codebook(uint64_t* enc /* [trees.size() * 256] */) const;
+	// Smallest byte range [lo, lo + r) holding every symbol that has a codeword and every non-empty context.
+	void live_range(uint32_t& lo, uint32_t& r) const;
+	// box[(prev - lo) * (r + 1) + (c - lo)] (order 1) or box[c] (order 0) = code << (32 - len) | len; needs max bits
+	// <= 27. Row r and column r are a zero border that out-of-range bytes are clamped onto.
+	// `box` must hold (r + 1) * (r + 1) (order 1) or 256 (order 0) entries.
+	void flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const;
 	// lut[ctx*256 + w]: leaf   : 0x0000 | len << 8 | symbol           (len 1..8)
 	//                  deep   : 0x8000 | node index within the context (internal node at depth 8)
 	//                  null   : 0x4000 | 1 << 8 | ' '                  (speculation-safe; an error if verified)

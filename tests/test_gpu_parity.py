@@ -167,3 +167,14 @@ def test_single_symbol_contexts(session):
             stream, provider = session.compress(data, order)
             assert stream == o.compress_from_input(data, bool(order))[0]
             assert session.decompress(provider, stream) == data
+
+
+@pytest.mark.parametrize("fmt", ["1", "2"])
+def test_encoder_table_formats_agree(session, ipsum_counts, fmt, monkeypatch):
+    """The encoder picks a table format from the codebook (u32 box in shared memory / u32 box in global memory /
+    u64 wide entries). Force the two fallbacks on data that would normally take the first."""
+    data = o.synth_markov(ipsum_counts, 5, 65536, 0, (3 << 20) + 77)
+    want = {order: o.compress_from_input(data, bool(order))[0] for order in (0, 1)}
+    monkeypatch.setenv("MH_ENC_FMT", fmt)
+    for order in (0, 1):
+        assert session.compress(data, order)[0] == want[order]
