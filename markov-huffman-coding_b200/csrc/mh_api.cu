@@ -333,7 +333,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 	WS_CUDA(cudaMemset(ws->counters, 0, 16 * sizeof(uint32_t)));
 	WS_CUDA(cudaMemset(ws->hist_params, 0, 8 * sizeof(uint32_t)));
 	ws->enc_tiles_cap = encode_tiles_for(max_input_bytes) + 1;
-	WS_CUDA(cudaMalloc(&ws->enc_desc, 2 * ws->enc_tiles_cap * sizeof(uint64_t)));
+	WS_CUDA(cudaMalloc(&ws->enc_desc, ws->enc_tiles_cap * (2 * sizeof(uint64_t) + sizeof(uint32_t))));
 	const uint64_t min_sub = decode_sub_bits(0) < decode_sub_bits(1) ? decode_sub_bits(0) : decode_sub_bits(1);
 	ws->dec_subs_cap = (max_payload_bytes * 8 + min_sub - 1) / min_sub + 1;
 	ws->dec_chunks_cap = ws->dec_subs_cap / (kDecThreads - kDecWarmSubs) + 2;

@@ -4,20 +4,24 @@
 // bitbuffer::push_encoding_descriptor / push_byte / flush (src/bitbuffer.cpp:21-73, :170-180): for every input
 // byte c with predecessor prev, append codeword[prev][c] MSB-first to one contiguous bit stream.
 //
-// Shape of the kernel. Persistent CTAs (a multiple of the SM count) pull tiles of ROUNDS x 4 KiB of
-// input from an atomic ticket, so a tile only ever waits on tiles that are already running.
-//   0. once per CTA the codebook is staged in shared memory: u32 entries (27-bit left-aligned code | 5-bit length)
-//      for the RxR box of byte values the table actually uses (text: R ~ 113 -> 50 KiB). Tables whose box does not
-//      fit, or whose codewords exceed 27 bits, are gathered from global memory (L1/L2) instead;
-//   1. per round, each thread takes 16 consecutive bytes with one coalesced 128-bit load (the byte before them
-//      comes from the neighbouring lane by shuffle), looks up its 16 entries and sums their lengths;
-//   2. a block-wide exclusive scan of the per-thread bit counts gives every thread its bit offset in the tile;
-//   3. each thread funnels its codewords through a 64-bit window and ORs whole 32-bit words into a zeroed
-//      shared-memory staging area (neighbouring threads share their boundary words, hence the OR);
-//   4. warp 0 publishes the tile's (bit count, last 31 bits) in ONE 64-bit word and resolves the tile's global bit
-//      offset by a warp-wide decoupled look-back (32 predecessors per poll, relaxed loads that bypass L1). The tile
-//      that ends a partially filled 32-bit output word writes it, using the predecessor's published tail bits — so
-//      every output word has exactly one writer: no pre-zeroed output, no global atomics, no second pass;
+// Shape of the kernel. Persistent CTAs (a multiple of the SM count) pull tiles of 512 x SPT input
+// bytes (SPT = 32 or 16 symbols per thread) from an atomic ticket, so a tile only ever waits on tiles that are
+// already running.
+//   0. once per CTA the codebook is staged in shared memory: u32 entries (5-bit length | 27-bit code) for the
+//      RxR box of byte values the table actually uses (text: R ~ 113 -> 51 KiB), with a zero border that bytes
+//      outside the box are clamped onto. Tables whose box does not fit, or whose codewords exceed 27 bits, are
+//      gathered from global memory (L1/L2) instead;
+//   1. each thread takes SPT consecutive bytes with coalesced 128-bit loads (the byte before them comes from the
+//      neighbouring lane by shuffle), looks up its entries and sums their lengths;
+//   2. a block-wide exclusive scan of the per-thread bit counts gives every thread its bit offset in the tile; the
+//      tile's bit count is PUBLISHED RIGHT AWAY, so successors can resolve their offsets while this tile packs;
+//   3. codewords are merged pairwise, then by fours, in registers (a quad is one <= 64-bit unit; the rare longer
+//      quad goes out as two pairs) and funnelled through a 96-bit window; only completed 32-bit words are ORed
+//      into the zeroed shared-memory staging area (neighbouring threads share their boundary words, hence the OR);
+//   4. warp 0 publishes the tile's last 31 bits and resolves the tile's global bit offset by a warp-wide
+//      decoupled look-back (128 predecessors per poll, relaxed loads that bypass L1). The tile that ends a
+//      partially filled 32-bit output word writes it, using the predecessor's published tail bits — so every
+//      output word has exactly one writer: no pre-zeroed output, no global atomics, no second pass;
 //   5. the staged bits are funnel-shifted by the tile's global bit phase and written with coalesced 32-bit
 //      stores, byte-swapped so that stream bit p lands in byte p/8, bit 7 - p%8 (src/bitbuffer.cpp:12); the words
 //      just copied are re-zeroed for the next tile.
@@ -31,9 +35,10 @@ constexpr int FMT_BOX_SMEM = 0;     // u32 box table in shared memory
 constexpr int FMT_BOX_GLOBAL = 1;   // u32 box table gathered from global memory
 constexpr int FMT_WIDE = 2;         // u64 entries (8-bit length | 56-bit code) gathered from global memory
 
-constexpr uint64_t kAgg = 1ull << 62;   // aggregate word : kAgg | tail31 << 31 | bits31   (this tile only)
-constexpr uint64_t kInc = 2ull << 62;   // inclusive word : kInc | bits62                   (all tiles up to this one)
+constexpr uint64_t kAgg = 1ull << 62;   // aggregate word : kAgg | bits of this tile
+constexpr uint64_t kInc = 2ull << 62;   // inclusive word : kInc | bits of all tiles up to and including this one
 constexpr uint64_t kLow31 = 0x7fffffffull;
+constexpr uint32_t kTailValid = 0x80000000u;   // tail word: kTailValid | last min(bits, 31) bits of this tile
 
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
 	unsigned long long v;
@@ -42,6 +47,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
 }
 __device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
 	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed32(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_relaxed32(uint32_t* p, uint32_t v) {
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
 	uint4 r;
@@ -62,16 +75,36 @@ __device__ __forceinline__ uint32_t stage_bits(const uint32_t* stage, uint32_t p
 	return uint32_t((two << off) >> (64 - count));
 }
 
-// Warp-wide decoupled look-back over a window of kWin x 32 predecessors per poll. All 32 lanes of warp 0 call
-// this. Returns, on every lane, the number of bits that precede this tile and the last min(that, 31) of them.
+struct EncArgs {
+	const uint8_t* in;
+	uint64_t n;
+	uint32_t prev0;
+	int order;
+	const unsigned long long* wide;   // FMT_WIDE table: len << 56 | code
+	const uint32_t* box;              // u32 box table with a zero border: (R + 1) x (R + 1), or 256 entries (order 0)
+	uint32_t box_lo, box_r;
+	uint32_t bit0;
+	uint32_t stage_words;
+	uint32_t* out_words;
+	uint64_t out_capacity_words;
+	unsigned long long* agg;
+	unsigned long long* inc;
+	uint32_t* tail;
+	uint32_t* ticket;
+	unsigned long long* result;
+	uint32_t n_tiles;
+};
+
+// Warp-wide decoupled look-back over a window of kWin x 32 predecessors per poll. All 32 lanes of warp 0 call this.
+// Returns, on every lane, the number of bits that precede this tile and the bit count of tile - 1; publishes the
+// tile's inclusive prefix.
 constexpr int kWin = 4;
 
-__device__ __forceinline__ void look_back(uint32_t tile, uint32_t own_bits, uint32_t own_tail, unsigned long long* agg,
-                                          unsigned long long* inc, unsigned long long& excl_bits, uint32_t& excl_tail) {
+__device__ __forceinline__ void look_back(uint32_t tile, uint32_t own_bits, const EncArgs& A, unsigned long long& excl_bits,
+                                          uint32_t& nearest_bits) {
 	const uint32_t lane = threadIdx.x & 31;
-	if(lane == 0) st_relaxed(agg + tile, kAgg | (uint64_t(own_tail) << 31) | own_bits);
 	unsigned long long sum = 0;
-	unsigned long long nearest = kAgg;   // aggregate word of tile - 1 (an empty tile if there is none)
+	unsigned long long nearest = 0;
 	bool first_window = true;
 	long long base = (long long) tile - 1;
 	while(base >= 0) {
@@ -80,7 +113,7 @@ __device__ __forceinline__ void look_back(uint32_t tile, uint32_t own_bits, uint
 		for(int k = 0; k < kWin; ++k) {
 			const long long j = base - (k * 32 + int(lane));
 			a[k] = kAgg; p[k] = kInc;   // tiles before the stream: inclusive, zero bits
-			if(j >= 0) { p[k] = ld_relaxed(inc + j); a[k] = ld_relaxed(agg + j); }
+			if(j >= 0) { p[k] = ld_relaxed(A.inc + j); a[k] = ld_relaxed(A.agg + j); }
 		}
 		int stop = -1;        // window index of the nearest predecessor with an inclusive prefix
 		bool ready = true;    // every aggregate nearer than `stop` is visible
@@ -91,17 +124,17 @@ __device__ __forceinline__ void look_back(uint32_t tile, uint32_t own_bits, uint
 			if(stop < 0) {
 				unsigned need = 0xffffffffu;
 				if(has_inc) { const int l = __ffs(has_inc) - 1; stop = k * 32 + l; need = (1u << l) - 1u; }
-				if(k == 0 && first_window) need |= 1u;   // the tail always comes from tile - 1's aggregate word
+				if(k == 0 && first_window) need |= 1u;   // tile - 1's own bit count is needed for the seam word
 				if((has_agg & need) != need) ready = false;
 			}
 		}
 		if(!ready) continue;   // a predecessor has not published yet: poll again
-		if(first_window) { nearest = __shfl_sync(0xffffffffu, a[0], 0); first_window = false; }
+		if(first_window) { nearest = __shfl_sync(0xffffffffu, a[0], 0) & kDescValueMask; first_window = false; }
 		unsigned long long v = 0;
 #pragma unroll
 		for(int k = 0; k < kWin; ++k) {
 			const int idx = k * 32 + int(lane);
-			if(stop < 0 || idx < stop) v += a[k] & kLow31;
+			if(stop < 0 || idx < stop) v += a[k] & kDescValueMask;
 			else if(idx == stop) v += p[k] & kDescValueMask;
 		}
 		sum += warp_sum(v);
@@ -109,89 +142,97 @@ __device__ __forceinline__ void look_back(uint32_t tile, uint32_t own_bits, uint
 		base -= kWin * 32;
 	}
 	excl_bits = sum;
-	uint32_t t_bits = uint32_t(nearest & kLow31), t_tail = uint32_t((nearest >> 31) & kLow31);
-	if(t_bits < 31 && tile > 1) {
-		// Rare (a predecessor produced fewer than 31 bits, e.g. dropped symbols): gather the tail serially.
-		if(lane == 0) {
-			for(long long j = (long long) tile - 2; j >= 0 && t_bits < 31; --j) {
-				unsigned long long w;
-				do { w = ld_relaxed(agg + j); } while((w >> 62) != 1);
-				const uint32_t b = uint32_t(w & kLow31), tl = uint32_t((w >> 31) & kLow31);
-				// concatenate (b, tl) in front of (t_bits, t_tail), keep the last 31 bits
-				t_tail = uint32_t(((uint64_t(tl) << t_bits) | t_tail) & kLow31);
-				t_bits = b + t_bits > 31 ? 31 : b + t_bits;
-			}
-		}
-		t_tail = __shfl_sync(0xffffffffu, t_tail, 0);
-	}
-	excl_tail = t_tail;
-	if(lane == 0) st_relaxed(inc + tile, kInc | (sum + own_bits));
+	nearest_bits = nearest > 31 ? 31u : uint32_t(nearest);
+	if(lane == 0) st_relaxed(A.inc + tile, kInc | (sum + own_bits));
 }
 
-struct EncArgs {
-	const uint8_t* in;
-	uint64_t n;
-	uint32_t prev0;
-	int order;
-	const unsigned long long* wide;   // FMT_WIDE table
-	const uint32_t* box;              // u32 box table with a zero border: (R + 1) x (R + 1), or 256 entries (order 0)
-	uint32_t box_lo, box_r;
-	uint32_t bit0;
-	uint32_t stage_words;
-	uint32_t* out_words;
-	uint64_t out_capacity_words;
-	unsigned long long* agg;
-	unsigned long long* inc;
-	uint32_t* ticket;
-	unsigned long long* result;
-	uint32_t n_tiles;
+// The last min(bits before this tile, 31) bits of the stream before this tile. Lane 0 of warp 0 only.
+__device__ __forceinline__ uint32_t predecessor_tail(uint32_t tile, uint32_t nearest_bits, const EncArgs& A) {
+	if(tile == 0) return 0;
+	uint32_t tv;
+	do { tv = ld_relaxed32(A.tail + tile - 1); } while(!(tv & kTailValid));
+	uint32_t t_tail = tv & uint32_t(kLow31), t_bits = nearest_bits;
+	// Rare (a predecessor produced fewer than 31 bits, e.g. dropped symbols): keep prepending older tiles.
+	for(long long j = (long long) tile - 2; j >= 0 && t_bits < 31; --j) {
+		unsigned long long a;
+		do { a = ld_relaxed(A.agg + j); } while((a >> 62) != 1);
+		do { tv = ld_relaxed32(A.tail + j); } while(!(tv & kTailValid));
+		const unsigned long long b = a & kDescValueMask;
+		t_tail = uint32_t(((uint64_t(tv & uint32_t(kLow31)) << t_bits) | t_tail) & kLow31);
+		t_bits = b + t_bits > 31 ? 31u : uint32_t(b) + t_bits;
+	}
+	return t_tail;
+}
+
+// Block-wide exclusive scan (one value per thread). One barrier; `total` is the block sum.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+	constexpr int NW = kEncThreads / 32;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = v;
+#pragma unroll
+	for(int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+		if(lane >= uint32_t(d)) incl += t;
+	}
+	if(lane == 31) warp_sums[warp] = incl;
+	__syncthreads();
+	const uint32_t ws = lane < NW ? warp_sums[lane] : 0u;   // every warp scans the warp totals itself
+	uint32_t wincl = ws;
+#pragma unroll
+	for(int d = 1; d < NW; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, d);
+		if(lane >= uint32_t(d)) wincl += t;
+	}
+	total = __shfl_sync(0xffffffffu, wincl, NW - 1);
+	const uint32_t before = __shfl_sync(0xffffffffu, wincl - ws, warp);
+	return before + incl - v;
+}
+
+// A thread's bit window: `fill` (< 32) pending bits left-aligned in `hi`; completed words are ORed into the stage.
+struct Packer {
+	uint32_t* word;
+	uint32_t hi, fill;
+	__device__ __forceinline__ void start(uint32_t* stage, uint32_t pos) { word = stage + (pos >> 5); hi = 0; fill = pos & 31; }
+	// append a right-aligned unit of len <= 64 bits
+	__device__ __forceinline__ void put(unsigned long long v, uint32_t len) {
+		const unsigned long long q = len ? v << (64 - len) : 0ull;
+		const uint32_t qh = uint32_t(q >> 32), ql = uint32_t(q);
+		const uint32_t w0 = hi | (qh >> fill);
+		const uint32_t w1 = __funnelshift_r(ql, qh, fill);
+		const uint32_t w2 = __funnelshift_r(0u, ql, fill);   // ql << (32 - fill), 0 when fill == 0
+		const uint32_t nf = fill + len;                      // < 96
+		const uint32_t full = nf >> 5;                       // 0, 1 or 2 words completed
+		if(full >= 1) atomicOr(word, w0);
+		if(full == 2) atomicOr(word + 1, w1);
+		word += full;
+		hi = full == 0 ? w0 : (full == 1 ? w1 : w2);
+		fill = nf & 31;
+	}
+	__device__ __forceinline__ void finish() {
+		if(fill) atomicOr(word, hi);
+	}
 };
 
-// One thread's 16 bytes -> 16 u32 entries (code left-aligned in [31:5], length in [4:0]). Returns the bit count;
-// `floor` tracks the smallest entry seen (0 = some symbol had no codeword).
-template <int FMT, bool FULL>
-__device__ __forceinline__ uint32_t gather_box(const EncArgs& A, const uint32_t* table, const uint32_t (&w)[4], int live,
-                                               uint32_t prev, uint32_t (&e)[16], uint32_t& floor) {
-	const uint32_t R = A.box_r, lo = A.box_lo, pitch = R + 1;
-	uint32_t bits = 0;
-	uint32_t row = A.order ? min(prev - lo, R) * pitch : 0u;
-#pragma unroll
-	for(int i = 0; i < 16; ++i) {
-		const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
-		uint32_t ent = 0;
-		if(FULL || i < live) {
-			if(A.order) {
-				const uint32_t uc = min(c - lo, R);   // bytes outside the box land on the zero border
-				ent = FMT == FMT_BOX_SMEM ? table[row + uc] : __ldg(A.box + row + uc);
-				row = uc * pitch;
-			} else {
-				ent = FMT == FMT_BOX_SMEM ? table[c] : __ldg(A.box + c);
-			}
-			floor = min(floor, ent);
-		}
-		e[i] = ent;
-		bits += ent & 31u;
-	}
-	return bits;
-}
-
-template <int ROUNDS, int FMT, bool ALIGNED>
+template <int SPT, int FMT, bool ALIGNED>
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
+	constexpr int NWORDS = SPT / 4;
 	extern __shared__ uint32_t smem[];
-	uint32_t* stage = smem;                          // [stage_words + 4]
-	uint32_t* table = smem + A.stage_words + 4;      // FMT_BOX_SMEM: [(R + 1)^2] or [256]
+	uint32_t* table = smem;   // FMT_BOX_SMEM: [(R + 1)^2] or [256]
 	__shared__ uint32_t warp_sums[kEncThreads / 32];
 	__shared__ uint32_t s_tile[2];
 	__shared__ unsigned long long s_prefix_bits;
 	__shared__ uint32_t s_prefix_tail;
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	for(uint32_t i = tid; i < A.stage_words + 4; i += kEncThreads) stage[i] = 0;
+	uint32_t table_entries = 0;
 	if(FMT == FMT_BOX_SMEM) {
-		const uint32_t entries = A.order ? (A.box_r + 1) * (A.box_r + 1) : 256u;
-		for(uint32_t i = tid; i < entries; i += kEncThreads) table[i] = __ldg(A.box + i);
+		table_entries = A.order ? (A.box_r + 1) * (A.box_r + 1) : 256u;
+		for(uint32_t i = tid; i < table_entries; i += kEncThreads) table[i] = __ldg(A.box + i);
 	}
+	uint32_t* stage = smem + ((table_entries + 3) & ~3u);   // [stage_words + 4]
+	for(uint32_t i = tid; i < A.stage_words + 4; i += kEncThreads) stage[i] = 0;
 	if(tid == 0) s_tile[0] = atomicAdd(A.ticket, 1u);
+	const uint32_t R = A.box_r, lo = A.box_lo, pitch = R + 1;
 	uint32_t dropped = 0;
 
 	for(uint32_t it = 0;; ++it) {
@@ -199,140 +240,114 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 		const uint32_t tile = s_tile[it & 1];
 		if(tile >= A.n_tiles) break;
 		if(tid == 0) s_tile[(it + 1) & 1] = atomicAdd(A.ticket, 1u);   // next ticket, off the critical path
-		const uint64_t tile_base = uint64_t(tile) * (ROUNDS * kEncRoundBytes);
-		uint32_t tile_bits = 0;   // running bit count of the tile (uniform across the block)
-#pragma unroll 1
-		for(int r = 0; r < ROUNDS; ++r) {
-			const uint64_t round_base = tile_base + uint64_t(r) * kEncRoundBytes;
-			if(round_base >= A.n) break;   // uniform
-			const uint64_t my = round_base + tid * 16;
-			// ---- 1. my 16 bytes + the byte before them ----
-			uint32_t w[4] = {0, 0, 0, 0};
-			int live = 0;
-			if(my < A.n) {
-				live = A.n - my >= 16 ? 16 : int(A.n - my);
-				if(ALIGNED && live == 16) {
-					const uint4 v = ld_stream_128(A.in + my);
-					w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-				} else {
-#pragma unroll
-					for(int i = 0; i < 16; ++i)
-						if(i < live) w[i >> 2] |= uint32_t(A.in[my + i]) << (8 * (i & 3));
-				}
-			}
-			uint32_t prev = __shfl_up_sync(0xffffffffu, w[3] >> 24, 1);
-			if(lane == 0 && my < A.n) prev = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
+		const uint64_t my = uint64_t(tile) * (kEncThreads * SPT) + uint64_t(tid) * SPT;
 
-			uint32_t my_bits = 0;
-			if(FMT != FMT_WIDE) {
-				uint32_t e[16];
-				uint32_t floor = 0xffffffffu;
-				if(live == 16) my_bits = gather_box<FMT, true>(A, table, w, live, prev, e, floor);
-				else my_bits = gather_box<FMT, false>(A, table, w, live, prev, e, floor);
-				if(floor == 0) {   // rare: count the symbols without a codeword exactly
+		// ---- 1. my SPT bytes + the byte before them ----
+		uint32_t w[NWORDS];
 #pragma unroll
-					for(int i = 0; i < 16; ++i) dropped += (i < live && e[i] == 0) ? 1u : 0u;
-				}
-				// ---- 2. block exclusive scan ----
-				uint32_t incl = my_bits;
+		for(int k = 0; k < NWORDS; ++k) w[k] = 0;
+		int live = 0;
+		if(my < A.n) {
+			live = A.n - my >= uint64_t(SPT) ? SPT : int(A.n - my);
+			if(ALIGNED && live == SPT) {
 #pragma unroll
-				for(int d = 1; d < 32; d <<= 1) {
-					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-					if(lane >= uint32_t(d)) incl += t;
+				for(int k = 0; k < SPT / 16; ++k) {
+					const uint4 v = ld_stream_128(A.in + my + 16 * k);
+					w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
 				}
-				if(lane == 31) warp_sums[warp] = incl;
-				__syncthreads();
-				uint32_t before = 0, round_bits = 0;
-#pragma unroll
-				for(int k = 0; k < kEncThreads / 32; ++k) {
-					const uint32_t s = warp_sums[k];
-					if(uint32_t(k) < warp) before += s;
-					round_bits += s;
-				}
-				const uint32_t pos = tile_bits + before + incl - my_bits;
-				// ---- 3. pack: hi holds `fill` (< 32) pending bits left-aligned; branch-free flush ----
-				uint32_t* word = stage + (pos >> 5);
-				uint32_t fill = pos & 31, hi = 0;
-#pragma unroll
-				for(int i = 0; i < 16; ++i) {
-					const uint32_t code = e[i] & ~31u, len = e[i] & 31u;
-					hi |= code >> fill;
-					const uint32_t spill = __funnelshift_r(0u, code, fill);   // code << (32 - fill), 0 when fill == 0
-					fill += len;
-					const bool full = fill >= 32;
-					if(full) atomicOr(word, hi);
-					word += full ? 1 : 0;
-					hi = full ? spill : hi;
-					fill &= 31;
-				}
-				if(fill) atomicOr(word, hi);
-				tile_bits += round_bits;
 			} else {
-				// ---- u64 entries (codewords up to 56 bits) ----
-				unsigned long long e[16];
 #pragma unroll
-				for(int i = 0; i < 16; ++i) {
-					const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
-					unsigned long long ent = 0;
-					if(i < live) {
-						ent = __ldg(A.wide + ((A.order ? prev : 0u) << 8) + c);
-						if(ent == 0) ++dropped;
-					}
-					e[i] = ent;
-					my_bits += uint32_t(ent >> 56);
-					prev = c;
-				}
-				uint32_t incl = my_bits;
-#pragma unroll
-				for(int d = 1; d < 32; d <<= 1) {
-					const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-					if(lane >= uint32_t(d)) incl += t;
-				}
-				if(lane == 31) warp_sums[warp] = incl;
-				__syncthreads();
-				uint32_t before = 0, round_bits = 0;
-#pragma unroll
-				for(int k = 0; k < kEncThreads / 32; ++k) {
-					const uint32_t s = warp_sums[k];
-					if(uint32_t(k) < warp) before += s;
-					round_bits += s;
-				}
-				const uint32_t pos = tile_bits + before + incl - my_bits;
-				if(my_bits) {
-					uint32_t word = pos >> 5, fill = pos & 31;
-					unsigned long long acc = 0;
-					auto push = [&](uint32_t code, uint32_t len) {   // len <= 32, fill < 32
-						acc = (acc << len) | code;
-						fill += len;
-						if(fill >= 32) {
-							atomicOr(&stage[word], uint32_t(acc >> (fill - 32)));
-							++word;
-							fill -= 32;
-						}
-					};
-#pragma unroll
-					for(int i = 0; i < 16; ++i) {
-						const uint32_t len = uint32_t(e[i] >> 56);
-						if(len > 32) { push(uint32_t((e[i] & 0x00ffffffffffffffull) >> 32), len - 32); push(uint32_t(e[i]), 32); }
-						else if(len) push(uint32_t(e[i]), len);
-					}
-					if(fill) atomicOr(&stage[word], uint32_t(acc) << (32 - fill));
-				}
-				tile_bits += round_bits;
+				for(int i = 0; i < SPT; ++i)
+					if(i < live) w[i >> 2] |= uint32_t(A.in[my + i]) << (8 * (i & 3));
 			}
-			__syncthreads();   // warp_sums reuse + staged bits visible
 		}
+		uint32_t prev = __shfl_up_sync(0xffffffffu, w[NWORDS - 1] >> 24, 1);
+		if(lane == 0 && my < A.n) prev = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
 
-		// ---- 4. publish + warp-wide look-back ----
+		uint32_t tile_bits;
+		if constexpr(FMT != FMT_WIDE) {
+			// ---- entries: length in [31:27], right-aligned code in [26:0] ----
+			uint32_t e[SPT];
+			uint32_t my_bits = 0, floor = 0xffffffffu;
+			uint32_t row = A.order ? min(prev - lo, R) * pitch : 0u;
+			const bool whole = live == SPT;
+#pragma unroll
+			for(int i = 0; i < SPT; ++i) {
+				const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+				uint32_t ent = 0;
+				if(whole || i < live) {
+					if(A.order) {
+						const uint32_t uc = min(c - lo, R);   // bytes outside the box land on the zero border
+						ent = FMT == FMT_BOX_SMEM ? table[row + uc] : __ldg(A.box + row + uc);
+						row = uc * pitch;
+					} else {
+						ent = FMT == FMT_BOX_SMEM ? table[c] : __ldg(A.box + c);
+					}
+					floor = min(floor, ent);
+				}
+				e[i] = ent;
+				my_bits += ent >> 27;
+			}
+			if(floor == 0) {   // rare: count the symbols without a codeword exactly
+#pragma unroll
+				for(int i = 0; i < SPT; ++i) dropped += (i < live && e[i] == 0) ? 1u : 0u;
+			}
+			// ---- 2. block exclusive scan; publish the tile's bit count early ----
+			const uint32_t pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
+			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
+			// ---- 3. merge pairs -> quads, funnel through the window ----
+			Packer pk;
+			pk.start(stage, pos);
+#pragma unroll
+			for(int q = 0; q < SPT / 4; ++q) {
+				const uint32_t l0 = e[4 * q] >> 27, l1 = e[4 * q + 1] >> 27, l2 = e[4 * q + 2] >> 27, l3 = e[4 * q + 3] >> 27;
+				const unsigned long long p0 = (uint64_t(e[4 * q] & 0x07ffffffu) << l1) | (e[4 * q + 1] & 0x07ffffffu);
+				const unsigned long long p1 = (uint64_t(e[4 * q + 2] & 0x07ffffffu) << l3) | (e[4 * q + 3] & 0x07ffffffu);
+				const uint32_t lp0 = l0 + l1, lp1 = l2 + l3;
+				if(lp0 + lp1 <= 64) {
+					pk.put((p0 << lp1) | p1, lp0 + lp1);
+				} else {   // four long codewords in a row: two <= 54-bit units
+					pk.put(p0, lp0);
+					pk.put(p1, lp1);
+				}
+			}
+			pk.finish();
+		} else {
+			// ---- u64 entries (codewords up to 56 bits), one unit per symbol ----
+			unsigned long long e[SPT];
+			uint32_t my_bits = 0;
+#pragma unroll
+			for(int i = 0; i < SPT; ++i) {
+				const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+				unsigned long long ent = 0;
+				if(i < live) {
+					ent = __ldg(A.wide + ((A.order ? prev : 0u) << 8) + c);
+					if(ent == 0) ++dropped;
+				}
+				e[i] = ent;
+				my_bits += uint32_t(ent >> 56);
+				prev = c;
+			}
+			const uint32_t pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
+			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
+			Packer pk;
+			pk.start(stage, pos);
+#pragma unroll
+			for(int i = 0; i < SPT; ++i) pk.put(e[i] & 0x00ffffffffffffffull, uint32_t(e[i] >> 56));
+			pk.finish();
+		}
+		__syncthreads();   // staged bits visible
+
+		// ---- 4. publish the tail, resolve the global bit offset ----
 		if(warp == 0) {
 			const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
-			const uint32_t own_tail = stage_bits(stage, tile_bits - tcount, tcount);
+			if(lane == 0) st_relaxed32(A.tail + tile, kTailValid | stage_bits(stage, tile_bits - tcount, tcount));
 			unsigned long long excl_bits;
-			uint32_t excl_tail;
-			look_back(tile, tile_bits, own_tail, A.agg, A.inc, excl_bits, excl_tail);
+			uint32_t nearest_bits;
+			look_back(tile, tile_bits, A, excl_bits, nearest_bits);
 			if(lane == 0) {
 				s_prefix_bits = excl_bits;
-				s_prefix_tail = excl_tail;
+				s_prefix_tail = predecessor_tail(tile, nearest_bits, A);
 				if(tile == A.n_tiles - 1) A.result[0] = excl_bits + tile_bits;
 			}
 		}
@@ -365,9 +380,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 	if(lane == 0 && dropped) atomicAdd(A.result + 1, (unsigned long long) dropped);
 }
 
-template <int ROUNDS, int FMT>
+template <int SPT, int FMT>
 int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStream_t st) {
-	auto kern = aligned ? encode_kernel<ROUNDS, FMT, true> : encode_kernel<ROUNDS, FMT, false>;
+	auto kern = aligned ? encode_kernel<SPT, FMT, true> : encode_kernel<SPT, FMT, false>;
 	MH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
 	int per_sm = 0;
 	MH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEncThreads, smem_bytes));
@@ -385,7 +400,7 @@ int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStr
 
 }  // namespace
 
-uint64_t encode_tiles_for(uint64_t n) { return (n + kEncRoundBytes - 1) / kEncRoundBytes; }
+uint64_t encode_tiles_for(uint64_t n) { return (n + kEncThreads * 16 - 1) / (kEncThreads * 16); }
 
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
                   uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st) {
@@ -394,17 +409,28 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	if(!ws || !ws->enc_desc) return MH_ERR_WORKSPACE;
 	MH_CUDA(cudaMemsetAsync(d_result, 0, 4 * sizeof(unsigned long long), st));
 	if(n == 0) return MH_OK;
-	// Tile size: the staged bits of one tile must fit the staging area whatever the input, so rounds x round bytes x
-	// longest codeword bounds it. Prefer 2 rounds (16 KiB tiles); the staging area is sized to that bound.
+
+	// table format
 	const int maxb = cb->max_bits > 0 ? cb->max_bits : 1;
-	int rounds = 1;
-	if(uint64_t(4) * kEncRoundBytes * maxb <= uint64_t(kEncStageMaxWords) * 32 / 2) rounds = 4;
-	else if(uint64_t(2) * kEncRoundBytes * maxb <= uint64_t(kEncStageMaxWords) * 32) rounds = 2;
-	const uint32_t stage_words = uint32_t((uint64_t(rounds) * kEncRoundBytes * maxb + 31) / 32 + 4);
-	const uint64_t tile_bytes = uint64_t(rounds) * kEncRoundBytes;
+	const char* fmt_env = getenv("MH_ENC_FMT");   // experiments / tests: force a table format (1: box in global, 2: wide)
+	const int force_fmt = fmt_env ? atoi(fmt_env) : -1;
+	int fmt = FMT_WIDE;
+	size_t table_bytes = 0;
+	if(cb->has_box && force_fmt != FMT_WIDE) {
+		table_bytes = size_t(cb->order ? (cb->box_r + 1) * (cb->box_r + 1) : 256) * 4;
+		fmt = table_bytes <= size_t(kEncBoxSmemLimit) && force_fmt != FMT_BOX_GLOBAL ? FMT_BOX_SMEM : FMT_BOX_GLOBAL;
+	}
+	if(fmt != FMT_BOX_SMEM) table_bytes = 0;
+	// Tile size: the staged bits of one tile must fit the staging area whatever the input, so symbols per tile x
+	// longest codeword bounds it: 32 symbols per thread while that bound stays within kEncStageMaxWords.
+	int spt = 16;
+	if(fmt != FMT_WIDE && uint64_t(kEncThreads) * 32 * maxb <= uint64_t(kEncStageMaxWords) * 32) spt = 32;
+	const uint32_t stage_words = uint32_t(((uint64_t(kEncThreads) * spt * maxb + 31) / 32 + 7) & ~uint64_t(3));
+	const uint64_t tile_bytes = uint64_t(kEncThreads) * spt;
 	const uint64_t tiles = (n + tile_bytes - 1) / tile_bytes;
 	if(tiles > ws->enc_tiles_cap || tiles > 0x7fffffffull) return MH_ERR_WORKSPACE;
-	MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, 2 * tiles * sizeof(uint64_t), st));   // aggregate words, then inclusive words
+	// descriptors: aggregate words, inclusive words, tail words
+	MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, tiles * (2 * sizeof(uint64_t) + sizeof(uint32_t)), st));
 	MH_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(uint32_t), st));
 
 	EncArgs a;
@@ -417,36 +443,16 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.out_capacity_words = out_capacity / 4;
 	a.agg = reinterpret_cast<unsigned long long*>(ws->enc_desc);
 	a.inc = a.agg + tiles;
+	a.tail = reinterpret_cast<uint32_t*>(a.inc + tiles);
 	a.ticket = ws->counters;
 	a.result = d_result;
 	a.n_tiles = uint32_t(tiles);
 	const bool aligned = (reinterpret_cast<uint64_t>(d_in) & 15) == 0;
-	const size_t stage_bytes = (size_t(stage_words) + 4) * sizeof(uint32_t);
+	const size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 4) * sizeof(uint32_t);
 
-	const char* fmt_env = getenv("MH_ENC_FMT");   // experiments / tests: force a table format (1: box in global, 2: wide)
-	const int force_fmt = fmt_env ? atoi(fmt_env) : -1;
-	int fmt = FMT_WIDE;
-	size_t smem = stage_bytes;
-	if(cb->has_box) {
-		const size_t table_bytes = size_t(cb->order ? (cb->box_r + 1) * (cb->box_r + 1) : 256) * 4;
-		if(table_bytes <= size_t(kEncBoxSmemLimit)) { fmt = FMT_BOX_SMEM; smem = stage_bytes + table_bytes; }
-		else fmt = FMT_BOX_GLOBAL;
-		if(force_fmt == FMT_BOX_GLOBAL) { fmt = FMT_BOX_GLOBAL; smem = stage_bytes; }
-	}
-	if(force_fmt == FMT_WIDE) { fmt = FMT_WIDE; smem = stage_bytes; }
-	if(fmt == FMT_WIDE) {
-		if(maxb > 32 || rounds == 1) return launch_variant<1, FMT_WIDE>(aligned, a, smem, st);
-		if(rounds == 2) return launch_variant<2, FMT_WIDE>(aligned, a, smem, st);
-		return launch_variant<4, FMT_WIDE>(aligned, a, smem, st);
-	}
-	if(fmt == FMT_BOX_SMEM) {
-		if(rounds == 4) return launch_variant<4, FMT_BOX_SMEM>(aligned, a, smem, st);
-		if(rounds == 2) return launch_variant<2, FMT_BOX_SMEM>(aligned, a, smem, st);
-		return launch_variant<1, FMT_BOX_SMEM>(aligned, a, smem, st);
-	}
-	if(rounds == 4) return launch_variant<4, FMT_BOX_GLOBAL>(aligned, a, smem, st);
-	if(rounds == 2) return launch_variant<2, FMT_BOX_GLOBAL>(aligned, a, smem, st);
-	return launch_variant<1, FMT_BOX_GLOBAL>(aligned, a, smem, st);
+	if(fmt == FMT_WIDE) return launch_variant<16, FMT_WIDE>(aligned, a, smem, st);
+	if(fmt == FMT_BOX_SMEM) return spt == 32 ? launch_variant<32, FMT_BOX_SMEM>(aligned, a, smem, st) : launch_variant<16, FMT_BOX_SMEM>(aligned, a, smem, st);
+	return spt == 32 ? launch_variant<32, FMT_BOX_GLOBAL>(aligned, a, smem, st) : launch_variant<16, FMT_BOX_GLOBAL>(aligned, a, smem, st);
 }
 
 }  // namespace mh

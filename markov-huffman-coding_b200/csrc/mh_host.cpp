@@ -353,7 +353,7 @@ void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
 		if(cw.length == 0) return 0u;
 		uint32_t v = 0;
 		for(int i = 0; i < cw.length; ++i) v = (v << 1) | uint32_t(cw.bit(i));
-		return (v << (32 - cw.length)) | uint32_t(cw.length);
+		return (uint32_t(cw.length) << 27) | v;
 	};
 	if(!order) {
 		for(int c = 0; c < 256; ++c) box[c] = entry(trees[0].code[c]);

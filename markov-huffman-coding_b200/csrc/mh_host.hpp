@@ -76,7 +76,7 @@ public:
 	int flatten_codebook(uint64_t* enc /* [trees.size() * 256] */) const;
 	// Smallest byte range [lo, lo + r) holding every symbol that has a codeword and every non-empty context.
 	void live_range(uint32_t& lo, uint32_t& r) const;
-	// box[(prev - lo) * (r + 1) + (c - lo)] (order 1) or box[c] (order 0) = code << (32 - len) | len; needs max bits
+	// box[(prev - lo) * (r + 1) + (c - lo)] (order 1) or box[c] (order 0) = len << 27 | code; needs max bits
 	// <= 27. Row r and column r are a zero border that out-of-range bytes are clamped onto.
 	// `box` must hold (r + 1) * (r + 1) (order 1) or 256 (order 0) entries.
 	void flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const;

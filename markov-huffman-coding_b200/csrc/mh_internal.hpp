@@ -34,10 +34,9 @@ int max_smem_optin();    // bytes of opt-in dynamic shared memory per block (cac
 
 // ---- tunables (env overrides exist for experiments; defaults are what DESIGN.md documents) ------------
 constexpr int kEncThreads = 512;
-constexpr int kEncRoundBytes = kEncThreads * 16;      // one 128-bit load per thread per round
 constexpr int kEncStageMaxWords = 14336;              // at most 56 KiB of staged output bits per tile
 constexpr int kEncBoxSmemLimit = 72 * 1024;           // largest u32 box table staged in shared memory (R <= 135)
-constexpr int kEncBoxMaxBits = 27;                    // u32 entry: 27-bit left-aligned code | 5-bit length
+constexpr int kEncBoxMaxBits = 27;                    // u32 entry: 5-bit length | 27-bit right-aligned code
 constexpr int kDecThreads = 1024;                     // subsequences per chunk (one thread each)
 constexpr int kDecMinSubBits = 256;
 constexpr int kDecWarmSubs = 8;                       // overlap subsequences re-decoded by the next chunk
@@ -54,7 +53,7 @@ constexpr uint64_t kDescValueMask = (1ull << 62) - 1;
 // Device scratch. All pointers are device memory owned by the workspace.
 struct mh_workspace {
 	// encode
-	uint64_t* enc_desc = nullptr;         // [2 * enc_tiles_cap] aggregate words, then inclusive words
+	uint64_t* enc_desc = nullptr;         // enc_tiles_cap x (u64 aggregate, u64 inclusive, u32 tail) as three arrays
 	uint64_t enc_tiles_cap = 0;
 	uint32_t* counters = nullptr;         // [16] dynamic tile counters / flags
 	// histogram
@@ -72,7 +71,7 @@ struct mh_workspace {
 
 struct mh_codebook {
 	uint64_t* d_enc = nullptr;     // [ntab * 256] len << 56 | code
-	uint32_t* d_box = nullptr;     // [(R + 1)^2] with a zero border (order 1) or [256] (order 0): code << (32 - len) | len
+	uint32_t* d_box = nullptr;     // [(R + 1)^2] with a zero border (order 1) or [256] (order 0): len << 27 | code
 	uint32_t box_lo = 0, box_r = 256;
 	bool has_box = false;
 	uint64_t* h_stage = nullptr;   // pinned image the async upload reads from
