@@ -30,103 +30,132 @@ namespace {
 constexpr int kWarm = kDecWarmSubs;
 constexpr int kChunkSubs = kDecThreads - kWarm;   // subsequences owned by one chunk
 
-struct Tables {
-	const uint16_t* lut;    // shared or global; row = context (order 1) or 0
-	const uint32_t* walk;   // global
-};
+// LUT entry (u16), see CodingTable::flatten_dectable:
+//   leaf : symbol << 8 | length (1..8)           deep : node << 7 | 0x10 (internal node at depth 8)
+//   null : ' ' << 8 | 0x20 | 1 (no such table entry: harmless while speculating, an error once verified)
+constexpr uint32_t kDeep = 0x10u, kNull = 0x20u;
 
-// MSB-first bit window over 32-bit words of the payload. `avail` valid bits are left-aligned in `buf`.
+// MSB-first bit window over the payload: (hi:lo) holds the bits [pos, loaded) left-aligned, `nextw` is the word
+// after them, fetched one refill ahead so that its latency is off the per-symbol dependency chain.
+// pos / loaded are bit offsets relative to an origin chosen by the caller.
 struct Cursor {
-	const uint32_t* words;
-	uint64_t n_bytes;
-	uint64_t next;   // index of the next word to fetch
-	uint64_t buf;
-	int avail;
+	const uint32_t* words;   // payload
+	uint64_t n_bytes;        // payload bytes; reads past them return zero (pop_rest pads, src/bitbuffer.cpp:129-140)
+	const uint32_t* p;       // word that held the bit the cursor was seeked to
+	uint32_t safe;           // words from p that lie completely inside the payload (clamped)
+	uint32_t k;              // next word (relative to p) to fetch
+	uint32_t hi, lo, nextw;
+	uint32_t pos, loaded;
 
-	__device__ __forceinline__ uint32_t fetch(uint64_t w) const {
-		const uint64_t o = w << 2;
-		if(o + 4 <= n_bytes) return __byte_perm(__ldg(words + w), 0, 0x0123);
-		uint32_t v = 0;   // ragged end: bytes past the payload read as zero (pop_rest pads, src/bitbuffer.cpp:129-140)
+	__device__ __forceinline__ uint32_t fetch(uint32_t i) const {
+		if(i < safe) return __byte_perm(__ldg(p + i), 0, 0x0123);
+		const uint64_t o = (uint64_t(p - words) + i) << 2;   // ragged end
+		uint32_t v = 0;
 		const uint8_t* b = reinterpret_cast<const uint8_t*>(words);
-		for(int i = 0; i < 4; ++i)
-			if(o + i < n_bytes) v |= uint32_t(b[o + i]) << (24 - 8 * i);
+		for(int j = 0; j < 4; ++j)
+			if(o + j < n_bytes) v |= uint32_t(b[o + j]) << (24 - 8 * j);
 		return v;
 	}
-	__device__ __forceinline__ void seek(uint64_t bit) {
+	__device__ __forceinline__ void seek(uint64_t bit, uint32_t rel) {
 		const uint64_t w = bit >> 5;
-		const int off = int(bit & 31);
-		buf = ((uint64_t(fetch(w)) << 32) | fetch(w + 1)) << off;
-		avail = 64 - off;
-		next = w + 2;
+		const uint32_t off = uint32_t(bit & 31);
+		p = words + w;
+		const uint64_t whole = n_bytes >> 2;
+		safe = whole > w ? uint32_t(whole - w > 0x7fffffffull ? 0x7fffffffull : whole - w) : 0u;
+		const uint32_t w0 = fetch(0), w1 = fetch(1);
+		nextw = fetch(2);
+		k = 3;
+		hi = __funnelshift_l(w1, w0, off);
+		lo = w1 << off;
+		pos = rel;
+		loaded = rel + 64 - off;
 	}
-	__device__ __forceinline__ void take(int nbits) { buf <<= nbits; avail -= nbits; }
+	__device__ __forceinline__ void take(uint32_t nbits) {   // nbits < 32
+		hi = __funnelshift_l(lo, hi, nbits);
+		lo <<= nbits;
+		pos += nbits;
+	}
 	__device__ __forceinline__ void top_up() {
-		if(avail <= 32) {
-			buf |= uint64_t(fetch(next)) << (32 - avail);
-			++next;
-			avail += 32;
+		const uint32_t avail = loaded - pos;
+		if(avail <= 32) {   // all valid bits sit in hi
+			hi |= __funnelshift_rc(nextw, 0u, avail);
+			lo = __funnelshift_rc(0u, nextw, avail);
+			loaded += 32;
+			nextw = fetch(k++);
 		}
 	}
 };
 
-// 8-byte packed output writer: single bytes until the address is 8-aligned, then whole 64-bit stores.
+// Output writer: symbols are packed eight at a time and stored as aligned 64-bit words; the ragged head and tail
+// of the thread's range go out as single bytes.
 struct Emitter {
-	uint8_t* out;
-	uint64_t at;
+	uint8_t* base;      // 8-byte aligned address of the group being filled
 	uint64_t pack;
-	int held;
-	__device__ __forceinline__ void init(uint8_t* o, uint64_t start) { out = o; at = start; pack = 0; held = 0; }
+	uint32_t held;      // bytes of the current group already accounted for (the first group starts mid-way)
+	uint32_t skip;      // leading bytes of the current group that belong to someone else
+	__device__ __forceinline__ void init(uint8_t* out, uint64_t start) {
+		const uint64_t addr = reinterpret_cast<uint64_t>(out) + start;
+		base = reinterpret_cast<uint8_t*>(addr & ~uint64_t(7));
+		skip = held = uint32_t(addr & 7);
+		pack = 0;
+	}
 	__device__ __forceinline__ void put(uint32_t sym) {
-		if(held == 0 && ((reinterpret_cast<uint64_t>(out) + at) & 7)) { out[at++] = uint8_t(sym); return; }
 		pack |= uint64_t(sym) << (8 * held);
 		if(++held == 8) {
-			*reinterpret_cast<uint64_t*>(out + at) = pack;
-			at += 8; held = 0; pack = 0;
+			if(skip == 0) *reinterpret_cast<uint64_t*>(base) = pack;
+			else for(uint32_t i = skip; i < 8; ++i) base[i] = uint8_t(pack >> (8 * i));
+			base += 8; held = 0; skip = 0; pack = 0;
 		}
 	}
 	__device__ __forceinline__ void finish() {
-		for(int i = 0; i < held; ++i) out[at + i] = uint8_t(pack >> (8 * i));
+		for(uint32_t i = skip; i < held; ++i) base[i] = uint8_t(pack >> (8 * i));
 	}
 };
 
-// Decode every symbol whose first bit lies in [pos, limit). pos/limit are bit offsets from the cursor's origin
-// (the caller seeks the cursor to origin + pos). Returns false if a null table entry was hit.
-template <int ORDER, bool WRITE>
-__device__ __forceinline__ bool decode_span(Cursor& cur, const Tables& tb, uint32_t& pos, uint32_t limit, uint32_t& ctx,
-                                            uint32_t& count, Emitter* em) {
+// Decode every symbol whose first bit lies in [cur.pos, limit). Returns false if a null table entry was hit.
+// lut_s: shared-space address of the LUT (LUT_SHARED) — lut_g: the same table in global memory otherwise.
+template <int ORDER, bool WRITE, bool LUT_SHARED>
+__device__ __forceinline__ bool decode_span(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
+                                            const uint32_t* __restrict__ walk, uint32_t limit, uint32_t& ctx, uint32_t& count,
+                                            Emitter* em) {
 	bool clean = true;
-	while(pos < limit) {
-		const uint32_t row = ORDER ? ctx : 0u;
-		const uint32_t e = tb.lut[(row << 8) + uint32_t(cur.buf >> 56)];
-		uint32_t sym;
-		if(!(e & 0x8000u)) {
-			const int len = int((e >> 8) & 15u);
-			sym = e & 255u;
-			if(e & 0x4000u) clean = false;
-			cur.take(len);
-			pos += len;
+	uint32_t sym = ctx;
+	uint32_t row_off = ORDER ? ctx << 9 : 0u;   // byte offset of the context's 256 x u16 row
+	while(cur.pos < limit) {
+		const uint32_t off = row_off + ((cur.hi >> 23) & 0x1feu);
+		uint32_t e;
+		if(LUT_SHARED) asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(lut_s + off));
+		else e = __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(lut_g) + off));
+		if(!(e & (kDeep | kNull))) {
+			cur.take(e & 15u);
+			sym = e >> 8;
+		} else if(e & kNull) {
+			clean = false;
+			cur.take(1);
+			sym = ' ';
 		} else {
+			// codeword longer than 8 bits: consume the 8 window bits, then walk the tree bit by bit (src/coding.cpp:129-149)
 			cur.take(8);
-			pos += 8;
-			uint32_t node = e & 0x1ffu;
+			uint32_t node = e >> 7;
+			const uint32_t* nodes = walk + (row_off >> 9 << 9);
 			sym = ' ';
 			for(int guard = 0; guard < 256; ++guard) {
 				cur.top_up();
-				const uint32_t bit = uint32_t(cur.buf >> 63);
+				const uint32_t bit = cur.hi >> 31;
 				cur.take(1);
-				++pos;
-				const uint32_t w = __ldg(tb.walk + (row << 9) + node);
+				const uint32_t w = __ldg(nodes + node);
 				const uint32_t child = bit ? (w & 0xffffu) : (w >> 16);
 				if(child & 0x8000u) { sym = child & 255u; break; }
 				node = child;
 				if(guard == 255) clean = false;
 			}
 		}
-		ctx = sym;
+		if(ORDER) row_off = sym << 9;
 		++count;
 		if(WRITE) em->put(sym);
 		cur.top_up();
 	}
+	ctx = sym;
 	return clean;
 }
 
@@ -151,7 +180,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
 	}
 	__syncthreads();
-	Tables tb{lut_s, walk};
+	const uint32_t lut_sa = uint32_t(__cvta_generic_to_shared(lut_s));
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = (n_bits + 7) >> 3;
@@ -177,9 +206,10 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 			pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
 			ctx = ' ';
 			if(my_sub == 0) { pos = start0 >> 8; ctx = start0 & 255u; }   // the one exactly known state
-			cur.seek(origin + pos);
+			cur.seek(origin + pos, pos);
 			const uint32_t lim = limit_of(k);
-			decode_span<ORDER, false>(cur, tb, pos, lim, ctx, cnt, nullptr);
+			decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
+			pos = cur.pos;
 			st_s[tid] = pack_state(pos - lim, ctx);
 			cnt_s[tid] = cnt;
 		}
@@ -191,7 +221,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 			if(active) {
 				const uint32_t lim = limit_of(k);
 				cnt = 0;
-				decode_span<ORDER, false>(cur, tb, pos, lim, ctx, cnt, nullptr);
+				decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
+				pos = cur.pos;
 				const uint32_t st = pack_state(pos - lim, ctx);
 				const uint32_t slot = uint32_t(k - first_sub);
 				cnt_s[slot] = cnt;
@@ -223,19 +254,19 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 	seam[chunk] = recorded;
 	const uint64_t last = first + kChunkSubs < n_subs ? first + kChunkSubs : n_subs;
 	const uint64_t origin = first * sub_bits;
-	Tables tb{lut_g, walk};
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = (n_bits + 7) >> 3;
 	uint32_t pos = recorded >> 8, ctx = recorded & 255u;
-	cur.seek(origin + pos);
+	cur.seek(origin + pos, pos);
 	bool merged = false;
 	for(uint64_t k = first; k < last; ++k) {
 		uint64_t e = (k + 1) * sub_bits;
 		if(e > n_bits) e = n_bits;
 		const uint32_t lim = uint32_t(e - origin);
 		uint32_t cnt = 0;
-		decode_span<ORDER, false>(cur, tb, pos, lim, ctx, cnt, nullptr);
+		decode_span<ORDER, false, false>(cur, 0u, lut_g, walk, lim, ctx, cnt, nullptr);
+		pos = cur.pos;
 		const uint32_t st = pack_state(pos - lim, ctx);
 		count[k] = cnt;
 		if(state[k] == st) { merged = true; break; }
@@ -321,7 +352,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
 	}
 	__syncthreads();
-	Tables tb{lut_s, walk};
+	const uint32_t lut_sa = uint32_t(__cvta_generic_to_shared(lut_s));
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = (n_bits + 7) >> 3;
@@ -350,8 +381,9 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 			Emitter em;
 			em.init(out, chunk_base[chunk] + before + incl - c);
 			if(pos < lim) {
-				cur.seek(origin + pos);
-				clean &= decode_span<ORDER, true>(cur, tb, pos, lim, ctx, cnt, &em);
+				cur.seek(origin + pos, pos);
+				clean &= decode_span<ORDER, true, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, &em);
+				pos = cur.pos;
 			}
 			em.finish();
 			if(cnt != c) clean = false;

@@ -366,7 +366,7 @@ void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
 }
 
 void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
-	std::fill(lut, lut + trees.size() * 256, uint16_t(kLutNull | (1u << 8) | ' '));
+	std::fill(lut, lut + trees.size() * 256, uint16_t((' ' << 8) | kLutNull | 1u));
 	std::fill(walk, walk + trees.size() * 512, uint32_t(0));
 	for(size_t t = 0; t < trees.size(); ++t) {
 		const CodeTree& tr = trees[t];
@@ -375,7 +375,7 @@ void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
 			const int n = tr.lut[w];
 			if(n == kNoChild) continue;
 			const TreeNode& nd = tr.nodes[n];
-			lut[t * 256 + w] = nd.internal ? uint16_t(kLutDeep | n) : uint16_t((nd.depth << 8) | nd.symbol);
+			lut[t * 256 + w] = nd.internal ? uint16_t((n << 7) | kLutDeep) : uint16_t((nd.symbol << 8) | nd.depth);
 		}
 		for(size_t n = 0; n < tr.nodes.size(); ++n) {
 			const TreeNode& nd = tr.nodes[n];

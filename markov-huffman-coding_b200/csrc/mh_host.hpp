@@ -80,15 +80,15 @@ public:
 	// <= 27. Row r and column r are a zero border that out-of-range bytes are clamped onto.
 	// `box` must hold (r + 1) * (r + 1) (order 1) or 256 (order 0) entries.
 	void flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const;
-	// lut[ctx*256 + w]: leaf   : 0x0000 | len << 8 | symbol           (len 1..8)
-	//                  deep   : 0x8000 | node index within the context (internal node at depth 8)
-	//                  null   : 0x4000 | 1 << 8 | ' '                  (speculation-safe; an error if verified)
+	// lut[ctx*256 + w]: leaf : symbol << 8 | length (1..8)
+	//                  deep : node index within the context << 7 | 0x10   (internal node at depth 8)
+	//                  null : ' ' << 8 | 0x20 | 1                         (speculation-safe; an error if verified)
 	// walk[ctx*512 + node] = left << 16 | right, child = 0x8000|symbol for a leaf, else node index
 	void flatten_dectable(uint16_t* lut /* [trees.size() * 256] */, uint32_t* walk /* [trees.size() * 512] */) const;
 };
 
-constexpr uint16_t kLutDeep = 0x8000;
-constexpr uint16_t kLutNull = 0x4000;
+constexpr uint16_t kLutDeep = 0x10;
+constexpr uint16_t kLutNull = 0x20;
 constexpr uint32_t kWalkLeaf = 0x8000;
 
 }  // namespace mh
