@@ -27,8 +27,6 @@ namespace mh {
 
 namespace {
 
-constexpr int kWarm = kDecWarmSubs;
-constexpr int kChunkSubs = kDecThreads - kWarm;   // subsequences owned by one chunk
 
 // LUT entry (u16), see CodingTable::flatten_dectable:
 //   leaf : symbol << 8 | length (1..8)           deep : node << 7 | 0x10 (internal node at depth 8)
@@ -159,20 +157,31 @@ __device__ __forceinline__ bool decode_span(Cursor& cur, uint32_t lut_s, const u
 	return clean;
 }
 
-__device__ __forceinline__ uint32_t pack_state(uint32_t rel_bits, uint32_t ctx) { return (rel_bits << 8) | ctx; }
 
 // ---------------------------------------------------------------------------------------------------------
 // D1: speculative decode + intra-chunk synchronisation
+//
+// Each subsequence carries kCp checkpoints (every sub_bits / kCp bits). Checkpoint j records the decoder state at
+// the first codeword boundary at or after it, and how many symbols started in the segment before it. A thread
+// that takes over its successor's subsequence stops at the first checkpoint where its own state equals the
+// recorded one: from there on the recorded trajectory is its own. Per-segment counts (not running totals) make
+// the records of a partially overwritten subsequence consistent whoever wrote which segment.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kCp = 8;
+
+__device__ __forceinline__ uint32_t pack_cp(uint32_t rel_bits, uint32_t ctx) { return ((rel_bits > 255u ? 255u : rel_bits) << 8) | ctx; }
+
 template <int ORDER>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
     const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, uint32_t* __restrict__ state, uint32_t* __restrict__ count,
-    uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks) {
+    uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm) {
 	extern __shared__ uint16_t lut_s[];
-	__shared__ uint32_t st_s[kDecThreads];
-	__shared__ uint32_t cnt_s[kDecThreads];
+	__shared__ uint16_t cp_state[kCp][kDecThreads];   // [checkpoint][slot]: conflict-free across a warp
+	__shared__ uint16_t cp_count[kCp][kDecThreads];
 	const uint32_t tid = threadIdx.x;
+	const uint32_t chunk_subs = kDecThreads - warm;
+	const uint32_t seg_bits = sub_bits / kCp;
 	{
 		const uint32_t n16 = ORDER ? 65536u : 256u;
 		const uint4* src = reinterpret_cast<const uint4*>(lut_g);
@@ -187,53 +196,66 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 
 	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
 		// thread t handles subsequence first_sub + t where first_sub may be negative for chunk 0
-		const int64_t first_sub = int64_t(chunk) * kChunkSubs - kWarm;
+		const int64_t first_sub = int64_t(chunk) * chunk_subs - warm;
 		const int64_t my_sub = first_sub + tid;
-		const int64_t end_sub = int64_t(chunk + 1) * kChunkSubs < int64_t(n_subs) ? int64_t(chunk + 1) * kChunkSubs : int64_t(n_subs);
+		const int64_t end_sub = int64_t(chunk + 1) * chunk_subs < int64_t(n_subs) ? int64_t(chunk + 1) * chunk_subs : int64_t(n_subs);
 		const uint64_t origin = first_sub < 0 ? 0 : uint64_t(first_sub) * sub_bits;   // bit origin of this CTA's window
 		const int64_t origin_sub = first_sub < 0 ? 0 : first_sub;
+		const uint64_t span = n_bits - origin;   // bits from the origin to the end of the stream
 		bool active = my_sub >= 0 && my_sub < end_sub;
 
-		auto limit_of = [&](int64_t k) -> uint32_t {   // end of subsequence k relative to origin
-			uint64_t e = uint64_t(k + 1) * sub_bits;
-			if(e > n_bits) e = n_bits;
-			return uint32_t(e - origin);
+		// end of segment j of subsequence k, relative to origin, clipped to the end of the stream
+		auto limit_of = [&](int64_t k, int j) -> uint32_t {
+			const uint64_t e = uint64_t(k - origin_sub) * sub_bits + uint64_t(j + 1) * seg_bits;
+			return uint32_t(e < span ? e : span);
 		};
 
-		uint32_t pos = 0, ctx = ' ', cnt = 0;
+		uint32_t ctx = ' ';
 		int64_t k = my_sub;
 		if(active) {
-			pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
-			ctx = ' ';
+			uint32_t pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
 			if(my_sub == 0) { pos = start0 >> 8; ctx = start0 & 255u; }   // the one exactly known state
 			cur.seek(origin + pos, pos);
-			const uint32_t lim = limit_of(k);
-			decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
-			pos = cur.pos;
-			st_s[tid] = pack_state(pos - lim, ctx);
-			cnt_s[tid] = cnt;
+#pragma unroll 1
+			for(int j = 0; j < kCp; ++j) {
+				const uint32_t lim = limit_of(k, j);
+				uint32_t cnt = 0;
+				decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
+				cp_state[j][tid] = uint16_t(pack_cp(cur.pos - lim, ORDER ? ctx : 0u));
+				cp_count[j][tid] = uint16_t(cnt);
+			}
 		}
 		__syncthreads();
-		// rounds: take over the next subsequence until my end state matches what is recorded there
+		// rounds: walk the successor's checkpoints until my state equals the recorded one
 		for(;;) {
 			++k;
 			if(active && k >= end_sub) active = false;
 			if(active) {
-				const uint32_t lim = limit_of(k);
-				cnt = 0;
-				decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
-				pos = cur.pos;
-				const uint32_t st = pack_state(pos - lim, ctx);
 				const uint32_t slot = uint32_t(k - first_sub);
-				cnt_s[slot] = cnt;
-				if(st_s[slot] == st) active = false;
-				else st_s[slot] = st;
+#pragma unroll 1
+				for(int j = 0; j < kCp; ++j) {
+					const uint32_t lim = limit_of(k, j);
+					uint32_t cnt = 0;
+					decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
+					const uint16_t st = uint16_t(pack_cp(cur.pos - lim, ORDER ? ctx : 0u));
+					cp_count[j][slot] = uint16_t(cnt);
+					if(cp_state[j][slot] == st) { active = false; break; }
+					cp_state[j][slot] = st;
+				}
 			}
 			if(!__syncthreads_or(active ? 1 : 0)) break;
 		}
 		if(my_sub >= 0 && my_sub < end_sub) {
-			if(tid >= uint32_t(kWarm)) { state[my_sub] = st_s[tid]; count[my_sub] = cnt_s[tid]; }
-			else if(tid == uint32_t(kWarm - 1)) seam[chunk] = st_s[tid];   // boundary state as this chunk saw it
+			const uint32_t e = cp_state[kCp - 1][tid];
+			if(tid >= warm) {
+				uint32_t total = 0;
+#pragma unroll
+				for(int j = 0; j < kCp; ++j) total += cp_count[j][tid];
+				state[my_sub] = e;
+				count[my_sub] = total;
+			} else if(tid == warm - 1) {
+				seam[chunk] = e;   // boundary state as this chunk saw it
+			}
 		}
 		__syncthreads();
 	}
@@ -245,14 +267,14 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 template <int ORDER>
 __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_bits, const uint16_t* __restrict__ lut_g,
                                 const uint32_t* __restrict__ walk, uint32_t* state, uint32_t* count, uint32_t* seam,
-                                uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t* flag) {
+                                uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t* flag) {
 	const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x + 1;
 	if(chunk >= n_chunks) return;
-	const uint64_t first = uint64_t(chunk) * kChunkSubs;
+	const uint64_t first = uint64_t(chunk) * chunk_subs;
 	const uint32_t recorded = *(volatile uint32_t*) (state + first - 1);
 	if(seam[chunk] == recorded) return;
 	seam[chunk] = recorded;
-	const uint64_t last = first + kChunkSubs < n_subs ? first + kChunkSubs : n_subs;
+	const uint64_t last = first + chunk_subs < n_subs ? first + chunk_subs : n_subs;
 	const uint64_t origin = first * sub_bits;
 	Cursor cur;
 	cur.words = words;
@@ -267,7 +289,7 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 		uint32_t cnt = 0;
 		decode_span<ORDER, false, false>(cur, 0u, lut_g, walk, lim, ctx, cnt, nullptr);
 		pos = cur.pos;
-		const uint32_t st = pack_state(pos - lim, ctx);
+		const uint32_t st = pack_cp(pos - lim, ORDER ? ctx : 0u);
 		count[k] = cnt;
 		if(state[k] == st) { merged = true; break; }
 		state[k] = st;
@@ -278,11 +300,11 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 // ---------------------------------------------------------------------------------------------------------
 // D3: per-chunk totals and their exclusive scan
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dec_total_kernel(const uint32_t* __restrict__ count, uint64_t n_subs,
+__global__ void __launch_bounds__(256) dec_total_kernel(const uint32_t* __restrict__ count, uint64_t n_subs, uint32_t chunk_subs,
                                                          unsigned long long* __restrict__ chunk_total) {
 	__shared__ unsigned long long part[8];
-	const uint64_t first = uint64_t(blockIdx.x) * kChunkSubs;
-	const uint64_t last = first + kChunkSubs < n_subs ? first + kChunkSubs : n_subs;
+	const uint64_t first = uint64_t(blockIdx.x) * chunk_subs;
+	const uint64_t last = first + chunk_subs < n_subs ? first + chunk_subs : n_subs;
 	unsigned long long s = 0;
 	for(uint64_t k = first + threadIdx.x; k < last; k += 256) s += count[k];
 	for(int d = 16; d; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
@@ -340,7 +362,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
     const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ state, const uint32_t* __restrict__ count,
     const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits, uint64_t n_subs,
-    uint32_t n_chunks, unsigned long long* result) {
+    uint32_t n_chunks, uint32_t chunk_subs, unsigned long long* result) {
 	extern __shared__ uint16_t lut_s[];
 	__shared__ uint32_t warp_tot[32];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -358,8 +380,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 	cur.n_bytes = (n_bits + 7) >> 3;
 	bool clean = true;
 	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-		const uint64_t k = uint64_t(chunk) * kChunkSubs + tid;
-		const bool mine = tid < uint32_t(kChunkSubs) && k < n_subs;
+		const uint64_t k = uint64_t(chunk) * chunk_subs + tid;
+		const bool mine = tid < chunk_subs && k < n_subs;
 		const uint32_t c = mine ? count[k] : 0u;
 		uint32_t incl = c;
 		for(int d = 1; d < 32; d <<= 1) {
@@ -396,15 +418,13 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 }  // namespace
 
 uint32_t decode_sub_bits(int order) {
-	static int cached[2] = {0, 0};
-	int& c = cached[order ? 1 : 0];
-	if(c == 0) {
-		c = order ? 1024 : 256;
-		const char* env = getenv(order ? "MH_DEC_SUB_BITS_MARKOV" : "MH_DEC_SUB_BITS_HUFFMAN");
-		if(env) {
-			int v = atoi(env);
-			if(v >= kDecMinSubBits && v % 32 == 0 && v <= (1 << 20)) c = v;
-		}
+	// Subsequence size: Markov streams re-synchronise ~10x slower than plain Huffman streams, so they
+	// get longer subsequences. The environment override exists for experiments and tests.
+	int c = order ? 4096 : 1024;
+	const char* env = getenv(order ? "MH_DEC_SUB_BITS_MARKOV" : "MH_DEC_SUB_BITS_HUFFMAN");
+	if(env) {
+		const int v = atoi(env);
+		if(v >= kDecMinSubBits && v % 256 == 0 && v <= (1 << 16)) c = v;
 	}
 	return uint32_t(c);
 }
@@ -416,7 +436,11 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh
                uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
 	const uint32_t sub_bits = decode_sub_bits(ORDER);
 	const uint64_t n_subs = (n_bits + sub_bits - 1) / sub_bits;
-	const uint64_t chunks64 = (n_subs + kChunkSubs - 1) / kChunkSubs;
+	// the next chunk re-decodes the last `warm` subsequences (>= 8192 bits) of this one as warm-up
+	uint32_t warm = 8192 / sub_bits;
+	warm = warm < 1 ? 1 : (warm > uint32_t(kDecWarmSubs) ? uint32_t(kDecWarmSubs) : warm);
+	const uint32_t chunk_subs = kDecThreads - warm;
+	const uint64_t chunks64 = (n_subs + chunk_subs - 1) / chunk_subs;
 	if(n_subs > ws->dec_subs_cap || chunks64 > ws->dec_chunks_cap) return MH_ERR_WORKSPACE;
 	const uint32_t n_chunks = uint32_t(chunks64);
 	const size_t lut_bytes = ORDER ? 65536 * 2 : 256 * 2;
@@ -432,7 +456,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh
 	{
 		ProfScope p("dec_sync_kernel", st);
 		dec_sync_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, start0, dt->d_lut, dt->d_walk, ws->dec_state,
-		    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks);
+		    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm);
 	}
 	count_launch(1);
 	int last_flag = -1;
@@ -442,14 +466,14 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh
 		for(int it = 0; it < fix_iters; ++it) {
 			ProfScope p("dec_seam_kernel", st);
 			dec_seam_kernel<ORDER><<<(n_chunks - 1 + 127) / 128, 128, 0, st>>>(words, n_bits, dt->d_lut, dt->d_walk, ws->dec_state,
-			    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, ws->dec_flags + it);
+			    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, chunk_subs, ws->dec_flags + it);
 			count_launch(1);
 			last_flag = it;
 		}
 	}
 	{
 		ProfScope p("dec_total_kernel", st);
-		dec_total_kernel<<<n_chunks, 256, 0, st>>>(ws->dec_count, n_subs, (unsigned long long*) ws->dec_chunk_total);
+		dec_total_kernel<<<n_chunks, 256, 0, st>>>(ws->dec_count, n_subs, chunk_subs, (unsigned long long*) ws->dec_chunk_total);
 	}
 	{
 		ProfScope p("dec_scan_kernel", st);
@@ -459,7 +483,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh
 	{
 		ProfScope p("dec_write_kernel", st);
 		dec_write_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, start0, dt->d_lut, dt->d_walk, ws->dec_state,
-		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, d_result);
+		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, d_result);
 	}
 	count_launch(3);
 	MH_CUDA(cudaGetLastError());

@@ -178,3 +178,20 @@ def test_encoder_table_formats_agree(session, ipsum_counts, fmt, monkeypatch):
     monkeypatch.setenv("MH_ENC_FMT", fmt)
     for order in (0, 1):
         assert session.compress(data, order)[0] == want[order]
+
+
+@pytest.mark.parametrize("sub_bits", ["256", "1024", "8192"])
+def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, monkeypatch):
+    """The subsequence size only changes how the work is cut, never the bytes."""
+    monkeypatch.setenv("MH_DEC_SUB_BITS_MARKOV", sub_bits)
+    monkeypatch.setenv("MH_DEC_SUB_BITS_HUFFMAN", sub_bits)
+    s = mh.Session(8 << 20)
+    try:
+        text = o.synth_markov(ipsum_counts, 9, 4096, 0, (2 << 20) + 123)
+        fib = o.synth_fibonacci(40, 48, 4321, 0, 1 << 20)
+        for data in (text, fib):
+            for order in (0, 1):
+                stream, provider = s.compress(data, order)
+                assert s.decompress(provider, stream) == data
+    finally:
+        s.close()
