@@ -61,6 +61,16 @@ __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
 	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
 	return r;
 }
+// Shared memory through explicit 32-bit shared-space addresses: keeps generic-address arithmetic out of the hot
+// loops.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void red_or_if(uint32_t addr, uint32_t v, bool go) {
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.or.b32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(uint32_t(go)) : "memory");
+}
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
 	for(int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -190,27 +200,27 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 
 // A thread's bit window: `fill` (< 32) pending bits left-aligned in `hi`; completed words are ORed into the stage.
 struct Packer {
-	uint32_t* word;
+	uint32_t word;   // shared-space byte address of the word being filled
 	uint32_t hi, fill;
-	__device__ __forceinline__ void start(uint32_t* stage, uint32_t pos) { word = stage + (pos >> 5); hi = 0; fill = pos & 31; }
-	// append a right-aligned unit of len <= 64 bits
+	__device__ __forceinline__ void start(uint32_t stage_addr, uint32_t pos) { word = stage_addr + ((pos >> 5) << 2); hi = 0; fill = pos & 31; }
+	// append a right-aligned unit of len <= 64 bits (len == 0: v == 0)
 	__device__ __forceinline__ void put(unsigned long long v, uint32_t len) {
-		const unsigned long long q = len ? v << (64 - len) : 0ull;
-		const uint32_t qh = uint32_t(q >> 32), ql = uint32_t(q);
+		const uint32_t vh = uint32_t(v >> 32), vl = uint32_t(v);
+		const uint32_t up = (64u - len) & 63u;                      // left-align: q = v << up (len == 64 or 0 -> no shift)
+		const uint32_t qh = up >= 32 ? vl << (up - 32) : __funnelshift_l(vl, vh, up);
+		const uint32_t ql = up >= 32 ? 0u : vl << up;
 		const uint32_t w0 = hi | (qh >> fill);
 		const uint32_t w1 = __funnelshift_r(ql, qh, fill);
-		const uint32_t w2 = __funnelshift_r(0u, ql, fill);   // ql << (32 - fill), 0 when fill == 0
-		const uint32_t nf = fill + len;                      // < 96
-		const uint32_t full = nf >> 5;                       // 0, 1 or 2 words completed
-		if(full >= 1) atomicOr(word, w0);
-		if(full == 2) atomicOr(word + 1, w1);
-		word += full;
+		const uint32_t w2 = __funnelshift_r(0u, ql, fill);          // ql << (32 - fill), 0 when fill == 0
+		const uint32_t nf = fill + len;                             // < 96
+		const uint32_t full = nf >> 5;                              // 0, 1 or 2 words completed
+		red_or_if(word, w0, full >= 1);
+		red_or_if(word + 4, w1, full == 2);
+		word += full << 2;
 		hi = full == 0 ? w0 : (full == 1 ? w1 : w2);
 		fill = nf & 31;
 	}
-	__device__ __forceinline__ void finish() {
-		if(fill) atomicOr(word, hi);
-	}
+	__device__ __forceinline__ void finish() { red_or_if(word, hi, fill != 0); }
 };
 
 template <int SPT, int FMT, bool ALIGNED>
@@ -230,6 +240,8 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 		for(uint32_t i = tid; i < table_entries; i += kEncThreads) table[i] = __ldg(A.box + i);
 	}
 	uint32_t* stage = smem + ((table_entries + 3) & ~3u);   // [stage_words + 4]
+	const uint32_t table_sa = uint32_t(__cvta_generic_to_shared(table));
+	const uint32_t stage_sa = uint32_t(__cvta_generic_to_shared(stage));
 	for(uint32_t i = tid; i < A.stage_words + 4; i += kEncThreads) stage[i] = 0;
 	if(tid == 0) s_tile[0] = atomicAdd(A.ticket, 1u);
 	const uint32_t R = A.box_r, lo = A.box_lo, pitch = R + 1;
@@ -269,7 +281,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			// ---- entries: length in [31:27], right-aligned code in [26:0] ----
 			uint32_t e[SPT];
 			uint32_t my_bits = 0, floor = 0xffffffffu;
-			uint32_t row = A.order ? min(prev - lo, R) * pitch : 0u;
+			// byte address of the current context's row (box formats keep the border row at index R)
+			const uint32_t pitch4 = pitch * 4;
+			uint32_t row = (FMT == FMT_BOX_SMEM ? table_sa : 0u) + (A.order ? min(prev - lo, R) * pitch4 : 0u);
 			const bool whole = live == SPT;
 #pragma unroll
 			for(int i = 0; i < SPT; ++i) {
@@ -278,10 +292,10 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 				if(whole || i < live) {
 					if(A.order) {
 						const uint32_t uc = min(c - lo, R);   // bytes outside the box land on the zero border
-						ent = FMT == FMT_BOX_SMEM ? table[row + uc] : __ldg(A.box + row + uc);
-						row = uc * pitch;
+						ent = FMT == FMT_BOX_SMEM ? lds32(row + uc * 4) : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(A.box) + row) + uc);
+						row = (FMT == FMT_BOX_SMEM ? table_sa : 0u) + uc * pitch4;
 					} else {
-						ent = FMT == FMT_BOX_SMEM ? table[c] : __ldg(A.box + c);
+						ent = FMT == FMT_BOX_SMEM ? lds32(row + c * 4) : __ldg(A.box + c);
 					}
 					floor = min(floor, ent);
 				}
@@ -297,7 +311,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
 			// ---- 3. merge pairs -> quads, funnel through the window ----
 			Packer pk;
-			pk.start(stage, pos);
+			pk.start(stage_sa, pos);
 #pragma unroll
 			for(int q = 0; q < SPT / 4; ++q) {
 				const uint32_t l0 = e[4 * q] >> 27, l1 = e[4 * q + 1] >> 27, l2 = e[4 * q + 2] >> 27, l3 = e[4 * q + 3] >> 27;
@@ -331,7 +345,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			const uint32_t pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
 			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
 			Packer pk;
-			pk.start(stage, pos);
+			pk.start(stage_sa, pos);
 #pragma unroll
 			for(int i = 0; i < SPT; ++i) pk.put(e[i] & 0x00ffffffffffffffull, uint32_t(e[i] >> 56));
 			pk.finish();
