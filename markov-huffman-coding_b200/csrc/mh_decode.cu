@@ -42,18 +42,19 @@ struct Cursor {
 	const uint32_t* p;       // word that held the bit the cursor was seeked to
 	uint32_t safe;           // words from p that lie completely inside the payload (clamped)
 	uint32_t k;              // next word (relative to p) to fetch
-	uint32_t hi, lo, nextw;
-	uint32_t pos, loaded;
+	uint32_t hi, lo, nextw;  // nextw is kept in memory (little-endian) order and byte-swapped only when consumed, so
+	uint32_t pos, loaded;    // that nothing waits on the load until the next refill
 
-	__device__ __forceinline__ uint32_t fetch(uint32_t i) const {
-		if(i < safe) return __byte_perm(__ldg(p + i), 0, 0x0123);
+	__device__ __forceinline__ uint32_t fetch_raw(uint32_t i) const {
+		if(i < safe) return __ldg(p + i);
 		const uint64_t o = (uint64_t(p - words) + i) << 2;   // ragged end
 		uint32_t v = 0;
 		const uint8_t* b = reinterpret_cast<const uint8_t*>(words);
 		for(int j = 0; j < 4; ++j)
-			if(o + j < n_bytes) v |= uint32_t(b[o + j]) << (24 - 8 * j);
+			if(o + j < n_bytes) v |= uint32_t(b[o + j]) << (8 * j);
 		return v;
 	}
+	__device__ __forceinline__ uint32_t fetch(uint32_t i) const { return __byte_perm(fetch_raw(i), 0, 0x0123); }
 	__device__ __forceinline__ void seek(uint64_t bit, uint32_t rel) {
 		const uint64_t w = bit >> 5;
 		const uint32_t off = uint32_t(bit & 31);
@@ -61,7 +62,7 @@ struct Cursor {
 		const uint64_t whole = n_bytes >> 2;
 		safe = whole > w ? uint32_t(whole - w > 0x7fffffffull ? 0x7fffffffull : whole - w) : 0u;
 		const uint32_t w0 = fetch(0), w1 = fetch(1);
-		nextw = fetch(2);
+		nextw = fetch_raw(2);
 		k = 3;
 		hi = __funnelshift_l(w1, w0, off);
 		lo = w1 << off;
@@ -76,10 +77,11 @@ struct Cursor {
 	__device__ __forceinline__ void top_up() {
 		const uint32_t avail = loaded - pos;
 		if(avail <= 32) {   // all valid bits sit in hi
-			hi |= __funnelshift_rc(nextw, 0u, avail);
-			lo = __funnelshift_rc(0u, nextw, avail);
+			const uint32_t w = __byte_perm(nextw, 0, 0x0123);
+			hi |= __funnelshift_rc(w, 0u, avail);
+			lo = __funnelshift_rc(0u, w, avail);
 			loaded += 32;
-			nextw = fetch(k++);
+			nextw = fetch_raw(k++);
 		}
 	}
 };
