@@ -215,6 +215,7 @@ def main():
     import torch
     import torch.distributed as dist
     mh = importlib.import_module("markov-huffman-coding_b200")   # raises if libmh_gpu.so is missing: no fallback
+    sharding = importlib.import_module("markov-huffman-coding_b200.sharding")
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -263,21 +264,21 @@ def main():
             h_counts[:65536].copy_(d_counts, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         all_counts = h_counts.numpy().view(np.uint64).reshape(world, 65536)
-        total_counts = np.ascontiguousarray(all_counts.sum(axis=0, dtype=np.uint64))
-        provider = mh.CodingProvider.from_counts_array(total_counts, 1)     # identical on every rank
+        provider = mh.CodingProvider.from_counts_array(sharding.global_counts(all_counts), 1)     # identical on every rank
         if book is None:
             book, dectab = mh.Codebook(provider), mh.DecodeTable(provider)
         book.update(provider, stream)
-        if world > 1:
-            lens = provider.code_lengths()
-            shard_bits = (all_counts * lens[None, :]).sum(axis=1, dtype=np.uint64)
-            bit_base = int(shard_bits[:rank].sum())
+        expect_bits = None
+        if world > 1:   # every rank derives every shard's global bit offset from the gathered histograms
+            base, shard_bits = sharding.shard_bit_bases(all_counts, provider.code_lengths())
+            bit_base, expect_bits = int(base[rank]), int(shard_bits[rank])
         mh.gpu_encode(d_in.data_ptr(), n, prev0, book, bit_base, d_payload.data_ptr(), payload_cap, d_res_enc.data_ptr(), ws, stream)
         h_res[:4].copy_(d_res_enc, non_blocking=True)
         ev[1].record()
         torch.cuda.current_stream().synchronize()
         bits = int(h_res[0])
         assert int(h_res[2]) == 0, "encode: capacity"
+        assert expect_bits is None or bits == expect_bits, "shard payload size differs from sum(count x length)"
         dectab.update(provider, stream)
         mh.gpu_decode(d_payload.data_ptr(), bit_base, bits, prev0, dectab, d_out.data_ptr(), n, d_res_dec.data_ptr(), ws, stream)
         h_res[4:].copy_(d_res_dec, non_blocking=True)

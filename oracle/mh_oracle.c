@@ -278,6 +278,24 @@ long mho_compress(const mho_table* t, const uint8_t* in, uint64_t n, uint8_t* ou
 	return 1 + (long) ((w.bit + 7) / 8);
 }
 
+long long mho_encode_shard(const mho_table* t, const uint8_t* in, uint64_t n, uint8_t prev0, uint64_t bit_base, uint8_t* out, size_t cap) {
+	uint64_t pos = bit_base & 7;                                /* the shard's first bit inside out[0] */
+	const uint64_t start = pos;
+	unsigned prev = prev0;
+	for(uint64_t i = 0; i < n; i++) {
+		const mho_tree* tr = &t->trees[t->markov ? prev : 0];
+		unsigned c = in[i];
+		int len = tr->code_len[c];
+		const uint8_t* bits = tr->code_bits[c];
+		for(int b = 0; b < len; b++, pos++) {
+			if(pos / 8 >= cap) return -1;
+			out[pos / 8] |= (uint8_t) (((bits[b / 8] >> (7 - b % 8)) & 1) << (7 - pos % 8));
+		}
+		prev = c;
+	}
+	return (long long) (pos - start);
+}
+
 uint64_t mho_payload_bits(const mho_table* t, const uint8_t* in, uint64_t n) {
 	uint64_t bits = 0; unsigned prev = ' ';
 	for(uint64_t i = 0; i < n; i++) { bits += (uint64_t) t->trees[t->markov ? prev : 0].code_len[in[i]]; prev = in[i]; }

@@ -80,6 +80,11 @@ long mho_compress(const mho_table* t, const uint8_t* in, uint64_t n, uint8_t* ou
  * missing child was reached (the reference would dereference null). */
 long mho_decompress(const mho_table* t, const uint8_t* stream, uint64_t stream_len, uint8_t* out, size_t cap);
 
+/* Shard form of the compress loop (test stand-in for one GPU of the sharded path): codes in[0..n) with the byte
+ * before in[0] being prev0, writing the payload (no header) so that its first bit lands at bit (bit_base & 7) of
+ * out[0]. Returns the number of payload bits, or -1 if cap is too small. out must be zeroed by the caller. */
+long long mho_encode_shard(const mho_table* t, const uint8_t* in, uint64_t n, uint8_t prev0, uint64_t bit_base, uint8_t* out, size_t cap);
+
 /* payload bit count a compress() of this input would produce, from counts alone: sum(counts * code_len). */
 uint64_t mho_payload_bits(const mho_table* t, const uint8_t* in, uint64_t n);
 

@@ -44,6 +44,8 @@ def _load():
     lib.mho_compress.restype = ctypes.c_long
     lib.mho_decompress.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t]
     lib.mho_decompress.restype = ctypes.c_long
+    lib.mho_encode_shard.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint8, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t]
+    lib.mho_encode_shard.restype = ctypes.c_longlong
     lib.mho_payload_bits.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
     lib.mho_payload_bits.restype = ctypes.c_uint64
     lib.mho_synth_markov.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64]
@@ -162,6 +164,15 @@ class Table:
         if n < 0:
             raise ValueError("oracle decompress error %d" % n)
         return out[:n].tobytes()
+
+    def encode_shard(self, data, prev0, bit_base):
+        """(payload bytes whose first bit sits at bit (bit_base & 7), n_bits) — what one GPU of the sharded path writes."""
+        a, p = _buf(data)
+        cap = 32 * len(a) + 16
+        out = np.zeros(cap, dtype=np.uint8)
+        nbits = lib().mho_encode_shard(self.h, p, len(a), prev0, bit_base, out.ctypes.data_as(ctypes.c_void_p), cap)
+        assert nbits >= 0
+        return out[: ((bit_base & 7) + nbits + 7) // 8].tobytes(), int(nbits)
 
     def payload_bits(self, data):
         a, p = _buf(data)

@@ -1,0 +1,137 @@
+"""The multi-GPU path without 8 GPUs.
+
+* CPU, world_size 2 over gloo: every rank holds a byte range, the local histograms are all-gathered, every rank
+  builds the tables with the product's host code and derives its own global bit offset; the shard payloads
+  (the oracle stands in for the encode kernel here) are merged and must equal the unsharded stream byte for byte.
+* GPU (`-m gpu`): the same with k logical shards on one device through mh_gpu_histogram / mh_gpu_encode /
+  mh_gpu_decode with prev0 and bit_base.
+"""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_py as o
+from conftest import golden_input
+from mhlib import load
+
+mh = load()
+sharding = importlib.import_module("markov-huffman-coding_b200.sharding")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, order, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = golden_input("input_wiki_cpp.html")
+        cut = [0, 150001, len(data)] if world == 2 else [len(data) * i // world for i in range(world + 1)]
+        mine = data[cut[rank]:cut[rank + 1]]
+        prev0 = 0x20 if rank == 0 else data[cut[rank] - 1]
+        bins = 65536 if order else 256
+        local = o.histogram(mine, bool(order), prev0).astype(np.int64)          # stand-in for mh_gpu_histogram
+        gathered = [torch.zeros(bins, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(local))
+        all_counts = np.stack([g.numpy() for g in gathered]).astype(np.uint64)
+        provider = mh.CodingProvider.from_counts_array(sharding.global_counts(all_counts), order)   # product host code
+        base, bits = sharding.shard_bit_bases(all_counts, provider.code_lengths())
+        table = o.Table.from_bytes(provider.write_coding_tree())
+        payload, nbits = table.encode_shard(mine, prev0, int(base[rank]))                            # stand-in for mh_gpu_encode
+        assert nbits == int(bits[rank])
+        parts = [None] * world
+        dist.all_gather_object(parts, (payload, int(base[rank]), nbits))
+        if rank == 0:
+            merged = sharding.merge_payload_shards(parts)
+            total = int(base[-1] + bits[-1])
+            stream = bytes([sharding.stream_header(order, total)]) + merged
+            want_stream, want_table = o.compress_from_input(data, bool(order))
+            q.put((stream == want_stream, provider.write_coding_tree() == want_table))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_two_rank_gloo_sharded_compress_equals_unsharded(order):
+    import torch.multiprocessing as tmp
+    ctx = tmp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, order, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == (True, True)
+
+
+def test_merge_handles_empty_and_byte_aligned_shards():
+    t = o.Table.from_counts(o.histogram(b"abracadabra" * 9, True), True)
+    data = b"abracadabra" * 9
+    cuts = [0, 0, 11, 11, 40, len(data)]
+    parts, base = [], 0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        prev0 = 0x20 if a == 0 else data[a - 1]
+        payload, nbits = t.encode_shard(data[a:b], prev0, base)
+        parts.append((payload, base, nbits))
+        base += nbits
+    assert bytes([sharding.stream_header(1, base)]) + sharding.merge_payload_shards(parts) == t.compress(data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("k", [2, 5])
+def test_logical_shards_on_one_gpu(order, k):
+    import torch
+    ipsum = o.histogram(golden_input("input_ipsum.txt"), True).astype(np.uint32)
+    data = o.synth_markov(ipsum, 31, 4096, 0, (3 << 20) + 1234)
+    n = len(data)
+    cuts = [n * i // k + (7 * i if 0 < i < k else 0) for i in range(k + 1)]
+    dev = torch.device("cuda", 0)
+    d_all = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    ws = mh.Workspace(n, n + n // 8 + 4096)
+    bins = 65536 if order else 256
+    all_counts = np.zeros((k, bins), dtype=np.uint64)
+    d_counts = torch.zeros(bins, dtype=torch.int64, device=dev)
+    for g in range(k):
+        prev0 = 0x20 if g == 0 else data[cuts[g] - 1]
+        shard = d_all[cuts[g]:cuts[g + 1]]                       # unaligned device pointers on purpose
+        mh.gpu_histogram(shard.data_ptr(), shard.numel(), prev0, order, d_counts.data_ptr(), ws)
+        all_counts[g] = d_counts.cpu().numpy().view(np.uint64)
+    provider = mh.CodingProvider.from_counts_array(sharding.global_counts(all_counts), order)
+    want_stream, want_table = o.compress_from_input(data, bool(order))
+    assert provider.write_coding_tree() == want_table
+    base, bits = sharding.shard_bit_bases(all_counts, provider.code_lengths())
+    book, dectab = mh.Codebook(provider), mh.DecodeTable(provider)
+    d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+    parts, outs = [], []
+    for g in range(k):
+        prev0 = 0x20 if g == 0 else data[cuts[g] - 1]
+        shard = d_all[cuts[g]:cuts[g + 1]]
+        cap = shard.numel() + shard.numel() // 8 + 4096
+        d_pay = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        mh.gpu_encode(shard.data_ptr(), shard.numel(), prev0, book, int(base[g]), d_pay.data_ptr(), cap, d_res.data_ptr(), ws)
+        res = d_res.cpu().numpy()
+        assert int(res[0]) == int(bits[g]) and int(res[2]) == 0
+        parts.append((d_pay.cpu().numpy().tobytes(), int(base[g]), int(bits[g])))
+        d_out = torch.zeros(shard.numel(), dtype=torch.uint8, device=dev)
+        mh.gpu_decode(d_pay.data_ptr(), int(base[g]), int(bits[g]), prev0, dectab, d_out.data_ptr(), shard.numel(), d_res.data_ptr(), ws)
+        res = d_res.cpu().numpy()
+        assert int(res[0]) == shard.numel() and int(res[1]) == 0 and int(res[2]) == 0
+        outs.append(d_out.cpu().numpy().tobytes())
+    total = int(base[-1] + bits[-1])
+    assert bytes([sharding.stream_header(order, total)]) + sharding.merge_payload_shards(parts) == want_stream
+    assert b"".join(outs) == data
