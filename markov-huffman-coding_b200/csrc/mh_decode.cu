@@ -86,79 +86,99 @@ struct Cursor {
 	}
 };
 
-// Output writer: symbols are packed eight at a time and stored as aligned 64-bit words; the ragged head and tail
-// of the thread's range go out as single bytes.
-struct Emitter {
-	uint8_t* base;      // 8-byte aligned address of the group being filled
-	uint64_t pack;
-	uint32_t held;      // bytes of the current group already accounted for (the first group starts mid-way)
-	uint32_t skip;      // leading bytes of the current group that belong to someone else
-	__device__ __forceinline__ void init(uint8_t* out, uint64_t start) {
-		const uint64_t addr = reinterpret_cast<uint64_t>(out) + start;
-		base = reinterpret_cast<uint8_t*>(addr & ~uint64_t(7));
-		skip = held = uint32_t(addr & 7);
-		pack = 0;
-	}
-	__device__ __forceinline__ void put(uint32_t sym) {
-		pack |= uint64_t(sym) << (8 * held);
-		if(++held == 8) {
-			if(skip == 0) *reinterpret_cast<uint64_t*>(base) = pack;
-			else for(uint32_t i = skip; i < 8; ++i) base[i] = uint8_t(pack >> (8 * i));
-			base += 8; held = 0; skip = 0; pack = 0;
+// One symbol: look the top 8 window bits up in the context's row; leaves take the fast path. Returns the symbol and
+// advances the cursor. `row_off` is the byte offset of the context's 256 x u16 row (always 0 for ORDER 0).
+template <int ORDER, bool LUT_SHARED>
+__device__ __forceinline__ uint32_t decode_one(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
+                                               const uint32_t* __restrict__ walk, uint32_t& row_off, bool& clean) {
+	const uint32_t off = row_off + ((cur.hi >> 23) & 0x1feu);
+	uint32_t e;
+	if(LUT_SHARED) asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(lut_s + off));
+	else e = __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(lut_g) + off));
+	uint32_t sym;
+	if(!(e & (kDeep | kNull))) {
+		cur.take(e & 15u);
+		sym = e >> 8;
+	} else if(e & kNull) {
+		clean = false;
+		cur.take(1);
+		sym = ' ';
+	} else {
+		// codeword longer than 8 bits: consume the 8 window bits, then walk the tree bit by bit (src/coding.cpp:129-149)
+		cur.take(8);
+		uint32_t node = e >> 7;
+		const uint32_t* nodes = walk + row_off;   // row_off = ctx * 512 is also the context's offset in the walk table
+		sym = ' ';
+		for(int guard = 0; guard < 256; ++guard) {
+			cur.top_up();
+			const uint32_t bit = cur.hi >> 31;
+			cur.take(1);
+			const uint32_t w = __ldg(nodes + node);
+			const uint32_t child = bit ? (w & 0xffffu) : (w >> 16);
+			if(child & 0x8000u) { sym = child & 255u; break; }
+			node = child;
+			if(guard == 255) clean = false;
 		}
+		cur.top_up();   // restore the "more than 32 valid bits" invariant the 4-symbol groups rely on
 	}
-	__device__ __forceinline__ void finish() {
-		for(uint32_t i = skip; i < held; ++i) base[i] = uint8_t(pack >> (8 * i));
-	}
-};
+	if(ORDER) row_off = sym << 9;
+	return sym;
+}
 
-// Decode every symbol whose first bit lies in [cur.pos, limit). Returns false if a null table entry was hit.
-// lut_s: shared-space address of the LUT (LUT_SHARED) — lut_g: the same table in global memory otherwise.
-template <int ORDER, bool WRITE, bool LUT_SHARED>
-__device__ __forceinline__ bool decode_span(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
-                                            const uint32_t* __restrict__ walk, uint32_t limit, uint32_t& ctx, uint32_t& count,
-                                            Emitter* em) {
+// Decode every symbol whose first bit lies in [cur.pos, limit), counting them. The window is topped up once per
+// group of four symbols (four LUT hits consume at most 32 bits), so lanes refill together instead of one by one.
+template <int ORDER, bool LUT_SHARED>
+__device__ __forceinline__ bool decode_until(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
+                                             const uint32_t* __restrict__ walk, uint32_t limit, uint32_t& ctx, uint32_t& count) {
 	bool clean = true;
 	uint32_t sym = ctx;
-	uint32_t row_off = ORDER ? ctx << 9 : 0u;   // byte offset of the context's 256 x u16 row
+	uint32_t row_off = ORDER ? ctx << 9 : 0u;
 	while(cur.pos < limit) {
-		const uint32_t off = row_off + ((cur.hi >> 23) & 0x1feu);
-		uint32_t e;
-		if(LUT_SHARED) asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(lut_s + off));
-		else e = __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const char*>(lut_g) + off));
-		if(!(e & (kDeep | kNull))) {
-			cur.take(e & 15u);
-			sym = e >> 8;
-		} else if(e & kNull) {
-			clean = false;
-			cur.take(1);
-			sym = ' ';
-		} else {
-			// codeword longer than 8 bits: consume the 8 window bits, then walk the tree bit by bit (src/coding.cpp:129-149)
-			cur.take(8);
-			uint32_t node = e >> 7;
-			const uint32_t* nodes = walk + (row_off >> 9 << 9);
-			sym = ' ';
-			for(int guard = 0; guard < 256; ++guard) {
-				cur.top_up();
-				const uint32_t bit = cur.hi >> 31;
-				cur.take(1);
-				const uint32_t w = __ldg(nodes + node);
-				const uint32_t child = bit ? (w & 0xffffu) : (w >> 16);
-				if(child & 0x8000u) { sym = child & 255u; break; }
-				node = child;
-				if(guard == 255) clean = false;
+#pragma unroll
+		for(int j = 0; j < 4; ++j) {
+			if(cur.pos < limit) {
+				sym = decode_one<ORDER, LUT_SHARED>(cur, lut_s, lut_g, walk, row_off, clean);
+				++count;
 			}
 		}
-		if(ORDER) row_off = sym << 9;
-		++count;
-		if(WRITE) em->put(sym);
 		cur.top_up();
 	}
 	ctx = sym;
 	return clean;
 }
 
+// Decode exactly `count` symbols and write them to `out`. Single bytes until the address is 8-byte aligned, then
+// eight symbols per aligned 64-bit store — every lane stores in the same iteration — then the ragged tail.
+template <int ORDER>
+__device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
+                                            const uint32_t* __restrict__ walk, uint32_t count, uint32_t ctx, uint8_t* out) {
+	bool clean = true;
+	uint32_t row_off = ORDER ? ctx << 9 : 0u;
+	uint32_t head = uint32_t((8 - (reinterpret_cast<uint64_t>(out) & 7)) & 7);
+	if(head > count) head = count;
+	for(uint32_t i = 0; i < head; ++i) {
+		*out++ = uint8_t(decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean));
+		cur.top_up();
+	}
+	const uint32_t groups = (count - head) >> 3;
+	for(uint32_t g = 0; g < groups; ++g) {
+		uint32_t lo = 0, hi = 0;
+#pragma unroll
+		for(int j = 0; j < 4; ++j) lo = __byte_perm(lo, decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean), 0x4321);
+		cur.top_up();
+#pragma unroll
+		for(int j = 0; j < 4; ++j) hi = __byte_perm(hi, decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean), 0x4321);
+		cur.top_up();
+		*reinterpret_cast<uint2*>(out) = make_uint2(lo, hi);
+		out += 8;
+	}
+	const uint32_t tail = (count - head) & 7;
+	for(uint32_t i = 0; i < tail; ++i) {
+		*out++ = uint8_t(decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean));
+		cur.top_up();
+	}
+	return clean;
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // D1: speculative decode + intra-chunk synchronisation
@@ -191,7 +211,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
 	}
 	__syncthreads();
-	const uint32_t lut_sa = uint32_t(__cvta_generic_to_shared(lut_s));
+	uint32_t lut_sa;
+	asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(lut_sa) : "l"(lut_s));
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = (n_bits + 7) >> 3;
@@ -222,7 +243,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 			for(int j = 0; j < kCp; ++j) {
 				const uint32_t lim = limit_of(k, j);
 				uint32_t cnt = 0;
-				decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
+				decode_until<ORDER, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt);
 				cp_state[j][tid] = uint16_t(pack_cp(cur.pos - lim, ORDER ? ctx : 0u));
 				cp_count[j][tid] = uint16_t(cnt);
 			}
@@ -238,7 +259,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 				for(int j = 0; j < kCp; ++j) {
 					const uint32_t lim = limit_of(k, j);
 					uint32_t cnt = 0;
-					decode_span<ORDER, false, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, nullptr);
+					decode_until<ORDER, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt);
 					const uint16_t st = uint16_t(pack_cp(cur.pos - lim, ORDER ? ctx : 0u));
 					cp_count[j][slot] = uint16_t(cnt);
 					if(cp_state[j][slot] == st) { active = false; break; }
@@ -289,7 +310,7 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 		if(e > n_bits) e = n_bits;
 		const uint32_t lim = uint32_t(e - origin);
 		uint32_t cnt = 0;
-		decode_span<ORDER, false, false>(cur, 0u, lut_g, walk, lim, ctx, cnt, nullptr);
+		decode_until<ORDER, false>(cur, 0u, lut_g, walk, lim, ctx, cnt);
 		pos = cur.pos;
 		const uint32_t st = pack_cp(pos - lim, ORDER ? ctx : 0u);
 		count[k] = cnt;
@@ -376,7 +397,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
 	}
 	__syncthreads();
-	const uint32_t lut_sa = uint32_t(__cvta_generic_to_shared(lut_s));
+	uint32_t lut_sa;
+	asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(lut_sa) : "l"(lut_s));
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = (n_bits + 7) >> 3;
@@ -400,18 +422,18 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 			const uint64_t origin = k * sub_bits;
 			uint64_t e = (k + 1) * sub_bits;
 			if(e > n_bits) e = n_bits;
-			uint32_t pos = start >> 8, ctx = start & 255u, cnt = 0;
+			uint32_t pos = start >> 8;
+			const uint32_t ctx = start & 255u;
 			const uint32_t lim = uint32_t(e - origin);
-			Emitter em;
-			em.init(out, chunk_base[chunk] + before + incl - c);
-			if(pos < lim) {
+			if(c) {
 				cur.seek(origin + pos, pos);
-				clean &= decode_span<ORDER, true, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt, &em);
+				clean &= decode_emit<ORDER>(cur, lut_sa, lut_g, walk, c, ctx, out + (chunk_base[chunk] + before + incl - c));
 				pos = cur.pos;
 			}
-			em.finish();
-			if(cnt != c) clean = false;
-			if(k == n_subs - 1 && origin + pos != n_bits) clean = false;   // the last codeword runs past the payload
+			// D1 counted the symbols that start before `lim`: decoding that many must land on or after it, and on
+			// the very end of the payload for the last subsequence (else the last codeword runs past the stream)
+			if(pos < lim) clean = false;
+			if(k == n_subs - 1 && origin + pos != n_bits) clean = false;
 		}
 	}
 	if(!clean) result[2] = (unsigned long long) (long long) MH_ERR_CORRUPT_STREAM;
