@@ -56,6 +56,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel, n_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture
+    (profiles/*_traffic.json, taken at 1 GiB), or None when the workload size differs / no capture exists."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            cap = json.load(open(path))
+            if cap.get("input_bytes") != n_bytes:
+                continue
+            for name, rec in cap["kernels"].items():
+                if kernel.split("<")[0] in name:
+                    return rec["traffic_bytes"]
+        except Exception:
+            continue
+    return None
+
+
 def ipsum_transition_counts():
     import numpy as np
     data = np.frombuffer(open(os.path.join(ROOT, "tests/golden/inputs/input_ipsum.txt"), "rb").read(), dtype=np.uint8)
@@ -395,7 +412,7 @@ def main():
                    "sharding": "byte-range shards, NCCL all-gather of histograms, exclusive scan of per-GPU bit totals" if world > 1 else "single GPU"},
         "encode_gbs": n * world * args.steps / (t_enc * 1e-3) / 1e9, "decode_gbs": n * world * args.steps / (t_dec * 1e-3) / 1e9,
         "gpu_launches": int(launches), "kernels_ms_per_launch": kern, "phases": phase,
-        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dominant, n),
                      "peak_source": peak_src, "algorithmic_bytes": algo.get(dominant, 0), "ms_per_launch": dom_ms},
         "clocks": clock_info,
     }

@@ -377,6 +377,15 @@ int mh_gpu_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uin
 	                     static_cast<cudaStream_t>(stream), 2);
 }
 
+int mh_gpu_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start,
+                        uint8_t prev0, uint32_t skip_subsequences, int stream_end, const mh_dectable* dt, uint8_t* d_out,
+                        uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream) {
+	return launch_decode_shard(d_bits, start_bit, n_bits, buf_bytes, exact_start, prev0, skip_subsequences, stream_end, dt, d_out,
+	                           out_capacity, reinterpret_cast<unsigned long long*>(d_result), ws, static_cast<cudaStream_t>(stream), 2);
+}
+
+uint32_t mh_decode_subsequence_bits(int order) { return decode_sub_bits(order); }
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------

@@ -195,7 +195,7 @@ __device__ __forceinline__ uint32_t pack_cp(uint32_t rel_bits, uint32_t ctx) { r
 
 template <int ORDER>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
-    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t start0, const uint16_t* __restrict__ lut_g,
+    const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, uint32_t* __restrict__ state, uint32_t* __restrict__ count,
     uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm) {
 	extern __shared__ uint16_t lut_s[];
@@ -215,14 +215,15 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 	asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(lut_sa) : "l"(lut_s));
 	Cursor cur;
 	cur.words = words;
-	cur.n_bytes = (n_bits + 7) >> 3;
+	cur.n_bytes = buf_bytes;
 
 	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
 		// thread t handles subsequence first_sub + t where first_sub may be negative for chunk 0
 		const int64_t first_sub = int64_t(chunk) * chunk_subs - warm;
 		const int64_t my_sub = first_sub + tid;
 		const int64_t end_sub = int64_t(chunk + 1) * chunk_subs < int64_t(n_subs) ? int64_t(chunk + 1) * chunk_subs : int64_t(n_subs);
-		const uint64_t origin = first_sub < 0 ? 0 : uint64_t(first_sub) * sub_bits;   // bit origin of this CTA's window
+		// bit origin of this CTA's window; the subsequence grid starts at the stream's first bit (start0 >> 8)
+		const uint64_t origin = (start0 >> 8) + (first_sub < 0 ? 0 : uint64_t(first_sub) * sub_bits);
 		const int64_t origin_sub = first_sub < 0 ? 0 : first_sub;
 		const uint64_t span = n_bits - origin;   // bits from the origin to the end of the stream
 		bool active = my_sub >= 0 && my_sub < end_sub;
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		int64_t k = my_sub;
 		if(active) {
 			uint32_t pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
-			if(my_sub == 0) { pos = start0 >> 8; ctx = start0 & 255u; }   // the one exactly known state
+			if(my_sub == 0) ctx = start0 & 255u;   // the stream's own start (exact, or a shard's guess)
 			cur.seek(origin + pos, pos);
 #pragma unroll 1
 			for(int j = 0; j < kCp; ++j) {
@@ -288,9 +289,9 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 // D2: chunk seams. flags[slot] is raised when some chunk's END state changed (the next pass must re-check).
 // ---------------------------------------------------------------------------------------------------------
 template <int ORDER>
-__global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_bits, const uint16_t* __restrict__ lut_g,
+__global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, const uint16_t* __restrict__ lut_g,
                                 const uint32_t* __restrict__ walk, uint32_t* state, uint32_t* count, uint32_t* seam,
-                                uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t* flag) {
+                                uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t phase, uint32_t* flag) {
 	const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x + 1;
 	if(chunk >= n_chunks) return;
 	const uint64_t first = uint64_t(chunk) * chunk_subs;
@@ -298,15 +299,15 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 	if(seam[chunk] == recorded) return;
 	seam[chunk] = recorded;
 	const uint64_t last = first + chunk_subs < n_subs ? first + chunk_subs : n_subs;
-	const uint64_t origin = first * sub_bits;
+	const uint64_t origin = first * sub_bits + phase;
 	Cursor cur;
 	cur.words = words;
-	cur.n_bytes = (n_bits + 7) >> 3;
+	cur.n_bytes = buf_bytes;
 	uint32_t pos = recorded >> 8, ctx = recorded & 255u;
 	cur.seek(origin + pos, pos);
 	bool merged = false;
 	for(uint64_t k = first; k < last; ++k) {
-		uint64_t e = (k + 1) * sub_bits;
+		uint64_t e = (k + 1) * sub_bits + phase;
 		if(e > n_bits) e = n_bits;
 		const uint32_t lim = uint32_t(e - origin);
 		uint32_t cnt = 0;
@@ -324,12 +325,13 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 // D3: per-chunk totals and their exclusive scan
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dec_total_kernel(const uint32_t* __restrict__ count, uint64_t n_subs, uint32_t chunk_subs,
-                                                         unsigned long long* __restrict__ chunk_total) {
+                                                         uint32_t skip_subs, unsigned long long* __restrict__ chunk_total) {
 	__shared__ unsigned long long part[8];
 	const uint64_t first = uint64_t(blockIdx.x) * chunk_subs;
 	const uint64_t last = first + chunk_subs < n_subs ? first + chunk_subs : n_subs;
 	unsigned long long s = 0;
-	for(uint64_t k = first + threadIdx.x; k < last; k += 256) s += count[k];
+	for(uint64_t k = first + threadIdx.x; k < last; k += 256)
+		if(k >= skip_subs) s += count[k];   // a shard's leading warm-up subsequences belong to its predecessor
 	for(int d = 16; d; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
 	if((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
 	__syncthreads();
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(256) dec_total_kernel(const uint32_t* __restri
 __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long* __restrict__ chunk_total,
                                                          unsigned long long* __restrict__ chunk_base, uint32_t n_chunks,
                                                          uint64_t out_capacity, const uint32_t* __restrict__ flags, int last_flag,
+                                                         const uint32_t* __restrict__ state, uint64_t n_subs, uint32_t skip_subs,
                                                          unsigned long long* __restrict__ result) {
 	__shared__ unsigned long long warp_tot[32];
 	__shared__ unsigned long long carry_s;
@@ -374,6 +377,9 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long
 		if(last_flag >= 0 && flags[last_flag]) status = MH_ERR_NOT_CONVERGED;
 		else if(total > out_capacity) status = MH_ERR_CAPACITY;
 		result[1] = (unsigned long long) status;
+		// shard seams: [63:32] the state at the ownership start as the warm-up saw it, [31:0] the state at the end
+		const unsigned long long view = skip_subs ? state[skip_subs - 1] : 0u;
+		result[3] = (view << 32) | state[n_subs - 1];
 	}
 }
 
@@ -382,10 +388,10 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long
 // ---------------------------------------------------------------------------------------------------------
 template <int ORDER>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
-    const uint32_t* __restrict__ words, uint64_t n_bits, uint32_t start0, const uint16_t* __restrict__ lut_g,
+    const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ state, const uint32_t* __restrict__ count,
     const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits, uint64_t n_subs,
-    uint32_t n_chunks, uint32_t chunk_subs, unsigned long long* result) {
+    uint32_t n_chunks, uint32_t chunk_subs, uint32_t skip_subs, uint32_t stream_end, unsigned long long* result) {
 	extern __shared__ uint16_t lut_s[];
 	__shared__ uint32_t warp_tot[32];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -401,11 +407,11 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 	asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(lut_sa) : "l"(lut_s));
 	Cursor cur;
 	cur.words = words;
-	cur.n_bytes = (n_bits + 7) >> 3;
+	cur.n_bytes = buf_bytes;
 	bool clean = true;
 	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
 		const uint64_t k = uint64_t(chunk) * chunk_subs + tid;
-		const bool mine = tid < chunk_subs && k < n_subs;
+		const bool mine = tid < chunk_subs && k < n_subs && k >= skip_subs;
 		const uint32_t c = mine ? count[k] : 0u;
 		uint32_t incl = c;
 		for(int d = 1; d < 32; d <<= 1) {
@@ -418,9 +424,9 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 		for(uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
 		__syncthreads();
 		if(mine) {
-			const uint32_t start = k == 0 ? start0 : state[k - 1];
-			const uint64_t origin = k * sub_bits;
-			uint64_t e = (k + 1) * sub_bits;
+			const uint32_t start = k == 0 ? (start0 & 255u) : state[k - 1];
+			const uint64_t origin = k * sub_bits + (start0 >> 8);
+			uint64_t e = origin + sub_bits;
 			if(e > n_bits) e = n_bits;
 			uint32_t pos = start >> 8;
 			const uint32_t ctx = start & 255u;
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 			// D1 counted the symbols that start before `lim`: decoding that many must land on or after it, and on
 			// the very end of the payload for the last subsequence (else the last codeword runs past the stream)
 			if(pos < lim) clean = false;
-			if(k == n_subs - 1 && origin + pos != n_bits) clean = false;
+			if(stream_end && k == n_subs - 1 && origin + pos != n_bits) clean = false;
 		}
 	}
 	if(!clean) result[2] = (unsigned long long) (long long) MH_ERR_CORRUPT_STREAM;
@@ -456,10 +462,11 @@ uint32_t decode_sub_bits(int order) {
 namespace {
 
 template <int ORDER>
-int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh_dectable* dt, uint8_t* d_out,
-               uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
+int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, uint32_t skip_subs, uint32_t stream_end,
+               const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws,
+               cudaStream_t st, int fix_iters) {
 	const uint32_t sub_bits = decode_sub_bits(ORDER);
-	const uint64_t n_subs = (n_bits + sub_bits - 1) / sub_bits;
+	const uint64_t n_subs = (n_bits - (start0 >> 8) + sub_bits - 1) / sub_bits;   // the grid starts at the stream's first bit
 	// the next chunk re-decodes the last `warm` subsequences (>= 8192 bits) of this one as warm-up
 	uint32_t warm = 8192 / sub_bits;
 	warm = warm < 1 ? 1 : (warm > uint32_t(kDecWarmSubs) ? uint32_t(kDecWarmSubs) : warm);
@@ -479,7 +486,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh
 	MH_CUDA(cudaMemsetAsync(ws->dec_flags, 0, 8 * sizeof(uint32_t), st));
 	{
 		ProfScope p("dec_sync_kernel", st);
-		dec_sync_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, start0, dt->d_lut, dt->d_walk, ws->dec_state,
+		dec_sync_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, ws->dec_state,
 		    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm);
 	}
 	count_launch(1);
@@ -489,25 +496,25 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint32_t start0, const mh
 		if(fix_iters > 8) fix_iters = 8;
 		for(int it = 0; it < fix_iters; ++it) {
 			ProfScope p("dec_seam_kernel", st);
-			dec_seam_kernel<ORDER><<<(n_chunks - 1 + 127) / 128, 128, 0, st>>>(words, n_bits, dt->d_lut, dt->d_walk, ws->dec_state,
-			    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, chunk_subs, ws->dec_flags + it);
+			dec_seam_kernel<ORDER><<<(n_chunks - 1 + 127) / 128, 128, 0, st>>>(words, n_bits, buf_bytes, dt->d_lut, dt->d_walk, ws->dec_state,
+			    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, chunk_subs, start0 >> 8, ws->dec_flags + it);
 			count_launch(1);
 			last_flag = it;
 		}
 	}
 	{
 		ProfScope p("dec_total_kernel", st);
-		dec_total_kernel<<<n_chunks, 256, 0, st>>>(ws->dec_count, n_subs, chunk_subs, (unsigned long long*) ws->dec_chunk_total);
+		dec_total_kernel<<<n_chunks, 256, 0, st>>>(ws->dec_count, n_subs, chunk_subs, skip_subs, (unsigned long long*) ws->dec_chunk_total);
 	}
 	{
 		ProfScope p("dec_scan_kernel", st);
 		dec_scan_kernel<<<1, 1024, 0, st>>>((const unsigned long long*) ws->dec_chunk_total, (unsigned long long*) ws->dec_chunk_base,
-		    n_chunks, out_capacity, ws->dec_flags, last_flag, d_result);
+		    n_chunks, out_capacity, ws->dec_flags, last_flag, ws->dec_state, n_subs, skip_subs, d_result);
 	}
 	{
 		ProfScope p("dec_write_kernel", st);
-		dec_write_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, start0, dt->d_lut, dt->d_walk, ws->dec_state,
-		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, d_result);
+		dec_write_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, ws->dec_state,
+		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, skip_subs, stream_end, d_result);
 	}
 	count_launch(3);
 	MH_CUDA(cudaGetLastError());
@@ -529,8 +536,28 @@ int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uin
 	const uint32_t bit0 = uint32_t(bit_base & 7);
 	const uint32_t start0 = (bit0 << 8) | prev0;
 	const uint64_t end_bit = n_bits + bit0;
-	if(dt->order) return run_decode<1>(words, end_bit, start0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
-	return run_decode<0>(words, end_bit, start0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	const uint64_t buf_bytes = (end_bit + 7) >> 3;
+	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	return run_decode<0>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+}
+
+int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start, uint8_t prev0,
+                        uint32_t skip_subs, int stream_end, const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity,
+                        unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
+	if(!dt || !dt->d_lut || !d_result || !d_bits || start_bit > 31) return MH_ERR_INVALID_ARG;
+	if(reinterpret_cast<uint64_t>(d_bits) & 3) return MH_ERR_INVALID_ARG;
+	if(!ws || !ws->dec_state) return MH_ERR_WORKSPACE;
+	MH_CUDA(cudaMemsetAsync(d_result, 0, 4 * sizeof(unsigned long long), st));
+	if(n_bits == 0) return MH_OK;
+	const uint64_t end_bit = n_bits + start_bit;
+	if(buf_bytes * 8 < end_bit) return MH_ERR_INVALID_ARG;
+	const uint64_t n_subs = (n_bits + decode_sub_bits(dt->order) - 1) / decode_sub_bits(dt->order);
+	if(skip_subs >= n_subs) return MH_ERR_INVALID_ARG;
+	const uint32_t* words = reinterpret_cast<const uint32_t*>(d_bits);
+	// a shard that does not know its start state guesses the context; its leading skip_subs subsequences are warm-up
+	const uint32_t start0 = (start_bit << 8) | (exact_start ? uint32_t(prev0) : uint32_t(' '));
+	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	return run_decode<0>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
 }
 
 }  // namespace mh

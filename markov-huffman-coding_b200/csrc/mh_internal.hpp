@@ -99,6 +99,9 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
                   uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st);
 int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
                   uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
+int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start, uint8_t prev0,
+                        uint32_t skip_subs, int stream_end, const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity,
+                        unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
 uint32_t decode_sub_bits(int order);                 // subsequence size in bits used for this coder type
 uint64_t encode_tiles_for(uint64_t n);               // worst-case tile count for n input bytes
 

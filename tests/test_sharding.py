@@ -135,3 +135,70 @@ def test_logical_shards_on_one_gpu(order, k):
     total = int(base[-1] + bits[-1])
     assert bytes([sharding.stream_header(order, total)]) + sharding.merge_payload_shards(parts) == want_stream
     assert b"".join(outs) == data
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("k", [2, 3, 8])
+def test_bit_range_sharded_decode_with_seam_handshake(order, k):
+    """Decode ONE stream as k bit-range shards: shard 0 knows its state, the others start a warm-up before their
+    range, guess, and must arrive at the state their predecessor ended in (mh_gpu_decode_shard)."""
+    import torch
+    ipsum = o.histogram(golden_input("input_ipsum.txt"), True).astype(np.uint32)
+    data = o.synth_markov(ipsum, 77, 4096, 0, (2 << 20) + 4321)
+    stream, table = o.compress_from_input(data, bool(order))
+    total_bits = (len(stream) - 1) * 8 - (stream[0] & 7)
+    dev = torch.device("cuda", 0)
+    pad = 64                                                        # readable bytes past the payload (zero = pop_rest padding)
+    d_pay = torch.zeros(len(stream) - 1 + pad, dtype=torch.uint8, device=dev)
+    d_pay[: len(stream) - 1] = torch.frombuffer(bytearray(stream[1:]), dtype=torch.uint8).to(dev)
+    provider = mh.CodingProvider.from_table_file(table)
+    dectab = mh.DecodeTable(provider)
+    ws = mh.Workspace(len(data), len(stream) + pad)
+    sub = mh.decode_subsequence_bits(order)
+    warm_subs = max(1, 8192 // sub)
+    bounds = [total_bits * g // k + (13 * g if 0 < g < k else 0) for g in range(k + 1)]   # arbitrary, mid-codeword boundaries
+    d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+    outs, seams = [], []
+    for g in range(k):
+        origin = 0 if g == 0 else bounds[g] - warm_subs * sub
+        assert origin >= 0
+        ptr_off = (origin // 32) * 4
+        d_out = torch.zeros(len(data), dtype=torch.uint8, device=dev)
+        mh.gpu_decode_shard(d_pay.data_ptr() + ptr_off, origin % 32, bounds[g + 1] - origin, d_pay.numel() - ptr_off,
+                            g == 0, 0x20, 0 if g == 0 else warm_subs, g == k - 1, dectab, d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), ws)
+        res = d_res.cpu().numpy().view(np.uint64)
+        assert int(res[1]) == 0 and int(res[2]) == 0, res
+        outs.append(d_out[: int(res[0])].cpu().numpy().tobytes())
+        seams.append((int(res[3]) >> 32, int(res[3]) & 0xFFFFFFFF))
+    for g in range(1, k):
+        assert seams[g][0] == seams[g - 1][1], "shard %d did not converge onto its predecessor's end state" % g
+    assert b"".join(outs) == data
+
+
+@pytest.mark.gpu
+def test_shard_restart_from_exact_seam_state():
+    """The fallback of the handshake: a shard decoded again from its predecessor's recorded end state."""
+    import torch
+    data = o.synth_fibonacci(40, 48, 5, 0, 1 << 20)
+    stream, table = o.compress_from_input(data, True)
+    total_bits = (len(stream) - 1) * 8 - (stream[0] & 7)
+    dev = torch.device("cuda", 0)
+    d_pay = torch.zeros(len(stream) - 1 + 64, dtype=torch.uint8, device=dev)
+    d_pay[: len(stream) - 1] = torch.frombuffer(bytearray(stream[1:]), dtype=torch.uint8).to(dev)
+    dectab = mh.DecodeTable(mh.CodingProvider.from_table_file(table))
+    ws = mh.Workspace(len(data), len(stream) + 64)
+    d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+    cut = total_bits // 2 + 5
+    d_a = torch.zeros(len(data), dtype=torch.uint8, device=dev)
+    mh.gpu_decode_shard(d_pay.data_ptr(), 0, cut, d_pay.numel(), True, 0x20, 0, False, dectab, d_a.data_ptr(), d_a.numel(), d_res.data_ptr(), ws)
+    res = d_res.cpu().numpy().view(np.uint64)
+    n_a, end_state = int(res[0]), int(res[3]) & 0xFFFFFFFF
+    start = cut + (end_state >> 8)                                  # first codeword boundary at or after the cut
+    ptr_off = (start // 32) * 4
+    d_b = torch.zeros(len(data), dtype=torch.uint8, device=dev)
+    mh.gpu_decode_shard(d_pay.data_ptr() + ptr_off, start % 32, total_bits - start, d_pay.numel() - ptr_off, True, end_state & 255, 0, True,
+                        dectab, d_b.data_ptr(), d_b.numel(), d_res.data_ptr(), ws)
+    res = d_res.cpu().numpy().view(np.uint64)
+    assert int(res[1]) == 0 and int(res[2]) == 0
+    assert d_a[:n_a].cpu().numpy().tobytes() + d_b[: int(res[0])].cpu().numpy().tobytes() == data
