@@ -16,8 +16,10 @@ Workload at N = 1: BASELINE.json configs[1] — 1 GiB of synthetic order-1 Marko
 Markov mode. At N > 1 each rank holds its own 1 GiB byte range of one logical N GiB stream (weak scaling): shard g
 seeds its histogram and encoder with the last byte of shard g-1, the per-GPU histograms are all-gathered over NCCL
 and summed so every rank builds identical tables, and the per-GPU bit totals (sum of local counts x code lengths) are
-exclusive-scanned so every shard is encoded at its global bit offset. Each shard is then decoded from its own bit
-range.
+exclusive-scanned so every shard is encoded at its global bit offset. Decode treats the shards as ONE stream cut by
+bit ranges: neighbours exchange a ~1 KiB halo, rank 0 starts exactly, every other rank starts a warm-up before its range
+from a guessed state, and the ranks all-gather their seam states until each agrees with its predecessor's end state
+(markov-huffman-coding_b200/sharding.py, mh_gpu_decode_shard).
 
 `--impl reference` runs the unmodified reference (built from /root/reference/src into oracle/_ref by oracle/Makefile)
 through its own CLI on this box's host cores — it has no threads, so one core — on a bounded sample per step.
@@ -247,7 +249,9 @@ def main():
     d_in = torch.empty(n, dtype=torch.uint8, device=dev)
     mh.synth_markov(tc, SEED, SEG_BYTES, rank * (n // SEG_BYTES), d_in.data_ptr(), n, stream)
     payload_cap = n + n // 8 + 4096
-    d_payload = torch.empty(payload_cap, dtype=torch.uint8, device=dev)
+    # the payload sits LOCAL_PAD bytes into a local buffer so that a neighbour's warm-up halo can be spliced in front
+    d_local = torch.zeros(sharding.LOCAL_PAD + payload_cap + 256, dtype=torch.uint8, device=dev)
+    d_payload = d_local[sharding.LOCAL_PAD:]
     d_out = torch.empty(n, dtype=torch.uint8, device=dev)
     d_counts = torch.zeros(65536, dtype=torch.int64, device=dev)
     d_res_enc = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -260,6 +264,7 @@ def main():
     if world > 1:
         last_bytes = torch.zeros(world, dtype=torch.uint8, device=dev)
         gathered = torch.zeros(65536 * world, dtype=torch.int64, device=dev)
+        shard_decoder = sharding.ShardedDecoder(mh, dist, torch, rank, world, 1, dev)
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     state = {}
@@ -297,7 +302,13 @@ def main():
         assert int(h_res[2]) == 0, "encode: capacity"
         assert expect_bits is None or bits == expect_bits, "shard payload size differs from sum(count x length)"
         dectab.update(provider, stream)
-        mh.gpu_decode(d_payload.data_ptr(), bit_base, bits, prev0, dectab, d_out.data_ptr(), n, d_res_dec.data_ptr(), ws, stream)
+        if world > 1:
+            # one stream, decoded by bit ranges: halo exchange, speculative start + warm-up, seam handshake over NCCL
+            got = shard_decoder.decode(d_local, base, shard_bits, dectab, d_out, n, d_res_dec, ws, stream)
+            assert got == n, "sharded decode returned %d symbols" % got
+            state["seam_rounds"] = shard_decoder.rounds
+        else:
+            mh.gpu_decode(d_payload.data_ptr(), bit_base, bits, prev0, dectab, d_out.data_ptr(), n, d_res_dec.data_ptr(), ws, stream)
         h_res[4:].copy_(d_res_dec, non_blocking=True)
         ev[2].record()
         torch.cuda.current_stream().synchronize()
@@ -409,7 +420,8 @@ def main():
         "config": {"workload": WORKLOAD if n == GIB else WORKLOAD.replace("1 GiB", "%d MiB" % (n >> 20)), "bytes_per_gpu": n,
                    "step": "compress (histogram + host trees + encode) then extract (decode); 2 x bytes_per_gpu uncompressed bytes per step and GPU",
                    "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no flush needed", "compressed_ratio": c_bytes / n,
-                   "sharding": "byte-range shards, NCCL all-gather of histograms, exclusive scan of per-GPU bit totals" if world > 1 else "single GPU"},
+                   "sharding": ("encode: byte-range shards, NCCL all-gather of histograms, exclusive scan of per-GPU bit totals; decode: bit-range shards, "
+                                "NCCL halo exchange, speculative start with warm-up, seam handshake (%d extra rounds)" % state.get("seam_rounds", 0)) if world > 1 else "single GPU"},
         "encode_gbs": n * world * args.steps / (t_enc * 1e-3) / 1e9, "decode_gbs": n * world * args.steps / (t_dec * 1e-3) / 1e9,
         "gpu_launches": int(launches), "kernels_ms_per_launch": kern, "phases": phase,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dominant, n),
