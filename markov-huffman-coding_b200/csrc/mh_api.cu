@@ -190,8 +190,11 @@ int mh_table_code_lengths(const mh_table* t, uint8_t* lens, size_t cap) {
 	if(!t || !lens) return MH_ERR_INVALID_ARG;
 	const size_t ntab = t->impl.trees.size();
 	if(cap < ntab * 256) return MH_ERR_CAPACITY;
-	for(size_t k = 0; k < ntab; ++k)
+	memset(lens, 0, ntab * 256);
+	for(size_t k = 0; k < ntab; ++k) {
+		if(t->impl.trees[k].empty()) continue;
 		for(int c = 0; c < 256; ++c) lens[k * 256 + c] = uint8_t(t->impl.trees[k].code[c].length);
+	}
 	return MH_OK;
 }
 

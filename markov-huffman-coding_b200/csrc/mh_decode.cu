@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long
 // D4: final decode + write
 // ---------------------------------------------------------------------------------------------------------
 template <int ORDER>
-__global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
+__global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(   // launched with kDecWriteThreads()
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ state, const uint32_t* __restrict__ count,
     const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits, uint64_t n_subs,
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 		const uint32_t n16 = ORDER ? 65536u : 256u;
 		const uint4* src = reinterpret_cast<const uint4*>(lut_g);
 		uint4* dst = reinterpret_cast<uint4*>(lut_s);
-		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
+		for(uint32_t i = tid; i < n16 / 8; i += blockDim.x) dst[i] = src[i];
 	}
 	__syncthreads();
 	uint32_t lut_sa;
@@ -409,9 +409,21 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 	cur.words = words;
 	cur.n_bytes = buf_bytes;
 	bool clean = true;
-	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-		const uint64_t k = uint64_t(chunk) * chunk_subs + tid;
-		const bool mine = tid < chunk_subs && k < n_subs && k >= skip_subs;
+	// A chunk (the unit D3 scanned) is written in slices of blockDim.x subsequences; fewer resident threads than D1
+	// keep every thread's current payload line in L1.
+	const uint32_t slices = (chunk_subs + blockDim.x - 1) / blockDim.x;
+	for(uint32_t work = blockIdx.x; work < n_chunks * slices; work += gridDim.x) {
+		const uint32_t chunk = work / slices, slice = work - chunk * slices;
+		const uint32_t in_chunk = slice * blockDim.x + tid;
+		const uint64_t k = uint64_t(chunk) * chunk_subs + in_chunk;
+		const bool mine = in_chunk < chunk_subs && k < n_subs && k >= skip_subs;
+		// symbols of the chunk's earlier slices: their counts are summed by every thread's warp-strided pass
+		uint32_t carry = 0;
+		for(uint32_t j = lane; j < slice * blockDim.x; j += 32) {
+			const uint64_t kk = uint64_t(chunk) * chunk_subs + j;
+			if(kk >= skip_subs && kk < n_subs) carry += count[kk];
+		}
+		for(int d = 16; d; d >>= 1) carry += __shfl_xor_sync(0xffffffffu, carry, d);
 		const uint32_t c = mine ? count[k] : 0u;
 		uint32_t incl = c;
 		for(int d = 1; d < 32; d <<= 1) {
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 		}
 		if(lane == 31) warp_tot[warp] = incl;
 		__syncthreads();
-		uint32_t before = 0;
+		uint32_t before = carry;
 		for(uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
 		__syncthreads();
 		if(mine) {
@@ -446,6 +458,12 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(
 }
 
 }  // namespace
+
+static uint32_t decode_write_threads() {
+	const char* env = getenv("MH_DEC_WRITE_THREADS");   // experiments
+	const int v = env ? atoi(env) : 512;
+	return (v >= 64 && v <= kDecThreads && v % 32 == 0) ? uint32_t(v) : 512u;
+}
 
 uint32_t decode_sub_bits(int order) {
 	// Subsequence size: Markov streams re-synchronise ~10x slower than plain Huffman streams, so they
@@ -513,7 +531,10 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	}
 	{
 		ProfScope p("dec_write_kernel", st);
-		dec_write_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, ws->dec_state,
+		const uint32_t wt = decode_write_threads();
+		const uint32_t wslices = (chunk_subs + wt - 1) / wt;
+		const uint64_t wwork = uint64_t(n_chunks) * wslices;
+		dec_write_kernel<ORDER><<<unsigned(wwork < uint64_t(sms) ? wwork : uint64_t(sms)), wt, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, ws->dec_state,
 		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, skip_subs, stream_end, d_result);
 	}
 	count_launch(3);

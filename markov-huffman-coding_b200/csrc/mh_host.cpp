@@ -15,12 +15,14 @@ namespace mh {
 // ------------------------------------------------------------------------------------------------------
 void Codeword::append(int bit) {
 	if(bit) bytes[length >> 3] |= uint8_t(0x80u >> (length & 7));
+	value = (value << 1) | uint64_t(bit & 1);
 	++length;
 }
 
 void Codeword::drop_last() {
 	--length;
 	bytes[length >> 3] &= uint8_t(~(0x80u >> (length & 7)));
+	value >>= 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -84,7 +86,7 @@ void CodeTree::build_from_counts(const int32_t* counts) {
 		nodes.push_back(leaf);
 		heap.push(counts[s], int(nodes.size()) - 1);
 	}
-	if(heap.size() == 0) { derive_codes(); return; }
+	if(heap.size() == 0) return;   // empty table: a freshly constructed CodeTree is already clean
 	while(heap.size() > 1) {
 		int a = heap.pop();
 		int b = heap.pop();
@@ -158,6 +160,7 @@ void CodeTree::derive_codes() {
 
 int CodeTree::max_code_bits() const {
 	int m = 0;
+	if(empty()) return 0;
 	for(const auto& c : code) m = std::max(m, c.length);
 	return m;
 }
@@ -323,15 +326,15 @@ int CodingTable::max_code_bits() const {
 
 int CodingTable::flatten_codebook(uint64_t* enc) const {
 	std::fill(enc, enc + trees.size() * 256, uint64_t(0));
-	for(size_t t = 0; t < trees.size(); ++t)
+	for(size_t t = 0; t < trees.size(); ++t) {
+		if(trees[t].empty()) continue;
 		for(int c = 0; c < 256; ++c) {
 			const Codeword& cw = trees[t].code[c];
 			if(cw.length == 0) continue;
 			if(cw.length > kMaxCodeBitsDevice) return MH_ERR_CODE_TOO_LONG;
-			uint64_t v = 0;
-			for(int i = 0; i < cw.length; ++i) v = (v << 1) | uint64_t(cw.bit(i));
-			enc[t * 256 + c] = (uint64_t(cw.length) << 56) | v;
+			enc[t * 256 + c] = (uint64_t(cw.length) << 56) | cw.value;
 		}
+	}
 	return MH_OK;
 }
 
@@ -339,7 +342,8 @@ void CodingTable::live_range(uint32_t& lo, uint32_t& r) const {
 	int first = 256, last = -1;
 	auto touch = [&](int s) { first = std::min(first, s); last = std::max(last, s); };
 	for(size_t t = 0; t < trees.size(); ++t) {
-		if(order && !trees[t].empty()) touch(int(t));
+		if(trees[t].empty()) continue;
+		if(order) touch(int(t));
 		for(int c = 0; c < 256; ++c)
 			if(trees[t].code[c].length) touch(c);
 	}
@@ -350,10 +354,7 @@ void CodingTable::live_range(uint32_t& lo, uint32_t& r) const {
 
 void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
 	auto entry = [](const Codeword& cw) -> uint32_t {
-		if(cw.length == 0) return 0u;
-		uint32_t v = 0;
-		for(int i = 0; i < cw.length; ++i) v = (v << 1) | uint32_t(cw.bit(i));
-		return (uint32_t(cw.length) << 27) | v;
+		return cw.length ? (uint32_t(cw.length) << 27) | uint32_t(cw.value) : 0u;
 	};
 	if(!order) {
 		for(int c = 0; c < 256; ++c) box[c] = entry(trees[0].code[c]);
@@ -361,8 +362,10 @@ void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
 	}
 	const uint32_t pitch = r + 1;
 	std::fill(box, box + size_t(pitch) * pitch, 0u);
-	for(uint32_t p = 0; p < r; ++p)
+	for(uint32_t p = 0; p < r; ++p) {
+		if(trees[lo + p].empty()) continue;
 		for(uint32_t c = 0; c < r; ++c) box[p * pitch + c] = entry(trees[lo + p].code[lo + c]);
+	}
 }
 
 void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {

@@ -31,6 +31,7 @@ struct TreeNode {
 // A codeword of up to 255 bits, MSB-first (bit i of the codeword is bit 7 - i%8 of bytes[i/8]).
 struct Codeword {
 	int length = 0;
+	uint64_t value = 0;   // the codeword as an integer (MSB-first reading); meaningful while length <= 64
 	std::array<uint8_t, 32> bytes{};
 	void append(int bit);
 	void drop_last();
