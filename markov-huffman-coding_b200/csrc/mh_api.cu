@@ -178,7 +178,7 @@ int mh_table_context_empty(const mh_table* t, int prev) {
 
 int mh_table_code(const mh_table* t, int prev, int c, uint8_t bits[32], int* len) {
 	if(!t || !len || prev < 0 || prev > 255 || c < 0 || c > 255) return MH_ERR_INVALID_ARG;
-	const Codeword& cw = t->impl.tree_for(prev).code[c];
+	const Codeword& cw = t->impl.tree_for(prev).code(c);
 	*len = cw.length;
 	if(bits) memcpy(bits, cw.bytes.data(), 32);
 	return MH_OK;
@@ -193,7 +193,7 @@ int mh_table_code_lengths(const mh_table* t, uint8_t* lens, size_t cap) {
 	memset(lens, 0, ntab * 256);
 	for(size_t k = 0; k < ntab; ++k) {
 		if(t->impl.trees[k].empty()) continue;
-		for(int c = 0; c < 256; ++c) lens[k * 256 + c] = uint8_t(t->impl.trees[k].code[c].length);
+		for(int c = 0; c < 256; ++c) lens[k * 256 + c] = uint8_t(t->impl.trees[k].code(c).length);
 	}
 	return MH_OK;
 }
@@ -201,7 +201,7 @@ int mh_table_code_lengths(const mh_table* t, uint8_t* lens, size_t cap) {
 int mh_table_lookup(const mh_table* t, int prev, int window, int* kind, int* value, int* depth) {
 	if(!t || prev < 0 || prev > 255 || window < 0 || window > 255 || !kind || !value || !depth) return MH_ERR_INVALID_ARG;
 	const CodeTree& tr = t->impl.tree_for(prev);
-	const int n = tr.lut[window];
+	const int n = tr.lut(window);
 	if(n == kNoChild) { *kind = 0; *value = 0; *depth = 0; return MH_OK; }
 	*kind = tr.nodes[n].internal ? 2 : 1;
 	*value = tr.nodes[n].symbol;

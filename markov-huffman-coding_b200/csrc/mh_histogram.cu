@@ -20,7 +20,7 @@ namespace {
 
 constexpr int kHistThreads = 512;
 constexpr int kHistWarps = kHistThreads / 32;
-constexpr int kProbeThreads = 1024;
+constexpr int kProbeThreads = 256;
 constexpr int kProbeWindows = 64;
 constexpr int kProbeWindowBytes = 4096;
 
@@ -30,53 +30,62 @@ __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
 	return r;
 }
 
-// params: [0] lo, [1] R, [2] replicas
+// Probe: kProbeWindows CTAs each mark the byte values present in one 4 KiB window spread over the input; the
+// result is a 256-bit presence bitmap in params[0..7] (zeroed by the launcher).
 __global__ void __launch_bounds__(kProbeThreads) hist_probe_kernel(const uint8_t* __restrict__ in, uint64_t n,
-                                                                    uint32_t* __restrict__ params, uint32_t smem_words) {
-	__shared__ uint32_t present[8];
-	if(threadIdx.x < 8) present[threadIdx.x] = 0;
-	__syncthreads();
+                                                                    uint32_t* __restrict__ params) {
 	const uint64_t windows = n < uint64_t(kProbeWindows) * kProbeWindowBytes ? 1 : kProbeWindows;
+	if(blockIdx.x >= windows) return;
 	const uint64_t stride = windows > 1 ? (n - kProbeWindowBytes) / (windows - 1) : 0;
 	const uint64_t wbytes = windows > 1 ? kProbeWindowBytes : n;
 	uint32_t mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-	for(uint64_t w = 0; w < windows; ++w)
-		for(uint64_t i = threadIdx.x; i < wbytes; i += kProbeThreads) {
-			const uint32_t b = in[w * stride + i];
+	for(uint64_t i = threadIdx.x; i < wbytes; i += kProbeThreads) {
+		const uint32_t b = in[blockIdx.x * stride + i];
 #pragma unroll
-			for(int k = 0; k < 8; ++k) mine[k] |= (b >> 5) == uint32_t(k) ? (1u << (b & 31)) : 0u;
-		}
+		for(int k = 0; k < 8; ++k) mine[k] |= (b >> 5) == uint32_t(k) ? (1u << (b & 31)) : 0u;
+	}
 #pragma unroll
 	for(int k = 0; k < 8; ++k) {
-		uint32_t v = __reduce_or_sync(0xffffffffu, mine[k]);
-		if((threadIdx.x & 31) == 0 && v) atomicOr(&present[k], v);
+		const uint32_t v = __reduce_or_sync(0xffffffffu, mine[k]);
+		if((threadIdx.x & 31) == 0 && v) atomicOr(&params[k], v);
 	}
-	__syncthreads();
-	if(threadIdx.x == 0) {
-		int lo = 256, hi = -1;
-		for(int b = 0; b < 256; ++b)
-			if(present[b >> 5] >> (b & 31) & 1) { if(lo > b) lo = b; hi = b; }
-		if(hi < 0) { lo = 0; hi = 0; }
-		uint32_t range = uint32_t(hi - lo + 1);
-		uint32_t rmax = 1;
-		while((rmax + 1) * (rmax + 1) <= smem_words) ++rmax;
-		if(range > rmax) range = rmax;
-		uint32_t reps = smem_words / (range * range);
-		if(reps > uint32_t(kHistWarps)) reps = kHistWarps;
-		params[0] = uint32_t(lo);
-		params[1] = range;
-		params[2] = reps;
+}
+
+// From the presence bitmap: the byte range [lo, lo + R) to keep in shared memory and how often to replicate it.
+__device__ __forceinline__ void hist_plan(const uint32_t* __restrict__ params, uint32_t smem_words, uint32_t& lo_out,
+                                          uint32_t& r_out, uint32_t& reps_out) {
+	int lo = 256, hi = -1;
+	for(int k = 0; k < 8; ++k) {
+		const uint32_t w = params[k];
+		if(!w) continue;
+		if(lo == 256) lo = 32 * k + (__ffs(w) - 1);
+		hi = 32 * k + (31 - __clz(w));
 	}
+	if(hi < 0) { lo = 0; hi = 0; }
+	uint32_t range = uint32_t(hi - lo + 1);
+	uint32_t rmax = 1;
+	while((rmax + 1) * (rmax + 1) <= smem_words) ++rmax;
+	if(range > rmax) range = rmax;
+	uint32_t reps = smem_words / (range * range);
+	if(reps > uint32_t(kHistWarps)) reps = kHistWarps;
+	lo_out = uint32_t(lo);
+	r_out = range;
+	reps_out = reps;
 }
 
 template <int ORDER>
 __global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t prev0,
                                                              unsigned long long* __restrict__ counts,
-                                                             const uint32_t* __restrict__ params) {
+                                                             const uint32_t* __restrict__ params, uint32_t smem_words) {
 	extern __shared__ uint32_t sh[];
-	const uint32_t lo = ORDER ? params[0] : 0u;
-	const uint32_t R = ORDER ? params[1] : 256u;
-	const uint32_t reps = ORDER ? params[2] : uint32_t(kHistWarps);
+	__shared__ uint32_t s_plan[3];
+	if(ORDER) {
+		if(threadIdx.x == 0) hist_plan(params, smem_words, s_plan[0], s_plan[1], s_plan[2]);
+		__syncthreads();
+	}
+	const uint32_t lo = ORDER ? s_plan[0] : 0u;
+	const uint32_t R = ORDER ? s_plan[1] : 256u;
+	const uint32_t reps = ORDER ? s_plan[2] : uint32_t(kHistWarps);
 	const uint32_t box = ORDER ? R * R : 256u;
 	for(uint32_t i = threadIdx.x; i < reps * box; i += kHistThreads) sh[i] = 0;
 	__syncthreads();
@@ -164,17 +173,18 @@ int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, 
 			attr_done = true;
 		}
 		{
+			MH_CUDA(cudaMemsetAsync(ws->hist_params, 0, 8 * sizeof(uint32_t), st));
 			ProfScope p("hist_probe_kernel", st);
-			hist_probe_kernel<<<1, kProbeThreads, 0, st>>>(d_in, n, ws->hist_params, smem_bytes / 4);
+			hist_probe_kernel<<<kProbeWindows, kProbeThreads, 0, st>>>(d_in, n, ws->hist_params);
 		}
 		{
 			ProfScope p("hist_kernel<1>", st);
-			hist_kernel<1><<<unsigned(grid), kHistThreads, smem_bytes, st>>>(d_in, n, prev0, d_counts, ws->hist_params);
+			hist_kernel<1><<<unsigned(grid), kHistThreads, smem_bytes, st>>>(d_in, n, prev0, d_counts, ws->hist_params, smem_bytes / 4);
 		}
 		count_launch(2);
 	} else {
 		ProfScope p("hist_kernel<0>", st);
-		hist_kernel<0><<<unsigned(grid), kHistThreads, kHistWarps * 256 * 4, st>>>(d_in, n, prev0, d_counts, ws->hist_params);
+		hist_kernel<0><<<unsigned(grid), kHistThreads, kHistWarps * 256 * 4, st>>>(d_in, n, prev0, d_counts, ws->hist_params, 0u);
 		count_launch(1);
 	}
 	MH_CUDA(cudaGetLastError());

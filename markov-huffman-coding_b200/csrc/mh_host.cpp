@@ -117,9 +117,12 @@ void CodeTree::build_from_counts(const int32_t* counts) {
 }
 
 void CodeTree::derive_codes() {
-	for(auto& c : code) c = Codeword{};
-	lut.fill(kNoChild);
+	derived.reset();
 	if(root == kNoChild) return;
+	derived.reset(new Derived());
+	auto& code = derived->code;
+	auto& lut = derived->lut;
+	lut.fill(kNoChild);
 	// Iterative pre-order walk, left edge = 0, right edge = 1 (src/huffman.cpp:97-123). `stage` per frame:
 	// 0 = entering, 1 = left subtree done, 2 = right subtree done.
 	struct Frame { int node; int stage; };
@@ -161,7 +164,7 @@ void CodeTree::derive_codes() {
 int CodeTree::max_code_bits() const {
 	int m = 0;
 	if(empty()) return 0;
-	for(const auto& c : code) m = std::max(m, c.length);
+	for(const auto& c : derived->code) m = std::max(m, c.length);
 	return m;
 }
 
@@ -270,7 +273,8 @@ int CodingTable::from_counts(const uint64_t* counts, int order, CodingTable& out
 	if(order != 0 && order != 1) return MH_ERR_INVALID_ARG;
 	out.order = order;
 	const int ntab = order ? 256 : 1;
-	out.trees.assign(ntab, CodeTree());
+	out.trees.clear();
+	out.trees.resize(ntab);
 	for(int t = 0; t < ntab; ++t) {
 		int32_t c32[256];
 		for(int s = 0; s < 256; ++s) {
@@ -288,7 +292,8 @@ int CodingTable::from_bytes(const uint8_t* bytes, size_t n, CodingTable& out) {
 	BitSource src(bytes, n);
 	const bool markov = (bytes[0] & 0x80) != 0;               // peek_bit (src/main.cpp:147)
 	out.order = markov ? 1 : 0;
-	out.trees.assign(markov ? 256 : 1, CodeTree());
+	out.trees.clear();
+	out.trees.resize(markov ? 256 : 1);
 	if(markov) {
 		src.bit();                                            // kind marker (src/markov_huffman.cpp:17)
 		for(int p = 0; p < 256; ++p) {
@@ -329,7 +334,7 @@ int CodingTable::flatten_codebook(uint64_t* enc) const {
 	for(size_t t = 0; t < trees.size(); ++t) {
 		if(trees[t].empty()) continue;
 		for(int c = 0; c < 256; ++c) {
-			const Codeword& cw = trees[t].code[c];
+			const Codeword& cw = trees[t].code(c);
 			if(cw.length == 0) continue;
 			if(cw.length > kMaxCodeBitsDevice) return MH_ERR_CODE_TOO_LONG;
 			enc[t * 256 + c] = (uint64_t(cw.length) << 56) | cw.value;
@@ -345,7 +350,7 @@ void CodingTable::live_range(uint32_t& lo, uint32_t& r) const {
 		if(trees[t].empty()) continue;
 		if(order) touch(int(t));
 		for(int c = 0; c < 256; ++c)
-			if(trees[t].code[c].length) touch(c);
+			if(trees[t].code(c).length) touch(c);
 	}
 	if(last < 0) { lo = 0; r = 1; return; }
 	lo = uint32_t(first);
@@ -357,14 +362,14 @@ void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
 		return cw.length ? (uint32_t(cw.length) << 27) | uint32_t(cw.value) : 0u;
 	};
 	if(!order) {
-		for(int c = 0; c < 256; ++c) box[c] = entry(trees[0].code[c]);
+		for(int c = 0; c < 256; ++c) box[c] = entry(trees[0].code(c));
 		return;
 	}
 	const uint32_t pitch = r + 1;
 	std::fill(box, box + size_t(pitch) * pitch, 0u);
 	for(uint32_t p = 0; p < r; ++p) {
 		if(trees[lo + p].empty()) continue;
-		for(uint32_t c = 0; c < r; ++c) box[p * pitch + c] = entry(trees[lo + p].code[lo + c]);
+		for(uint32_t c = 0; c < r; ++c) box[p * pitch + c] = entry(trees[lo + p].code(lo + c));
 	}
 }
 
@@ -375,7 +380,7 @@ void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
 		const CodeTree& tr = trees[t];
 		if(tr.empty()) continue;
 		for(int w = 0; w < 256; ++w) {
-			const int n = tr.lut[w];
+			const int n = tr.lut(w);
 			if(n == kNoChild) continue;
 			const TreeNode& nd = tr.nodes[n];
 			lut[t * 256 + w] = nd.internal ? uint16_t((n << 7) | kLutDeep) : uint16_t((nd.symbol << 8) | nd.depth);
@@ -417,7 +422,7 @@ std::string printable(uint8_t c) {     // charv(): the escapes are doubled becau
 void dump_codes(const CodeTree& t, std::string& out) {
 	out += "Table:\n";
 	for(int c = 0; c < 256; ++c) {
-		const Codeword& cw = t.code[c];
+		const Codeword& cw = t.code(c);
 		if(!cw.length) continue;
 		out += printable(uint8_t(c)) + " " + std::to_string(cw.length) + " ";
 		for(int i = 0; i < cw.length; ++i) out += char('0' + cw.bit(i));

@@ -10,6 +10,7 @@
 #include <array>
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -43,11 +44,16 @@ class CodeTree {
 public:
 	std::vector<TreeNode> nodes;
 	int root = kNoChild;
-	std::array<Codeword, 256> code;     // code[c].length == 0: no codeword
-	std::array<int, 256> lut;           // node index per 8-bit window, kNoChild = null
+	// Derived tables exist only for non-empty trees (a Markov table has 256 trees, most of them empty for text).
+	struct Derived {
+		std::array<Codeword, 256> code;   // code[c].length == 0: no codeword
+		std::array<int, 256> lut;         // node index per 8-bit window, kNoChild = null
+	};
+	std::unique_ptr<Derived> derived;
 
-	CodeTree() { lut.fill(kNoChild); }
 	bool empty() const { return root == kNoChild; }
+	const Codeword& code(int c) const { static const Codeword none; return derived ? derived->code[c] : none; }
+	int lut(int window) const { return derived ? derived->lut[window] : kNoChild; }
 	int max_code_bits() const;
 
 	// counts are the reference's ints (already truncated to int32 by the caller)
