@@ -19,7 +19,7 @@
 //      quad goes out as two pairs) and funnelled through a 96-bit window; only completed 32-bit words are ORed
 //      into the zeroed shared-memory staging area (neighbouring threads share their boundary words, hence the OR);
 //   4. warp 0 publishes the tile's last 31 bits and resolves the tile's global bit offset by a warp-wide
-//      decoupled look-back (128 predecessors per poll, relaxed loads that bypass L1). The tile that ends a
+//      decoupled look-back (32 predecessors per poll, relaxed loads that bypass L1). The tile that ends a
 //      partially filled 32-bit output word writes it, using the predecessor's published tail bits — so every
 //      output word has exactly one writer: no pre-zeroed output, no global atomics, no second pass;
 //   5. the staged bits are funnel-shifted by the tile's global bit phase and written with coalesced 32-bit
@@ -105,10 +105,10 @@ struct EncArgs {
 	uint32_t n_tiles;
 };
 
-// Warp-wide decoupled look-back over a window of kWin x 32 predecessors per poll. All 32 lanes of warp 0 call this.
+// Warp-wide decoupled look-back over a window of kWin x 32 predecessors per poll (one warp-load measured best). All 32 lanes of warp 0 call this.
 // Returns, on every lane, the number of bits that precede this tile and the bit count of tile - 1; publishes the
 // tile's inclusive prefix.
-constexpr int kWin = 4;
+constexpr int kWin = 1;
 
 __device__ __forceinline__ void look_back(uint32_t tile, uint32_t own_bits, const EncArgs& A, unsigned long long& excl_bits,
                                           uint32_t& nearest_bits) {
