@@ -150,6 +150,9 @@ uint32_t mh_decode_subsequence_bits(int order);
 typedef struct mh_session mh_session;
 
 int mh_session_create(int device, uint64_t max_input_bytes, mh_session** out);
+/* Same with an explicit bound for the compressed side (stream bytes), e.g. for a session that only extracts: the
+ * decoded size is not stored in the stream, so the uncompressed-side buffer grows on demand during decompress. */
+int mh_session_create_sized(int device, uint64_t max_input_bytes, uint64_t max_stream_bytes, mh_session** out);
 void mh_session_destroy(mh_session* s);
 
 /* `markovhuffman in -o out [-h] -d table` minus the file I/O: histogram -> tables -> encode.
@@ -162,9 +165,12 @@ int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
 int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n,
                                    uint8_t* out, uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped);
 /* `markovhuffman in -o out -x -e table`: header checks (src/coding.cpp:100-116) then decode.
- * Call with out == NULL to get the decoded size in *out_len without writing. */
+ * Call with out == NULL to decode on the device and get the size in *out_len; mh_session_fetch then delivers it. */
 int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* stream, uint64_t stream_len,
                           uint8_t* out, uint64_t out_capacity, uint64_t* out_len);
+/* Copies the bytes decoded by the last mh_session_decompress(out == NULL) call to the host: the size query and the
+ * fetch then cost one decode, not two. */
+int mh_session_fetch(mh_session* s, uint8_t* out, uint64_t out_capacity, uint64_t* out_len);
 /* Histogram only (host buffer in, host counts out): construct_table on the device. */
 int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order, uint64_t* counts);
 

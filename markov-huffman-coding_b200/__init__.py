@@ -85,6 +85,8 @@ _SIGNATURES = {
     "mh_gpu_decode_shard": (_i, [_vp, ctypes.c_uint32, _u64, _u64, _i, _u8, ctypes.c_uint32, _i, _vp, _vp, _u64, _vp, _vp, _vp]),
     "mh_decode_subsequence_bits": (ctypes.c_uint32, [_i]),
     "mh_session_create": (_i, [_i, _u64, _pp]),
+    "mh_session_create_sized": (_i, [_i, _u64, _u64, _pp]),
+    "mh_session_fetch": (_i, [_vp, _vp, _u64, _pu64]),
     "mh_session_destroy": (None, [_vp]),
     "mh_session_compress": (_i, [_vp, _vp, _u64, _i, _vp, _u64, _pu64, _pp]),
     "mh_session_compress_with_table": (_i, [_vp, _vp, _vp, _u64, _vp, _u64, _pu64, _pu64]),
@@ -292,9 +294,13 @@ class Session:
         import numpy as np
         keep, addr, n = _as_buffer(stream)
         out_len = ctypes.c_uint64(0)
-        _check(_lib.mh_session_decompress(self._h, provider._h, addr, n, None, 0, ctypes.byref(out_len)), "mh_session_decompress(size)")
+        rc = _lib.mh_session_decompress(self._h, provider._h, addr, n, None, 0, ctypes.byref(out_len))   # decode on the device, learn the size
+        if rc not in (MH_OK, MH_ERR_CORRUPT_STREAM):
+            raise MhError(rc, "mh_session_decompress")
         buf = np.empty(max(1, out_len.value), dtype=np.uint8)
-        _check(_lib.mh_session_decompress(self._h, provider._h, addr, n, buf.ctypes.data, buf.size, ctypes.byref(out_len)), "mh_session_decompress")
+        _check(_lib.mh_session_fetch(self._h, buf.ctypes.data, buf.size, ctypes.byref(out_len)), "mh_session_fetch")
+        if rc != MH_OK:
+            raise MhError(rc, "mh_session_decompress")
         return buf[: out_len.value].tobytes()
 
 

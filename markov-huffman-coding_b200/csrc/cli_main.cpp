@@ -171,11 +171,10 @@ int main(int argc, char* argv[]) {
 		if(rc != MH_OK) die_status("loading the encoding table", rc);
 	}
 
-	// device buffers: the uncompressed side bounds the session. For -x the decoded size is unknown until the count
-	// pass; every symbol costs at least one bit, so 8x the payload is a safe bound and the usual ratio needs far less.
-	uint64_t raw_bound = in_bytes.size();
-	if(extract) raw_bound = in_bytes.size() * 8 + 64;
-	int rc = mh_session_create(0, raw_bound + 64, &session);
+	// Device buffers. Compressing: the input bounds both sides. Extracting: the stream bounds the compressed side; the
+	// decoded size is not stored in the stream, so the session grows its uncompressed-side buffer after the count pass.
+	int rc = extract ? mh_session_create_sized(0, in_bytes.size() * 3 + 4096, in_bytes.size() + 64, &session)
+	                 : mh_session_create(0, in_bytes.size() + 64, &session);
 	if(rc != MH_OK) die_status("creating the GPU session", rc);
 
 	bool built_here = false;
@@ -221,11 +220,11 @@ int main(int argc, char* argv[]) {
 	if(extract) {
 		eprintf("Extracting %s ===> %s...\n", input, shown(output));
 		uint64_t n_out = 0;
-		rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), nullptr, 0, &n_out);
+		rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), nullptr, 0, &n_out);   // decode, learn the size
 		if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
 		result.resize(n_out ? n_out : 1);
-		rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), result.data(), result.size(), &n_out);
-		if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
+		rc = mh_session_fetch(session, result.data(), result.size(), &n_out);
+		if(rc != MH_OK) die_status("extracting", rc);
 		result.resize(n_out);
 		if(n_out && fwrite(result.data(), 1, n_out, output_fd) != n_out) {
 			eprintf("Error occurred while writing file.\n");

@@ -397,8 +397,9 @@ uint32_t mh_decode_subsequence_bits(int order) { return decode_sub_bits(order); 
 struct mh_session {
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	uint64_t max_input = 0;
+	uint64_t max_input = 0;      // capacity of d_raw (grows on demand when extracting)
 	uint64_t payload_cap = 0;
+	uint64_t pending_out = 0;    // decoded bytes waiting in d_raw for mh_session_fetch
 	uint8_t* d_raw = nullptr;       // uncompressed side
 	uint8_t* d_payload = nullptr;   // compressed side (no header byte)
 	uint64_t* d_counts = nullptr;   // [65536]
@@ -413,6 +414,12 @@ struct mh_session {
 extern "C" {
 
 int mh_session_create(int device, uint64_t max_input_bytes, mh_session** out) {
+	// An optimal prefix code built from the data's own counts never averages more than 8 bits per byte; a foreign
+	// -e table can expand, which is reported as MH_ERR_CAPACITY rather than silently truncated.
+	return mh_session_create_sized(device, max_input_bytes, max_input_bytes + (max_input_bytes >> 3) + 4096, out);
+}
+
+int mh_session_create_sized(int device, uint64_t max_input_bytes, uint64_t max_stream_bytes, mh_session** out) {
 	if(!out) return MH_ERR_INVALID_ARG;
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -423,9 +430,7 @@ int mh_session_create(int device, uint64_t max_input_bytes, mh_session** out) {
 	if(!s) return MH_ERR_INVALID_ARG;
 	s->device = device;
 	s->max_input = max_input_bytes;
-	// An optimal prefix code built from the data's own counts never averages more than 8 bits per byte; a foreign
-	// -e table can expand, which is reported as MH_ERR_CAPACITY rather than silently truncated.
-	s->payload_cap = ((max_input_bytes + (max_input_bytes >> 3) + 4096 + 15) / 16) * 16;
+	s->payload_cap = ((max_stream_bytes + 64 + 15) / 16) * 16;
 	auto fail = [&](int rc) { mh_session_destroy(s); return rc; };
 #define S_CUDA(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(cuda_fail(e_, #call)); } while(0)
 	S_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -462,6 +467,7 @@ void mh_session_destroy(mh_session* s) {
 int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order, uint64_t* counts) {
 	if(!s || !counts || (!in && n)) return MH_ERR_INVALID_ARG;
 	if(n > s->max_input) return MH_ERR_CAPACITY;
+	s->pending_out = 0;
 	MH_CUDA(cudaSetDevice(s->device));
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
@@ -503,6 +509,7 @@ int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
                         uint64_t* out_len, mh_table** table_out) {
 	if(!s || !out || !out_len || (!in && n) || (order != 0 && order != 1)) return MH_ERR_INVALID_ARG;
 	if(n > s->max_input) return MH_ERR_CAPACITY;
+	s->pending_out = 0;
 	MH_CUDA(cudaSetDevice(s->device));
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
@@ -523,6 +530,7 @@ int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8
                                    uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped) {
 	if(!s || !t || !out || !out_len || (!in && n)) return MH_ERR_INVALID_ARG;
 	if(n > s->max_input) return MH_ERR_CAPACITY;
+	s->pending_out = 0;
 	MH_CUDA(cudaSetDevice(s->device));
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	return session_encode(s, t, n, out, out_capacity, out_len, dropped);
@@ -544,26 +552,46 @@ int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* strea
 	int rc = upload_dectable(t, &s->dec, s->stream);
 	if(rc != MH_OK) return rc;
 	if(payload_bytes) MH_CUDA(cudaMemcpyAsync(s->d_payload, stream + 1, payload_bytes, cudaMemcpyHostToDevice, s->stream));
-	const uint64_t dev_cap = s->max_input;
 	int iters = 2;
+	s->pending_out = 0;
 	for(;;) {
-		rc = launch_decode(s->d_payload, 0, n_bits, MH_PREV0, &s->dec, s->d_raw, dev_cap,
+		rc = launch_decode(s->d_payload, 0, n_bits, MH_PREV0, &s->dec, s->d_raw, s->max_input,
 		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
 		if(rc != MH_OK) return rc;
 		MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
 		MH_CUDA(cudaStreamSynchronize(s->stream));
-		if(int64_t(s->h_result[1]) == MH_ERR_NOT_CONVERGED && iters < 8) { iters = 8; continue; }
+		const int64_t dev_status = int64_t(s->h_result[1]);
+		if(dev_status == MH_ERR_NOT_CONVERGED && iters < (1 << 20)) { iters *= 4; continue; }   // pathological seams: keep fixing
+		if(dev_status == MH_ERR_CAPACITY) {
+			// the decoded size is only known after the count pass: grow the device buffer to fit and decode again
+			const uint64_t need = s->h_result[0];
+			cudaFree(s->d_raw);
+			s->d_raw = nullptr;
+			s->max_input = 0;
+			MH_CUDA(cudaMalloc(&s->d_raw, need + 64));
+			s->max_input = need;
+			continue;
+		}
 		break;
 	}
 	*out_len = s->h_result[0];
 	if(int64_t(s->h_result[1]) != 0) return int(int64_t(s->h_result[1]));
-	if(!out) return MH_OK;
-	if(s->h_result[0] > out_capacity) return MH_ERR_CAPACITY;
-	if(s->h_result[0]) {
-		MH_CUDA(cudaMemcpyAsync(out, s->d_raw, s->h_result[0], cudaMemcpyDeviceToHost, s->stream));
+	s->pending_out = s->h_result[0];
+	const int corrupt = int(int64_t(s->h_result[2]));   // bytes are delivered, like the reference, but flagged
+	if(!out) return corrupt;
+	rc = mh_session_fetch(s, out, out_capacity, out_len);
+	return rc != MH_OK ? rc : corrupt;
+}
+
+int mh_session_fetch(mh_session* s, uint8_t* out, uint64_t out_capacity, uint64_t* out_len) {
+	if(!s || !out_len || (!out && s->pending_out)) return MH_ERR_INVALID_ARG;
+	*out_len = s->pending_out;
+	if(s->pending_out > out_capacity) return MH_ERR_CAPACITY;
+	MH_CUDA(cudaSetDevice(s->device));
+	if(s->pending_out) {
+		MH_CUDA(cudaMemcpyAsync(out, s->d_raw, s->pending_out, cudaMemcpyDeviceToHost, s->stream));
 		MH_CUDA(cudaStreamSynchronize(s->stream));
 	}
-	if(int64_t(s->h_result[2]) != 0) return int(int64_t(s->h_result[2]));   // bytes are delivered, like the reference, but flagged
 	return MH_OK;
 }
 

@@ -511,13 +511,14 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	int last_flag = -1;
 	if(n_chunks > 1) {
 		if(fix_iters < 1) fix_iters = 1;
-		if(fix_iters > 8) fix_iters = 8;
 		for(int it = 0; it < fix_iters; ++it) {
+			const int slot = it & 7;   // the flag slots are reused round-robin
+			if(it >= 8) MH_CUDA(cudaMemsetAsync(ws->dec_flags + slot, 0, sizeof(uint32_t), st));
 			ProfScope p("dec_seam_kernel", st);
 			dec_seam_kernel<ORDER><<<(n_chunks - 1 + 127) / 128, 128, 0, st>>>(words, n_bits, buf_bytes, dt->d_lut, dt->d_walk, ws->dec_state,
-			    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, chunk_subs, start0 >> 8, ws->dec_flags + it);
+			    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, chunk_subs, start0 >> 8, ws->dec_flags + slot);
 			count_launch(1);
-			last_flag = it;
+			last_flag = slot;
 		}
 	}
 	{
