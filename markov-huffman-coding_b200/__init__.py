@@ -159,7 +159,7 @@ class CodingProvider:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None:
             _lib.mh_table_destroy(h)
             self._h = None
 
@@ -254,7 +254,7 @@ class Session:
         self.max_input_bytes = int(max_input_bytes)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.mh_session_destroy(self._h)
             self._h = None
 
@@ -338,7 +338,7 @@ class Workspace:
         self._h = out
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.mh_workspace_destroy(self._h)
             self._h = None
 
@@ -355,7 +355,7 @@ class Codebook:
         _check(_lib.mh_codebook_update(self._h, provider._h, stream or None), "mh_codebook_update")
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.mh_codebook_destroy(self._h)
             self._h = None
 
@@ -372,7 +372,7 @@ class DecodeTable:
         _check(_lib.mh_dectable_update(self._h, provider._h, stream or None), "mh_dectable_update")
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:
             _lib.mh_dectable_destroy(self._h)
             self._h = None
 

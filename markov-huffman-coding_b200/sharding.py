@@ -15,7 +15,10 @@ import numpy as np
 
 def global_counts(all_counts):
     """all_counts: uint64 [world, bins] (all-gathered local histograms) -> uint64 [bins]."""
-    return np.ascontiguousarray(np.asarray(all_counts, dtype=np.uint64).sum(axis=0, dtype=np.uint64))
+    a = np.asarray(all_counts, dtype=np.uint64)
+    if a.ndim == 1 or a.shape[0] == 1:
+        return np.ascontiguousarray(a.reshape(-1))
+    return np.ascontiguousarray(a.sum(axis=0, dtype=np.uint64))
 
 
 def shard_bits(all_counts, code_lengths):
