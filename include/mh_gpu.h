@@ -128,19 +128,20 @@ int mh_gpu_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uin
 /* Decoding ONE stream on several GPUs by bit ranges. A shard decodes the bits
  * [start_bit, start_bit + n_bits) of d_bits (start_bit in 0..31; d_bits 4-byte aligned; buf_bytes readable bytes, which
  * must include a few bytes past the range so the last codeword can complete). Shard 0 knows its state
- * (exact_start = 1, prev0); every other shard starts skip_subsequences x mh_decode_subsequence_bits() bits BEFORE the
- * first bit it owns, guesses, and lets the self-synchronising decode converge over that warm-up, whose symbols it
- * does not emit. d_result is 4 x uint64: [0] symbols this shard owns (written to d_out from offset 0), [1]/[2] as
+ * (exact_start = 1, prev0, warm_bits = 0); every other shard starts warm_bits (a multiple of MH_DECODE_WARM_UNIT,
+ * included in n_bits) BEFORE the first bit it owns, guesses, and lets the self-synchronising decode converge over
+ * that warm-up, whose symbols it does not emit. d_result is 4 x uint64: [0] symbols this shard owns (written to d_out from offset 0), [1]/[2] as
  * mh_gpu_decode, [3] = seam words: bits 63..32 the decoder state at the ownership start as the warm-up found it,
  * bits 31..0 the state at the range end; a state is (bits past the boundary << 8 | previous symbol).
  * The handshake: shard g is consistent when its start word equals shard g-1's end word; otherwise it is decoded
  * again with exact_start = 1 from that state (rare: the warm-up is several synchronisation distances long).
  * stream_end = 1 on the last shard enables the "last codeword ends exactly at the payload end" check. */
 int mh_gpu_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start,
-                        uint8_t prev0, uint32_t skip_subsequences, int stream_end, const mh_dectable* dt, uint8_t* d_out,
+                        uint8_t prev0, uint32_t warm_bits, int stream_end, const mh_dectable* dt, uint8_t* d_out,
                         uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream);
-/* Subsequence size (bits) the decoder uses for this coder type. */
-uint32_t mh_decode_subsequence_bits(int order);
+#define MH_DECODE_WARM_UNIT 8192   /* every subsequence size the decoder picks divides this */
+/* Subsequence size (bits) the decoder picks for a stream of n_bits of this coder type. */
+uint32_t mh_decode_subsequence_bits(int order, uint64_t n_bits);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Host-buffer calls: what a maintainer binds in place of compress(FILE*, FILE*) / decompress(FILE*, FILE*)

@@ -83,7 +83,7 @@ _SIGNATURES = {
     "mh_gpu_encode": (_i, [_vp, _u64, _u8, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "mh_gpu_decode": (_i, [_vp, _u64, _u64, _u8, _vp, _vp, _u64, _vp, _vp, _vp]),
     "mh_gpu_decode_shard": (_i, [_vp, ctypes.c_uint32, _u64, _u64, _i, _u8, ctypes.c_uint32, _i, _vp, _vp, _u64, _vp, _vp, _vp]),
-    "mh_decode_subsequence_bits": (ctypes.c_uint32, [_i]),
+    "mh_decode_subsequence_bits": (ctypes.c_uint32, [_i, _u64]),
     "mh_session_create": (_i, [_i, _u64, _pp]),
     "mh_session_create_sized": (_i, [_i, _u64, _u64, _pp]),
     "mh_session_fetch": (_i, [_vp, _vp, _u64, _pu64]),
@@ -400,11 +400,14 @@ def synth_fibonacci(k, base, seed, first_index, d_out, n, stream=0):
     _check(_lib.mh_synth_fibonacci(k, base, seed, first_index, d_out, n, stream or None), "mh_synth_fibonacci")
 
 
-def gpu_decode_shard(d_bits, start_bit, n_bits, buf_bytes, exact_start, prev0, skip_subsequences, stream_end, dectable, d_out,
+DECODE_WARM_UNIT = 8192
+
+
+def gpu_decode_shard(d_bits, start_bit, n_bits, buf_bytes, exact_start, prev0, warm_bits, stream_end, dectable, d_out,
                      out_capacity, d_result, ws, stream=0):
-    _check(_lib.mh_gpu_decode_shard(d_bits, start_bit, n_bits, buf_bytes, int(exact_start), prev0, skip_subsequences, int(stream_end),
+    _check(_lib.mh_gpu_decode_shard(d_bits, start_bit, n_bits, buf_bytes, int(exact_start), prev0, warm_bits, int(stream_end),
                                     dectable._h, d_out, out_capacity, d_result, ws._h, stream or None), "mh_gpu_decode_shard")
 
 
-def decode_subsequence_bits(order):
-    return _lib.mh_decode_subsequence_bits(int(order))
+def decode_subsequence_bits(order, n_bits):
+    return _lib.mh_decode_subsequence_bits(int(order), int(n_bits))

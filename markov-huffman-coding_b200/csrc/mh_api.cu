@@ -337,8 +337,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 	WS_CUDA(cudaMemset(ws->hist_params, 0, 8 * sizeof(uint32_t)));
 	ws->enc_tiles_cap = encode_tiles_for(max_input_bytes) + 1;
 	WS_CUDA(cudaMalloc(&ws->enc_desc, ws->enc_tiles_cap * (2 * sizeof(uint64_t) + sizeof(uint32_t))));
-	const uint64_t min_sub = decode_sub_bits(0) < decode_sub_bits(1) ? decode_sub_bits(0) : decode_sub_bits(1);
-	ws->dec_subs_cap = (max_payload_bytes * 8 + min_sub - 1) / min_sub + 1;
+	ws->dec_subs_cap = decode_max_subs(max_payload_bytes);
 	ws->dec_chunks_cap = ws->dec_subs_cap / (kDecThreads - kDecWarmSubs) + 2;
 	WS_CUDA(cudaMalloc(&ws->dec_state, ws->dec_subs_cap * sizeof(uint32_t)));
 	WS_CUDA(cudaMalloc(&ws->dec_count, ws->dec_subs_cap * sizeof(uint32_t)));
@@ -381,13 +380,13 @@ int mh_gpu_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uin
 }
 
 int mh_gpu_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start,
-                        uint8_t prev0, uint32_t skip_subsequences, int stream_end, const mh_dectable* dt, uint8_t* d_out,
+                        uint8_t prev0, uint32_t warm_bits, int stream_end, const mh_dectable* dt, uint8_t* d_out,
                         uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream) {
-	return launch_decode_shard(d_bits, start_bit, n_bits, buf_bytes, exact_start, prev0, skip_subsequences, stream_end, dt, d_out,
+	return launch_decode_shard(d_bits, start_bit, n_bits, buf_bytes, exact_start, prev0, warm_bits, stream_end, dt, d_out,
 	                           out_capacity, reinterpret_cast<unsigned long long*>(d_result), ws, static_cast<cudaStream_t>(stream), 2);
 }
 
-uint32_t mh_decode_subsequence_bits(int order) { return decode_sub_bits(order); }
+uint32_t mh_decode_subsequence_bits(int order, uint64_t n_bits) { return decode_sub_bits(order, n_bits); }
 
 }  // extern "C"
 

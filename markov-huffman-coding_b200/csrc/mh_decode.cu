@@ -465,16 +465,32 @@ static uint32_t decode_write_threads() {
 	return (v >= 64 && v <= kDecThreads && v % 32 == 0) ? uint32_t(v) : 512u;
 }
 
-uint32_t decode_sub_bits(int order) {
-	// Subsequence size: Markov streams re-synchronise ~10x slower than plain Huffman streams, so they
-	// get longer subsequences. The environment override exists for experiments and tests.
-	int c = order ? 4096 : 1024;
+uint32_t decode_sub_bits(int order, uint64_t n_bits) {
+	// Subsequence size. Longer subsequences amortise the self-synchronisation overlap (Markov streams re-synchronise
+	// ~10x slower than plain Huffman streams) but there must be enough of them to fill the machine:
+	// the largest candidate that still yields kDecTargetSubs subsequences, else the smallest.
+	// The environment override exists for experiments and tests.
 	const char* env = getenv(order ? "MH_DEC_SUB_BITS_MARKOV" : "MH_DEC_SUB_BITS_HUFFMAN");
 	if(env) {
 		const int v = atoi(env);
-		if(v >= kDecMinSubBits && v % 256 == 0 && v <= (1 << 16)) c = v;
+		if(v >= kDecMinSubBits && v % 256 == 0 && v <= (1 << 16)) return uint32_t(v);
 	}
-	return uint32_t(c);
+	const uint32_t largest = order ? kDecMaxSubBitsMarkov : kDecMaxSubBitsHuffman;
+	const uint32_t smallest = order ? 1024u : 512u;
+	uint32_t sub = largest;
+	while(sub > smallest && n_bits / sub < kDecTargetSubs) sub >>= 1;
+	return sub;
+}
+
+uint64_t decode_max_subs(uint64_t max_payload_bytes) {
+	// workspace bound: a candidate below the largest is only chosen while it yields fewer than 2 x kDecTargetSubs
+	const uint64_t bits = max_payload_bytes * 8 + 64;
+	uint64_t cap = 2 * kDecTargetSubs + 2;
+	for(int order = 0; order < 2; ++order) {
+		const uint64_t by_largest = bits / decode_sub_bits(order, ~0ull >> 8) + 2;   // also honours an env override
+		if(by_largest > cap) cap = by_largest;
+	}
+	return cap;
 }
 
 namespace {
@@ -482,8 +498,7 @@ namespace {
 template <int ORDER>
 int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, uint32_t skip_subs, uint32_t stream_end,
                const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws,
-               cudaStream_t st, int fix_iters) {
-	const uint32_t sub_bits = decode_sub_bits(ORDER);
+               cudaStream_t st, int fix_iters, uint32_t sub_bits) {
 	const uint64_t n_subs = (n_bits - (start0 >> 8) + sub_bits - 1) / sub_bits;   // the grid starts at the stream's first bit
 	// the next chunk re-decodes the last `warm` subsequences (>= 8192 bits) of this one as warm-up
 	uint32_t warm = 8192 / sub_bits;
@@ -559,12 +574,13 @@ int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uin
 	const uint32_t start0 = (bit0 << 8) | prev0;
 	const uint64_t end_bit = n_bits + bit0;
 	const uint64_t buf_bytes = (end_bit + 7) >> 3;
-	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
-	return run_decode<0>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	const uint32_t sub_bits = decode_sub_bits(dt->order, n_bits);
+	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
+	return run_decode<0>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
 }
 
 int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start, uint8_t prev0,
-                        uint32_t skip_subs, int stream_end, const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity,
+                        uint32_t warm_bits, int stream_end, const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity,
                         unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters) {
 	if(!dt || !dt->d_lut || !d_result || !d_bits || start_bit > 31) return MH_ERR_INVALID_ARG;
 	if(reinterpret_cast<uint64_t>(d_bits) & 3) return MH_ERR_INVALID_ARG;
@@ -573,13 +589,15 @@ int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bi
 	if(n_bits == 0) return MH_OK;
 	const uint64_t end_bit = n_bits + start_bit;
 	if(buf_bytes * 8 < end_bit) return MH_ERR_INVALID_ARG;
-	const uint64_t n_subs = (n_bits + decode_sub_bits(dt->order) - 1) / decode_sub_bits(dt->order);
-	if(skip_subs >= n_subs) return MH_ERR_INVALID_ARG;
+	if(warm_bits >= n_bits) return MH_ERR_INVALID_ARG;
+	const uint32_t sub_bits = decode_sub_bits(dt->order, n_bits - warm_bits);   // sized by the bits the shard owns
+	if(warm_bits % sub_bits) return MH_ERR_INVALID_ARG;                         // warm-up = whole subsequences
+	const uint32_t skip_subs = warm_bits / sub_bits;
 	const uint32_t* words = reinterpret_cast<const uint32_t*>(d_bits);
 	// a shard that does not know its start state guesses the context; its leading skip_subs subsequences are warm-up
 	const uint32_t start0 = (start_bit << 8) | (exact_start ? uint32_t(prev0) : uint32_t(' '));
-	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
-	return run_decode<0>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters);
+	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
+	return run_decode<0>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
 }
 
 }  // namespace mh

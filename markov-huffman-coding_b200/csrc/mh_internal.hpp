@@ -39,6 +39,9 @@ constexpr int kEncBoxSmemLimit = 72 * 1024;           // largest u32 box table s
 constexpr int kEncBoxMaxBits = 27;                    // u32 entry: 5-bit length | 27-bit right-aligned code
 constexpr int kDecThreads = 1024;                     // subsequences per chunk (one thread each)
 constexpr int kDecMinSubBits = 256;
+constexpr uint32_t kDecMaxSubBitsMarkov = 8192;       // measured best of 2048..16384 on the 1 GiB Markov text
+constexpr uint32_t kDecMaxSubBitsHuffman = 2048;
+constexpr uint64_t kDecTargetSubs = 300000;           // ~2 subsequences per resident thread (148 SMs x 1024)
 constexpr int kDecWarmSubs = 8;                       // overlap subsequences re-decoded by the next chunk
 
 // ---- encode look-back descriptors -----------------------------------------------------------------------
@@ -100,9 +103,10 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
                   uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
 int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start, uint8_t prev0,
-                        uint32_t skip_subs, int stream_end, const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity,
+                        uint32_t warm_bits, int stream_end, const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity,
                         unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
-uint32_t decode_sub_bits(int order);                 // subsequence size in bits used for this coder type
+uint32_t decode_sub_bits(int order, uint64_t n_bits);   // subsequence size in bits for a stream of n_bits of this coder type
+uint64_t decode_max_subs(uint64_t max_payload_bytes);   // workspace bound on the number of subsequences
 uint64_t encode_tiles_for(uint64_t n);               // worst-case tile count for n input bytes
 
 }  // namespace mh

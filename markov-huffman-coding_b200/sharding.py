@@ -74,7 +74,7 @@ class ShardedDecoder:
     mh_gpu_encode put it). decode():
       1. all-gather the halos (each rank's last `tail_bytes` and first HALO_HEAD bytes) and splice them around the
          local payload, OR-merging the byte two neighbours share;
-      2. mh_gpu_decode_shard: rank 0 starts exactly; every other rank starts `warm_subs` subsequences before its
+      2. mh_gpu_decode_shard: rank 0 starts exactly; every other rank starts `warm_bits` bits before its
          first bit from a guessed state and converges over that warm-up;
       3. all-gather (symbol count, seam words). Rank r is consistent when the state it reached at its first bit
          equals the state rank r-1 ended in; a rank that is not decodes again from that exact state. Repeat until
@@ -85,9 +85,8 @@ class ShardedDecoder:
     def __init__(self, mh, dist, torch, rank, world, order, device):
         self.mh, self.dist, self.torch = mh, dist, torch
         self.rank, self.world, self.order = rank, world, order
-        self.sub_bits = mh.decode_subsequence_bits(order)
-        self.warm_subs = max(1, 8192 // self.sub_bits)
-        self.tail_bytes = self.warm_subs * self.sub_bits // 8 + 8
+        self.warm_bits = mh.DECODE_WARM_UNIT                 # several synchronisation distances
+        self.tail_bytes = self.warm_bits // 8 + 8
         assert self.tail_bytes + 8 <= LOCAL_PAD
         self.my_halo = torch.zeros(self.tail_bytes + HALO_HEAD, dtype=torch.uint8, device=device)
         self.halos = torch.zeros(world * (self.tail_bytes + HALO_HEAD), dtype=torch.uint8, device=device)
@@ -127,14 +126,14 @@ class ShardedDecoder:
         # ---- 2. speculative decode of my bit range ----
         own_bit = LOCAL_PAD * 8 + phase                      # my first bit, in local-buffer bit coordinates
         exact, prev0, start = (r == 0), 0x20, own_bit
-        skip = 0 if r == 0 else self.warm_subs
+        warm = 0 if r == 0 else self.warm_bits
         self.rounds = 0
         started_from = -1                                    # the predecessor end state I started from exactly, if any
         while True:
-            origin = start - skip * self.sub_bits
+            origin = start - warm
             off = (origin // 32) * 4
             n_bits = own_bit + int(bits[r]) - origin
-            mh.gpu_decode_shard(d_local.data_ptr() + off, origin % 32, n_bits, buf_end - off, exact, prev0, skip, r == self.world - 1,
+            mh.gpu_decode_shard(d_local.data_ptr() + off, origin % 32, n_bits, buf_end - off, exact, prev0, warm, r == self.world - 1,
                                 dectab, d_out.data_ptr(), out_capacity, d_result.data_ptr(), ws, stream)
             # ---- 3. handshake ----
             self.my_seam[:4] = d_result
@@ -153,7 +152,7 @@ class ShardedDecoder:
             assert self.rounds <= self.world + 1, "seam handshake did not converge"
             if not ok[r]:      # decode again, this time from the state my predecessor really ended in
                 e = int(ends[r - 1])
-                exact, prev0, skip, start, started_from = True, e & 255, 0, own_bit + (e >> 8), e
+                exact, prev0, warm, start, started_from = True, e & 255, 0, own_bit + (e >> 8), e
         # ---- 4. output offsets ----
         counts = s[:, 0]
         self.out_offset = int(counts[:r].sum())

@@ -155,18 +155,17 @@ def test_bit_range_sharded_decode_with_seam_handshake(order, k):
     provider = mh.CodingProvider.from_table_file(table)
     dectab = mh.DecodeTable(provider)
     ws = mh.Workspace(len(data), len(stream) + pad)
-    sub = mh.decode_subsequence_bits(order)
-    warm_subs = max(1, 8192 // sub)
+    warm = mh.DECODE_WARM_UNIT
     bounds = [total_bits * g // k + (13 * g if 0 < g < k else 0) for g in range(k + 1)]   # arbitrary, mid-codeword boundaries
     d_res = torch.zeros(4, dtype=torch.int64, device=dev)
     outs, seams = [], []
     for g in range(k):
-        origin = 0 if g == 0 else bounds[g] - warm_subs * sub
+        origin = 0 if g == 0 else bounds[g] - warm
         assert origin >= 0
         ptr_off = (origin // 32) * 4
         d_out = torch.zeros(len(data), dtype=torch.uint8, device=dev)
         mh.gpu_decode_shard(d_pay.data_ptr() + ptr_off, origin % 32, bounds[g + 1] - origin, d_pay.numel() - ptr_off,
-                            g == 0, 0x20, 0 if g == 0 else warm_subs, g == k - 1, dectab, d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), ws)
+                            g == 0, 0x20, 0 if g == 0 else warm, g == k - 1, dectab, d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), ws)
         res = d_res.cpu().numpy().view(np.uint64)
         assert int(res[1]) == 0 and int(res[2]) == 0, res
         outs.append(d_out[: int(res[0])].cpu().numpy().tobytes())
