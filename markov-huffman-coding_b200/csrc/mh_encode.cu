@@ -247,148 +247,167 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 	const uint32_t R = A.box_r, lo = A.box_lo, pitch = R + 1;
 	uint32_t dropped = 0;
 
+	// Software pipeline: the copy-out of tile k is deferred until tile k+1 has been loaded, looked up and counted.
+	// The look-back of tile k therefore starts a good part of a tile-time after its predecessors were handed out,
+	// which absorbs the jitter between CTAs (every tile has to wait for the slowest tile before it), and the next
+	// tile's global loads are already in flight while warp 0 polls. The staging area is reused: tile k+1 is packed
+	// only after tile k has left it.
+	bool pending = false;          // a packed tile is waiting in the staging area
+	uint32_t p_tile = 0, p_bits = 0;
 	for(uint32_t it = 0;; ++it) {
 		__syncthreads();
 		const uint32_t tile = s_tile[it & 1];
-		if(tile >= A.n_tiles) break;
-		if(tid == 0) s_tile[(it + 1) & 1] = atomicAdd(A.ticket, 1u);   // next ticket, off the critical path
+		const bool valid = tile < A.n_tiles;
+		if(!valid && !pending) break;
+		if(valid && tid == 0) s_tile[(it + 1) & 1] = atomicAdd(A.ticket, 1u);   // next ticket, off the critical path
+		else if(!valid && tid == 0) s_tile[(it + 1) & 1] = tile;
 		const uint64_t my = uint64_t(tile) * (kEncThreads * SPT) + uint64_t(tid) * SPT;
 
-		// ---- 1. my SPT bytes + the byte before them ----
-		uint32_t w[NWORDS];
+		// ================= phase A: load, look up, count (tile `tile`) =================
+		uint32_t tile_bits = 0, pos = 0;
+		uint32_t e32[FMT != FMT_WIDE ? SPT : 1];
+		unsigned long long e64[FMT == FMT_WIDE ? SPT : 1];
+		if(valid) {
+			uint32_t w[NWORDS];
 #pragma unroll
-		for(int k = 0; k < NWORDS; ++k) w[k] = 0;
-		int live = 0;
-		if(my < A.n) {
-			live = A.n - my >= uint64_t(SPT) ? SPT : int(A.n - my);
-			if(ALIGNED && live == SPT) {
+			for(int k = 0; k < NWORDS; ++k) w[k] = 0;
+			int live = 0;
+			if(my < A.n) {
+				live = A.n - my >= uint64_t(SPT) ? SPT : int(A.n - my);
+				if(ALIGNED && live == SPT) {
 #pragma unroll
-				for(int k = 0; k < SPT / 16; ++k) {
-					const uint4 v = ld_stream_128(A.in + my + 16 * k);
-					w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+					for(int k = 0; k < SPT / 16; ++k) {
+						const uint4 v = ld_stream_128(A.in + my + 16 * k);
+						w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+					}
+				} else {
+#pragma unroll
+					for(int i = 0; i < SPT; ++i)
+						if(i < live) w[i >> 2] |= uint32_t(A.in[my + i]) << (8 * (i & 3));
+				}
+			}
+			uint32_t prev = __shfl_up_sync(0xffffffffu, w[NWORDS - 1] >> 24, 1);
+			if(lane == 0 && my < A.n) prev = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
+			uint32_t my_bits = 0;
+			if constexpr(FMT != FMT_WIDE) {
+				// entries: length in [31:27], right-aligned code in [26:0]
+				uint32_t floor = 0xffffffffu;
+				// byte address of the current context's row (box formats keep the border row at index R)
+				const uint32_t pitch4 = pitch * 4;
+				uint32_t row = (FMT == FMT_BOX_SMEM ? table_sa : 0u) + (A.order ? min(prev - lo, R) * pitch4 : 0u);
+				const bool whole = live == SPT;
+#pragma unroll
+				for(int i = 0; i < SPT; ++i) {
+					const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+					uint32_t ent = 0;
+					if(whole || i < live) {
+						if(A.order) {
+							const uint32_t uc = min(c - lo, R);   // bytes outside the box land on the zero border
+							ent = FMT == FMT_BOX_SMEM ? lds32(row + uc * 4) : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(A.box) + row) + uc);
+							row = (FMT == FMT_BOX_SMEM ? table_sa : 0u) + uc * pitch4;
+						} else {
+							ent = FMT == FMT_BOX_SMEM ? lds32(row + c * 4) : __ldg(A.box + c);
+						}
+						floor = min(floor, ent);
+					}
+					e32[i] = ent;
+					my_bits += ent >> 27;
+				}
+				if(floor == 0) {   // rare: count the symbols without a codeword exactly
+#pragma unroll
+					for(int i = 0; i < SPT; ++i) dropped += (i < live && e32[i] == 0) ? 1u : 0u;
+				}
+			} else {
+				// u64 entries (codewords up to 56 bits)
+#pragma unroll
+				for(int i = 0; i < SPT; ++i) {
+					const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
+					unsigned long long ent = 0;
+					if(i < live) {
+						ent = __ldg(A.wide + ((A.order ? prev : 0u) << 8) + c);
+						if(ent == 0) ++dropped;
+					}
+					e64[i] = ent;
+					my_bits += uint32_t(ent >> 56);
+					prev = c;
+				}
+			}
+			// block exclusive scan; the tile's bit count is published right away
+			pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
+			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
+		}
+
+		// ================= phase B: resolve and write out the pending tile =================
+		if(pending) {
+			if(warp == 0) {
+				unsigned long long excl_bits;
+				uint32_t nearest_bits;
+				look_back(p_tile, p_bits, A, excl_bits, nearest_bits);
+				if(lane == 0) {
+					s_prefix_bits = excl_bits;
+					s_prefix_tail = predecessor_tail(p_tile, nearest_bits, A);
+					if(p_tile == A.n_tiles - 1) A.result[0] = excl_bits + p_bits;
+				}
+			}
+			__syncthreads();
+			// funnel-shift copy-out
+			const unsigned long long g0 = A.bit0 + s_prefix_bits;     // global bit index of the tile's first bit
+			const unsigned long long g1 = g0 + p_bits;
+			const uint32_t s = uint32_t(g0 & 31);
+			const unsigned long long w0 = g0 >> 5;
+			unsigned long long w1 = g1 >> 5;                          // words [w0, w1) are completed by this tile
+			if(p_tile == A.n_tiles - 1 && (g1 & 31)) ++w1;            // the stream's last partial word, zero padded
+			const uint32_t nw = uint32_t(w1 - w0);
+			if(w1 > A.out_capacity_words) {
+				if(tid == 0) A.result[2] = 1;                         // capacity error; this tile writes nothing
+			} else {
+				const uint32_t carry = s ? (s_prefix_tail & ((1u << s) - 1u)) : 0u;   // predecessor bits that open word w0
+				for(uint32_t j = tid; j < nw; j += kEncThreads) {
+					const uint32_t hi = j ? stage[j - 1] : carry;
+					const uint32_t v = __funnelshift_r(stage[j], hi, s);
+					A.out_words[w0 + j] = __byte_perm(v, 0, 0x0123);
+				}
+			}
+			__syncthreads();
+			const uint32_t used = (p_bits + 31) / 32 + 1;
+			for(uint32_t j = tid; j < used; j += kEncThreads) stage[j] = 0;
+			__syncthreads();   // the staging area is clean before the next tile is packed into it
+			pending = false;
+		}
+
+		// ================= phase C: pack tile `tile` into the staging area =================
+		if(valid) {
+			Packer pk;
+			pk.start(stage_sa, pos);
+			if constexpr(FMT != FMT_WIDE) {
+				// merge pairs -> quads, funnel through the window
+#pragma unroll
+				for(int q = 0; q < SPT / 4; ++q) {
+					const uint32_t l0 = e32[4 * q] >> 27, l1 = e32[4 * q + 1] >> 27, l2 = e32[4 * q + 2] >> 27, l3 = e32[4 * q + 3] >> 27;
+					const unsigned long long p0 = (uint64_t(e32[4 * q] & 0x07ffffffu) << l1) | (e32[4 * q + 1] & 0x07ffffffu);
+					const unsigned long long p1 = (uint64_t(e32[4 * q + 2] & 0x07ffffffu) << l3) | (e32[4 * q + 3] & 0x07ffffffu);
+					const uint32_t lp0 = l0 + l1, lp1 = l2 + l3;
+					if(lp0 + lp1 <= 64) {
+						pk.put((p0 << lp1) | p1, lp0 + lp1);
+					} else {   // four long codewords in a row: two <= 54-bit units
+						pk.put(p0, lp0);
+						pk.put(p1, lp1);
+					}
 				}
 			} else {
 #pragma unroll
-				for(int i = 0; i < SPT; ++i)
-					if(i < live) w[i >> 2] |= uint32_t(A.in[my + i]) << (8 * (i & 3));
-			}
-		}
-		uint32_t prev = __shfl_up_sync(0xffffffffu, w[NWORDS - 1] >> 24, 1);
-		if(lane == 0 && my < A.n) prev = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
-
-		uint32_t tile_bits;
-		if constexpr(FMT != FMT_WIDE) {
-			// ---- entries: length in [31:27], right-aligned code in [26:0] ----
-			uint32_t e[SPT];
-			uint32_t my_bits = 0, floor = 0xffffffffu;
-			// byte address of the current context's row (box formats keep the border row at index R)
-			const uint32_t pitch4 = pitch * 4;
-			uint32_t row = (FMT == FMT_BOX_SMEM ? table_sa : 0u) + (A.order ? min(prev - lo, R) * pitch4 : 0u);
-			const bool whole = live == SPT;
-#pragma unroll
-			for(int i = 0; i < SPT; ++i) {
-				const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
-				uint32_t ent = 0;
-				if(whole || i < live) {
-					if(A.order) {
-						const uint32_t uc = min(c - lo, R);   // bytes outside the box land on the zero border
-						ent = FMT == FMT_BOX_SMEM ? lds32(row + uc * 4) : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(A.box) + row) + uc);
-						row = (FMT == FMT_BOX_SMEM ? table_sa : 0u) + uc * pitch4;
-					} else {
-						ent = FMT == FMT_BOX_SMEM ? lds32(row + c * 4) : __ldg(A.box + c);
-					}
-					floor = min(floor, ent);
-				}
-				e[i] = ent;
-				my_bits += ent >> 27;
-			}
-			if(floor == 0) {   // rare: count the symbols without a codeword exactly
-#pragma unroll
-				for(int i = 0; i < SPT; ++i) dropped += (i < live && e[i] == 0) ? 1u : 0u;
-			}
-			// ---- 2. block exclusive scan; publish the tile's bit count early ----
-			const uint32_t pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
-			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
-			// ---- 3. merge pairs -> quads, funnel through the window ----
-			Packer pk;
-			pk.start(stage_sa, pos);
-#pragma unroll
-			for(int q = 0; q < SPT / 4; ++q) {
-				const uint32_t l0 = e[4 * q] >> 27, l1 = e[4 * q + 1] >> 27, l2 = e[4 * q + 2] >> 27, l3 = e[4 * q + 3] >> 27;
-				const unsigned long long p0 = (uint64_t(e[4 * q] & 0x07ffffffu) << l1) | (e[4 * q + 1] & 0x07ffffffu);
-				const unsigned long long p1 = (uint64_t(e[4 * q + 2] & 0x07ffffffu) << l3) | (e[4 * q + 3] & 0x07ffffffu);
-				const uint32_t lp0 = l0 + l1, lp1 = l2 + l3;
-				if(lp0 + lp1 <= 64) {
-					pk.put((p0 << lp1) | p1, lp0 + lp1);
-				} else {   // four long codewords in a row: two <= 54-bit units
-					pk.put(p0, lp0);
-					pk.put(p1, lp1);
-				}
+				for(int i = 0; i < SPT; ++i) pk.put(e64[i] & 0x00ffffffffffffffull, uint32_t(e64[i] >> 56));
 			}
 			pk.finish();
-		} else {
-			// ---- u64 entries (codewords up to 56 bits), one unit per symbol ----
-			unsigned long long e[SPT];
-			uint32_t my_bits = 0;
-#pragma unroll
-			for(int i = 0; i < SPT; ++i) {
-				const uint32_t c = (w[i >> 2] >> (8 * (i & 3))) & 255u;
-				unsigned long long ent = 0;
-				if(i < live) {
-					ent = __ldg(A.wide + ((A.order ? prev : 0u) << 8) + c);
-					if(ent == 0) ++dropped;
-				}
-				e[i] = ent;
-				my_bits += uint32_t(ent >> 56);
-				prev = c;
+			__syncthreads();   // staged bits visible
+			if(tid == 0) {     // the tail goes out now: successors need it only when they write their first word
+				const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
+				st_relaxed32(A.tail + tile, kTailValid | stage_bits(stage, tile_bits - tcount, tcount));
 			}
-			const uint32_t pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
-			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
-			Packer pk;
-			pk.start(stage_sa, pos);
-#pragma unroll
-			for(int i = 0; i < SPT; ++i) pk.put(e[i] & 0x00ffffffffffffffull, uint32_t(e[i] >> 56));
-			pk.finish();
+			pending = true;
+			p_tile = tile;
+			p_bits = tile_bits;
 		}
-		__syncthreads();   // staged bits visible
-
-		// ---- 4. publish the tail, resolve the global bit offset ----
-		if(warp == 0) {
-			const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
-			if(lane == 0) st_relaxed32(A.tail + tile, kTailValid | stage_bits(stage, tile_bits - tcount, tcount));
-			unsigned long long excl_bits;
-			uint32_t nearest_bits;
-			look_back(tile, tile_bits, A, excl_bits, nearest_bits);
-			if(lane == 0) {
-				s_prefix_bits = excl_bits;
-				s_prefix_tail = predecessor_tail(tile, nearest_bits, A);
-				if(tile == A.n_tiles - 1) A.result[0] = excl_bits + tile_bits;
-			}
-		}
-		__syncthreads();
-
-		// ---- 5. funnel-shift copy-out ----
-		const unsigned long long g0 = A.bit0 + s_prefix_bits;     // global bit index of the tile's first bit
-		const unsigned long long g1 = g0 + tile_bits;
-		const uint32_t s = uint32_t(g0 & 31);
-		const unsigned long long w0 = g0 >> 5;
-		unsigned long long w1 = g1 >> 5;                          // words [w0, w1) are completed by this tile
-		if(tile == A.n_tiles - 1 && (g1 & 31)) ++w1;              // the stream's last partial word, zero padded
-		const uint32_t nw = uint32_t(w1 - w0);
-		if(w1 > A.out_capacity_words) {
-			if(tid == 0) A.result[2] = 1;                         // capacity error; this tile writes nothing
-		} else {
-			const uint32_t carry = s ? (s_prefix_tail & ((1u << s) - 1u)) : 0u;   // predecessor bits that open word w0
-			for(uint32_t j = tid; j < nw; j += kEncThreads) {
-				const uint32_t hi = j ? stage[j - 1] : carry;
-				const uint32_t v = __funnelshift_r(stage[j], hi, s);
-				A.out_words[w0 + j] = __byte_perm(v, 0, 0x0123);
-			}
-		}
-		__syncthreads();
-		const uint32_t used = (tile_bits + 31) / 32 + 1;
-		for(uint32_t j = tid; j < used; j += kEncThreads) stage[j] = 0;
-		// the barrier at the top of the loop orders this zeroing before the next tile's packing
 	}
 	dropped = uint32_t(warp_sum(dropped));
 	if(lane == 0 && dropped) atomicAdd(A.result + 1, (unsigned long long) dropped);
