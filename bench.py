@@ -253,17 +253,19 @@ def main():
     d_local = torch.zeros(sharding.LOCAL_PAD + payload_cap + 256, dtype=torch.uint8, device=dev)
     d_payload = d_local[sharding.LOCAL_PAD:]
     d_out = torch.empty(n, dtype=torch.uint8, device=dev)
-    d_counts = torch.zeros(65536, dtype=torch.int64, device=dev)
+    MSG = 65536 + 2   # the histogram, then this shard's first and last byte: one message per rank and step
+    d_msg = torch.zeros(MSG, dtype=torch.int64, device=dev)
+    d_counts = d_msg[:65536]
     d_res_enc = torch.zeros(4, dtype=torch.int64, device=dev)
     d_res_dec = torch.zeros(4, dtype=torch.int64, device=dev)
-    h_counts = torch.empty(65536 * world, dtype=torch.int64, pin_memory=True)
+    h_counts = torch.empty(MSG * world, dtype=torch.int64, pin_memory=True)
     h_res = torch.empty(8, dtype=torch.int64, pin_memory=True)
     ws = mh.Workspace(n, payload_cap)
     book = dectab = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB); inputs are also >> L2
     if world > 1:
-        last_bytes = torch.zeros(world, dtype=torch.uint8, device=dev)
-        gathered = torch.zeros(65536 * world, dtype=torch.int64, device=dev)
+        edge_idx = torch.tensor([0, n - 1], device=dev)
+        gathered = torch.zeros(MSG * world, dtype=torch.int64, device=dev)
         shard_decoder = sharding.ShardedDecoder(mh, dist, torch, rank, world, 1, dev)
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -274,18 +276,22 @@ def main():
         nonlocal book, dectab
         ev[0].record()
         prev0, bit_base = 0x20, 0
+        # Every shard counts its first byte as following ' '; the one seam pair per shard is corrected on the host from
+        # the first / last bytes that travel with the histograms, so the whole exchange is a single all-gather.
+        mh.gpu_histogram(d_in.data_ptr(), n, 0x20, 1, d_counts.data_ptr(), ws, stream)
         if world > 1:
-            dist.all_gather_into_tensor(last_bytes, d_in[-1:].contiguous())
-        if world > 1 and rank > 0:
-            prev0 = int(last_bytes[rank - 1].item())
-        mh.gpu_histogram(d_in.data_ptr(), n, prev0, 1, d_counts.data_ptr(), ws, stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, d_counts)
+            d_msg[65536:] = d_in[edge_idx]
+            dist.all_gather_into_tensor(gathered, d_msg)
             h_counts.copy_(gathered, non_blocking=True)
         else:
-            h_counts[:65536].copy_(d_counts, non_blocking=True)
+            h_counts[:MSG].copy_(d_msg, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        all_counts = h_counts.numpy().view(np.uint64).reshape(world, 65536)
+        msgs = h_counts.numpy().view(np.uint64).reshape(world, MSG)
+        all_counts = msgs[:, :65536]
+        if world > 1:
+            sharding.fix_seam_pairs(all_counts, msgs[:, 65536], msgs[:, 65537])
+            if rank > 0:
+                prev0 = int(msgs[rank - 1, 65537])
         provider = mh.CodingProvider.from_counts_array(sharding.global_counts(all_counts), 1)     # identical on every rank
         if book is None:
             book, dectab = mh.Codebook(provider), mh.DecodeTable(provider)

@@ -22,8 +22,21 @@ def global_counts(all_counts):
 
 
 def shard_bits(all_counts, code_lengths):
-    """Payload bits of every shard: uint64 [world]."""
-    return (np.asarray(all_counts, dtype=np.uint64) * np.asarray(code_lengths, dtype=np.uint64)[None, :]).sum(axis=1, dtype=np.uint64)
+    """Payload bits of every shard: uint64 [world]. Only the (prev, c) pairs that have a codeword contribute."""
+    lens = np.asarray(code_lengths, dtype=np.uint64)
+    live = np.flatnonzero(lens)
+    a = np.asarray(all_counts, dtype=np.uint64)
+    return (a[:, live] * lens[live][None, :]).sum(axis=1, dtype=np.uint64)
+
+
+def fix_seam_pairs(all_counts, first_bytes, last_bytes, guess=0x20):
+    """Every shard counted its first byte as following `guess`; move that one count to the pair it really forms with
+    the previous shard's last byte (order-1 histograms only). all_counts: uint64 [world, 65536], modified in place."""
+    for g in range(1, len(first_bytes)):
+        f, true_prev = int(first_bytes[g]), int(last_bytes[g - 1])
+        all_counts[g, 256 * guess + f] -= 1
+        all_counts[g, 256 * true_prev + f] += 1
+    return all_counts
 
 
 def shard_bit_bases(all_counts, code_lengths):

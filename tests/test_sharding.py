@@ -201,3 +201,18 @@ def test_shard_restart_from_exact_seam_state():
     res = d_res.cpu().numpy().view(np.uint64)
     assert int(res[1]) == 0 and int(res[2]) == 0
     assert d_a[:n_a].cpu().numpy().tobytes() + d_b[: int(res[0])].cpu().numpy().tobytes() == data
+
+
+def test_seam_pair_fixup_and_shard_sizes_from_histograms():
+    """Shards count their first byte as following ' '; fix_seam_pairs moves that one count to the real pair, after
+    which the summed histograms equal the unsharded one and sum(count x length) gives every shard's payload size."""
+    d = golden_input("input_wiki_cpp.html")
+    cuts = [0, 100000, 200001, len(d)]
+    ac = np.stack([o.histogram(d[a:b], True, 0x20).astype(np.int64).astype(np.uint64) for a, b in zip(cuts[:-1], cuts[1:])])
+    sharding.fix_seam_pairs(ac, [d[a] for a in cuts[:-1]], [d[b - 1] for b in cuts[1:]])
+    assert np.array_equal(sharding.global_counts(ac), o.histogram(d, True).astype(np.int64).astype(np.uint64))
+    provider = mh.CodingProvider.from_counts_array(sharding.global_counts(ac), 1)
+    base, bits = sharding.shard_bit_bases(ac, provider.code_lengths())
+    table = o.Table.from_counts(o.histogram(d, True), True)
+    for g, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        assert int(bits[g]) == table.encode_shard(d[a:b], 0x20 if a == 0 else d[a - 1], int(base[g]))[1]
