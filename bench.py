@@ -406,14 +406,14 @@ def main():
     peak, peak_src = peaks()
     c_bytes = (state["bits"] + 7) // 8
     algo = {   # algorithmic bytes per launch; D1 only reads the payload, D4 reads it and writes N
-        "hist_kernel<1>": n, "encode_kernel": n + c_bytes, "dec_sync_kernel": c_bytes, "dec_write_kernel": c_bytes + n,
+        "hist_kernel<1>": n, "hist_lane_kernel": n, "hist0_lane_kernel": n, "encode_kernel": n + c_bytes, "dec_sync_kernel": c_bytes, "dec_write_kernel": c_bytes + n,
     }
     kern = {k: v["ms"] / max(1, v["launches"]) for k, v in prof.items()}
     dominant = max(kern, key=kern.get)
     dom_ms = kern[dominant]
     achieved = algo.get(dominant, 0) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     phase = {
-        "histogram": {"algorithmic_bytes": n, "ms": sum(kern.get(k, 0) for k in ("hist_probe_kernel", "hist_kernel<1>"))},
+        "histogram": {"algorithmic_bytes": n, "ms": sum(v for k, v in kern.items() if k.startswith("hist"))},
         "encode": {"algorithmic_bytes": n + c_bytes, "ms": kern.get("encode_kernel", 0)},
         "decode": {"algorithmic_bytes": c_bytes + n, "ms": sum(v for k, v in kern.items() if k.startswith("dec_"))},
     }

@@ -12,6 +12,17 @@
 //     pairs outside the box (rare for text, everything beyond R for binary data) go straight to the global
 //     64-bit table with L2 atomics, so the result is exact whatever the probe saw;
 //   * the boxes are folded into the global table with one 64-bit atomic per non-zero bin.
+//
+// Lane-private variant (hist_lane_kernel, the one text-like inputs take). 32 lanes that add into 32 random bins hit
+// the same shared-memory bank ~3.3 deep, and that serialisation — not HBM — bounded the box kernel (ncu:
+// 3.3 wavefronts per ATOMS). When the probe finds an alphabet of K <= 53 byte values, every lane of a warp gets
+// its OWN column of bins: dense pair index (rank(prev), rank(c)) x 32 lanes, u16 counters packed in pairs so that
+// the word of (bin, lane) sits in bank `lane` — one wavefront per warp-wide atomic, whatever the data. The rank
+// comes from a lane-replicated u32 lookup (also conflict-free) that already carries the row offset, the column
+// offset and the half-word selector. u16 counters cannot overflow because the CTA drains them into the global
+// table every kLaneFlushIters iterations. Alphabets up to 221 values use the same code with u32 bins in 16..1
+// lane columns. Byte values the probe did not see land on a trash row/column and are fixed up per 16-byte group
+// with global atomics, so the result stays exact whatever the probe saw.
 #include "mh_internal.hpp"
 
 namespace mh {
@@ -73,6 +84,250 @@ __device__ __forceinline__ void hist_plan(const uint32_t* __restrict__ params, u
 	reps_out = reps;
 }
 
+// ---- lane-private kernels ---------------------------------------------------------------------------------
+constexpr int kLaneThreads = 1024;
+constexpr int kLaneWarps = kLaneThreads / 32;
+constexpr uint32_t kLaneSmemBytes = 224 * 1024;       // dynamic shared memory of hist_lane_kernel
+constexpr uint32_t kLaneLutBytes = 256 * 32 * 4;      // lane-replicated symbol lookup
+constexpr uint32_t kLaneFlushIters = 63;              // 63 iterations x 32 warps x 2 groups x 16 bytes < 65536
+
+__device__ __forceinline__ void red_add_shared(uint32_t addr, uint32_t v) {
+	asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+// mode 0: general box kernel; 1: packed u16 x 32 lane columns; 2: u32 x S lane columns (S = 16, 8, 4, 2, 1)
+struct LanePlan {
+	uint32_t mode, K, pitch, S;
+};
+__device__ __forceinline__ LanePlan lane_plan(const uint32_t* __restrict__ params) {
+	LanePlan p;
+	uint32_t k = 0;
+	for(int i = 0; i < 8; ++i) k += __popc(params[i]);
+	p.K = k;
+	const uint32_t k1 = k + 1, room = kLaneSmemBytes - kLaneLutBytes - 128;   // bin rows are 128-byte aligned
+	p.pitch = (k1 + 1) & ~1u;
+	p.S = 32;
+	p.mode = 0;
+	if(k1 * p.pitch * 64u <= room) { p.mode = 1; return p; }
+	for(uint32_t s = 16; s >= 1; s >>= 1)
+		if(k1 * k1 * 4u * s <= room) { p.mode = 2; p.S = s; p.pitch = k1; return p; }
+	return p;
+}
+
+// Lookup word of byte value c in lane l's column (rank ic, absolute shared-space address of its bin row):
+//   [31:20] byte offset of (column ic, lane l) inside a bin row
+//   [19:7] / [19:2]  shared-space address of context ic's bin row (128- / 4-byte aligned)
+//   packed mode: [4:0] shift of the u16 half (0 or 16), [5] trash;   u32 mode: [1] trash
+template <bool PACK16>
+struct LaneFmt {
+	static constexpr uint32_t kRowMask = PACK16 ? 0xfff80u : 0xffffcu;
+	static constexpr uint32_t kTrash = PACK16 ? 0x20u : 0x2u;
+};
+
+// 16 consecutive bytes whose predecessor is `prev`: one conflict-free lookup and one conflict-free atomic per byte.
+template <bool PACK16>
+__device__ __forceinline__ uint32_t lane_tally16(const uint4 v, uint32_t prev, uint32_t lutl) {
+	uint32_t e = lds_u32(lutl + prev * 128u);
+	uint32_t acc = e;
+	uint32_t row = e & LaneFmt<PACK16>::kRowMask;
+	const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+	for(int k = 0; k < 4; ++k) {
+#pragma unroll
+		for(int b = 0; b < 4; ++b) {
+			const uint32_t c = __byte_perm(w[k], 0, 0x4440 + b);
+			e = lds_u32(lutl + c * 128u);
+			red_add_shared(row + (e >> 20), PACK16 ? __funnelshift_l(0u, 1u, e) : 1u);
+			row = e & LaneFmt<PACK16>::kRowMask;
+			acc |= e;
+		}
+	}
+	return acc;
+}
+
+__global__ void __launch_bounds__(kLaneThreads, 1) hist_lane_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t prev0,
+                                                                     unsigned long long* __restrict__ counts,
+                                                                     const uint32_t* __restrict__ params) {
+	extern __shared__ uint32_t sh[];   // [256 x 32] lookup | bins
+	__shared__ uint8_t s_idx[256];     // byte value -> rank (K for values the probe did not see)
+	__shared__ uint8_t s_inv[256];     // rank -> byte value
+	__shared__ LanePlan s_plan;
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if(tid == 0) s_plan = lane_plan(params);
+	if(tid < 256) {
+		const uint32_t word = tid >> 5, bit = tid & 31;
+		uint32_t rank = 0;
+		for(uint32_t i = 0; i < word; ++i) rank += __popc(params[i]);
+		rank += __popc(params[word] & ((1u << bit) - 1u));
+		const bool present = (params[word] >> bit) & 1u;
+		s_idx[tid] = 0xff;
+		if(present) { s_idx[tid] = uint8_t(rank); s_inv[rank] = uint8_t(tid); }
+	}
+	__syncthreads();
+	const LanePlan P = s_plan;
+	if(P.mode == 0) return;   // hist_kernel<1> counts this input
+	const bool pack16 = P.mode == 1;
+	const uint32_t K = P.K, K1 = K + 1;
+	const uint32_t row_bytes = pack16 ? (P.pitch / 2) * 128u : K1 * P.S * 4u;
+	const uint32_t bin_words = K1 * row_bytes / 4;
+	if(tid < 256 && s_idx[tid] == 0xff) s_idx[tid] = uint8_t(K);
+	__syncthreads();
+	// bin rows start on a 128-byte boundary: the lookup word keeps flags in the low address bits
+	const uint32_t bins_sa = (uint32_t(__cvta_generic_to_shared(sh)) + kLaneLutBytes + 127u) & ~127u;
+	uint32_t* bins = sh + (bins_sa - uint32_t(__cvta_generic_to_shared(sh))) / 4;
+	for(uint32_t i = tid; i < 256 * 32; i += kLaneThreads) {
+		const uint32_t c = i >> 5, l = i & 31, ic = s_idx[c];
+		const uint32_t col = pack16 ? (ic >> 1) * 128u + l * 4u : (ic * P.S + (l & (P.S - 1))) * 4u;
+		const uint32_t flags = pack16 ? ((ic & 1u) << 4) | (ic == K ? LaneFmt<true>::kTrash : 0u) : (ic == K ? LaneFmt<false>::kTrash : 0u);
+		sh[i] = (col << 20) | (bins_sa + ic * row_bytes) | flags;
+	}
+	for(uint32_t i = tid; i < bin_words; i += kLaneThreads) bins[i] = 0;
+	__syncthreads();
+	const uint32_t lutl = uint32_t(__cvta_generic_to_shared(sh)) + lane * 4;
+
+	// packed mode: drain the u16 counters into the global table (warp per 32-lane word row)
+	auto drain16 = [&]() {
+		__syncthreads();
+		const uint32_t half = P.pitch / 2;
+		for(uint32_t r = warp; r < K * half; r += kLaneWarps) {   // rows of the trash context are dropped
+			const uint32_t v = bins[r * 32 + lane];
+			bins[r * 32 + lane] = 0;
+			const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xffffu), hi = __reduce_add_sync(0xffffffffu, v >> 16);
+			const uint32_t ip = r / half, ic = 2 * (r - ip * half);
+			if(lane == 0 && lo && ic < K) atomicAdd(&counts[uint32_t(s_inv[ip]) * 256u + s_inv[ic]], (unsigned long long) lo);
+			if(lane == 1 && hi && ic + 1 < K) atomicAdd(&counts[uint32_t(s_inv[ip]) * 256u + s_inv[ic + 1]], (unsigned long long) hi);
+		}
+		for(uint32_t i = K * half * 32 + tid; i < bin_words; i += kLaneThreads) bins[i] = 0;
+		__syncthreads();
+	};
+
+	const uint64_t addr = reinterpret_cast<uint64_t>(in);
+	uint64_t head = (16 - (addr & 15)) & 15;
+	if(head > n) head = n;
+	const uint64_t groups = (n - head) >> 4;
+	const uint8_t* body = in + head;
+	const uint64_t gstride = uint64_t(gridDim.x) * kLaneThreads;
+
+	// exact fix-up of a 16-byte group that touched the trash row/column (a byte value the probe missed)
+	auto fix_up = [&](const uint4 v, uint32_t prev) {
+		const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+		for(int k = 0; k < 4; ++k) {
+#pragma unroll 1
+			for(int b = 0; b < 4; ++b) {
+				const uint32_t c = (w[k] >> (8 * b)) & 255u;
+				if(s_idx[prev] == K || s_idx[c] == K) atomicAdd(&counts[prev * 256u + c], 1ull);
+				prev = c;
+			}
+		}
+	};
+	auto load_group = [&](uint64_t g, uint4& v, uint32_t& first_prev) {
+		v = make_uint4(0, 0, 0, 0);
+		first_prev = 0;
+		if(g < groups) {
+			v = ld_stream_128(body + (g << 4));
+			if(lane == 0) first_prev = (head + (g << 4)) == 0 ? prev0 : uint32_t(body[(g << 4) - 1]);
+		}
+	};
+	auto process = [&](uint64_t g, const uint4 v, uint32_t first_prev) {
+		uint32_t prev = __shfl_up_sync(0xffffffffu, v.w >> 24, 1);
+		if(lane == 0) prev = first_prev;
+		if(g < groups) {
+			const uint32_t acc = pack16 ? lane_tally16<true>(v, prev, lutl) & LaneFmt<true>::kTrash : lane_tally16<false>(v, prev, lutl) & LaneFmt<false>::kTrash;
+			if(acc) fix_up(v, prev);
+		}
+	};
+
+	// two groups per thread and iteration, the next pair prefetched while the current one is counted
+	uint64_t g = uint64_t(blockIdx.x) * kLaneThreads + tid;           // this thread's first group
+	const uint64_t cbase = uint64_t(blockIdx.x) * kLaneThreads;       // CTA-uniform loop bound (drain16 has barriers)
+	uint4 a, b;
+	uint32_t pa, pb;
+	load_group(g, a, pa);
+	load_group(g + gstride, b, pb);
+	uint32_t iters = 0;
+	for(uint64_t base = cbase; base < groups; base += 2 * gstride, g += 2 * gstride) {
+		uint4 na, nb;
+		uint32_t npa, npb;
+		load_group(g + 2 * gstride, na, npa);
+		load_group(g + 3 * gstride, nb, npb);
+		process(g, a, pa);
+		process(g + gstride, b, pb);
+		a = na; b = nb; pa = npa; pb = npb;
+		if(pack16 && ++iters == kLaneFlushIters) { iters = 0; drain16(); }   // CTA-uniform: every warp runs the same trip count
+	}
+	if(blockIdx.x == 0 && tid == 0) {   // unaligned lead-in and the ragged tail: a few bytes, straight to the global table
+		uint32_t prev = prev0;
+		for(uint64_t i = 0; i < head; ++i) { atomicAdd(&counts[prev * 256u + in[i]], 1ull); prev = in[i]; }
+		const uint64_t t0 = head + (groups << 4);
+		if(t0 < n) {
+			prev = t0 == 0 ? prev0 : uint32_t(in[t0 - 1]);
+			for(uint64_t i = t0; i < n; ++i) { atomicAdd(&counts[prev * 256u + in[i]], 1ull); prev = in[i]; }
+		}
+	}
+	if(pack16) {
+		drain16();
+	} else {
+		__syncthreads();
+		for(uint32_t bin = tid; bin < K * K1; bin += kLaneThreads) {
+			const uint32_t ip = bin / K1, ic = bin - ip * K1;
+			if(ic == K) continue;
+			uint32_t s = 0;
+			for(uint32_t j = 0; j < P.S; ++j) s += bins[bin * P.S + j];
+			if(s) atomicAdd(&counts[uint32_t(s_inv[ip]) * 256u + s_inv[ic]], (unsigned long long) s);
+		}
+	}
+}
+
+// order 0: 256 bins x 32 lane columns (32 KiB): bank = lane, no conflicts
+__global__ void __launch_bounds__(kLaneThreads, 2) hist0_lane_kernel(const uint8_t* __restrict__ in, uint64_t n,
+                                                                      unsigned long long* __restrict__ counts) {
+	__shared__ uint32_t bins[256 * 32];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	for(uint32_t i = tid; i < 256 * 32; i += kLaneThreads) bins[i] = 0;
+	__syncthreads();
+	const uint32_t mine = uint32_t(__cvta_generic_to_shared(bins)) + lane * 4;
+	const uint64_t addr = reinterpret_cast<uint64_t>(in);
+	uint64_t head = (16 - (addr & 15)) & 15;
+	if(head > n) head = n;
+	const uint64_t groups = (n - head) >> 4;
+	const uint8_t* body = in + head;
+	const uint64_t gstride = uint64_t(gridDim.x) * kLaneThreads;
+	auto tally16 = [&](const uint4 v) {
+		const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+		for(int k = 0; k < 4; ++k)
+#pragma unroll
+			for(int b = 0; b < 4; ++b) red_add_shared(mine + (((w[k] >> (8 * b)) & 255u) << 7), 1u);
+	};
+	uint64_t g = uint64_t(blockIdx.x) * kLaneThreads + tid;
+	uint4 a = make_uint4(0, 0, 0, 0), b = a;
+	if(g < groups) a = ld_stream_128(body + (g << 4));
+	if(g + gstride < groups) b = ld_stream_128(body + ((g + gstride) << 4));
+	for(; g < groups; g += 2 * gstride) {
+		uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+		if(g + 2 * gstride < groups) na = ld_stream_128(body + ((g + 2 * gstride) << 4));
+		if(g + 3 * gstride < groups) nb = ld_stream_128(body + ((g + 3 * gstride) << 4));
+		tally16(a);
+		if(g + gstride < groups) tally16(b);
+		a = na; b = nb;
+	}
+	if(blockIdx.x == 0 && tid == 0) {
+		for(uint64_t i = 0; i < head; ++i) atomicAdd(&counts[in[i]], 1ull);
+		for(uint64_t i = head + (groups << 4); i < n; ++i) atomicAdd(&counts[in[i]], 1ull);
+	}
+	__syncthreads();
+	for(uint32_t r = warp; r < 256; r += kLaneWarps) {
+		const uint32_t s = __reduce_add_sync(0xffffffffu, bins[r * 32 + lane]);
+		if(lane == 0 && s) atomicAdd(&counts[r], (unsigned long long) s);
+	}
+}
+
 template <int ORDER>
 __global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t prev0,
                                                              unsigned long long* __restrict__ counts,
@@ -80,6 +335,7 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint8_t* __res
 	extern __shared__ uint32_t sh[];
 	__shared__ uint32_t s_plan[3];
 	if(ORDER) {
+		if(lane_plan(params).mode != 0) return;   // hist_lane_kernel counted this input
 		if(threadIdx.x == 0) hist_plan(params, smem_words, s_plan[0], s_plan[1], s_plan[2]);
 		__syncthreads();
 	}
@@ -160,16 +416,19 @@ int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, 
 	// each CTA counts in u32: keep a CTA's share below 2^32 samples
 	const int sms = sm_count();
 	const uint64_t groups = n / 16 + 1;
-	uint64_t want = (groups + kHistThreads - 1) / kHistThreads;
-	int ctas_per_sm = 2;
-	uint64_t grid = uint64_t(sms) * ctas_per_sm;
-	if(grid > want) grid = want;
-	while(n / grid >= (1ull << 32)) grid *= 2;
+	auto grid_for = [&](int threads, int ctas_per_sm) {
+		const uint64_t want = (groups + threads - 1) / threads;
+		uint64_t grid = uint64_t(sms) * ctas_per_sm;
+		if(grid > want) grid = want;
+		while(n / grid >= (1ull << 32)) grid *= 2;
+		return unsigned(grid);
+	};
 	if(order) {
 		const uint32_t smem_bytes = 100 * 1024;
 		static bool attr_done = false;
 		if(!attr_done) {
 			MH_CUDA(cudaFuncSetAttribute(hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+			MH_CUDA(cudaFuncSetAttribute(hist_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLaneSmemBytes)));
 			attr_done = true;
 		}
 		{
@@ -177,14 +436,19 @@ int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, 
 			ProfScope p("hist_probe_kernel", st);
 			hist_probe_kernel<<<kProbeWindows, kProbeThreads, 0, st>>>(d_in, n, ws->hist_params);
 		}
+		// Both counting kernels derive the same plan from the probe's bitmap; exactly one of them does the work.
+		{
+			ProfScope p("hist_lane_kernel", st);
+			hist_lane_kernel<<<grid_for(kLaneThreads, 1), kLaneThreads, kLaneSmemBytes, st>>>(d_in, n, prev0, d_counts, ws->hist_params);
+		}
 		{
 			ProfScope p("hist_kernel<1>", st);
-			hist_kernel<1><<<unsigned(grid), kHistThreads, smem_bytes, st>>>(d_in, n, prev0, d_counts, ws->hist_params, smem_bytes / 4);
+			hist_kernel<1><<<grid_for(kHistThreads, 2), kHistThreads, smem_bytes, st>>>(d_in, n, prev0, d_counts, ws->hist_params, smem_bytes / 4);
 		}
-		count_launch(2);
+		count_launch(3);
 	} else {
-		ProfScope p("hist_kernel<0>", st);
-		hist_kernel<0><<<unsigned(grid), kHistThreads, kHistWarps * 256 * 4, st>>>(d_in, n, prev0, d_counts, ws->hist_params, 0u);
+		ProfScope p("hist0_lane_kernel", st);
+		hist0_lane_kernel<<<grid_for(kLaneThreads, 2), kLaneThreads, 0, st>>>(d_in, n, d_counts);
 		count_launch(1);
 	}
 	MH_CUDA(cudaGetLastError());
