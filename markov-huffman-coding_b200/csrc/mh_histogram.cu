@@ -206,12 +206,20 @@ __global__ void __launch_bounds__(kLaneThreads, 1) hist_lane_kernel(const uint8_
 		__syncthreads();
 	};
 
+	// [0, head) lead-in (1..16 bytes, so every 16-byte group has a predecessor byte in memory), G aligned groups, tail.
+	// Each CTA takes one contiguous span of groups and walks it two CTA-wide rows (2 x 1024 groups) per iteration.
 	const uint64_t addr = reinterpret_cast<uint64_t>(in);
-	uint64_t head = (16 - (addr & 15)) & 15;
+	uint64_t head = 16 - (addr & 15);
 	if(head > n) head = n;
 	const uint64_t groups = (n - head) >> 4;
 	const uint8_t* body = in + head;
-	const uint64_t gstride = uint64_t(gridDim.x) * kLaneThreads;
+	constexpr uint32_t kRow = kLaneThreads, kIterGroups = 2 * kRow;
+	uint64_t span = (groups + gridDim.x - 1) / gridDim.x;
+	span = (span + kIterGroups - 1) / kIterGroups * kIterGroups;
+	const uint64_t g0 = uint64_t(blockIdx.x) * span < groups ? uint64_t(blockIdx.x) * span : groups;
+	const uint64_t g1 = g0 + span < groups ? g0 + span : groups;
+	const uint32_t full = uint32_t((g1 - g0) / kIterGroups);
+	const uint32_t rest = uint32_t((g1 - g0) - uint64_t(full) * kIterGroups);
 
 	// exact fix-up of a 16-byte group that touched the trash row/column (a byte value the probe missed)
 	auto fix_up = [&](const uint4 v, uint32_t prev) {
@@ -226,40 +234,41 @@ __global__ void __launch_bounds__(kLaneThreads, 1) hist_lane_kernel(const uint8_
 			}
 		}
 	};
-	auto load_group = [&](uint64_t g, uint4& v, uint32_t& first_prev) {
-		v = make_uint4(0, 0, 0, 0);
-		first_prev = 0;
-		if(g < groups) {
-			v = ld_stream_128(body + (g << 4));
-			if(lane == 0) first_prev = (head + (g << 4)) == 0 ? prev0 : uint32_t(body[(g << 4) - 1]);
-		}
-	};
-	auto process = [&](uint64_t g, const uint4 v, uint32_t first_prev) {
+	auto process = [&](const uint4 v, uint32_t first_prev, bool live) {
 		uint32_t prev = __shfl_up_sync(0xffffffffu, v.w >> 24, 1);
 		if(lane == 0) prev = first_prev;
-		if(g < groups) {
+		if(live) {
 			const uint32_t acc = pack16 ? lane_tally16<true>(v, prev, lutl) & LaneFmt<true>::kTrash : lane_tally16<false>(v, prev, lutl) & LaneFmt<false>::kTrash;
 			if(acc) fix_up(v, prev);
 		}
 	};
+	auto load2 = [&](const uint8_t* q, uint4& x, uint4& y, uint32_t& px, uint32_t& py) {
+		x = ld_stream_128(q);
+		y = ld_stream_128(q + kRow * 16);
+		if(lane == 0) { px = q[-1]; py = q[kRow * 16 - 1]; }
+	};
 
-	// two groups per thread and iteration, the next pair prefetched while the current one is counted
-	uint64_t g = uint64_t(blockIdx.x) * kLaneThreads + tid;           // this thread's first group
-	const uint64_t cbase = uint64_t(blockIdx.x) * kLaneThreads;       // CTA-uniform loop bound (drain16 has barriers)
-	uint4 a, b;
-	uint32_t pa, pb;
-	load_group(g, a, pa);
-	load_group(g + gstride, b, pb);
-	uint32_t iters = 0;
-	for(uint64_t base = cbase; base < groups; base += 2 * gstride, g += 2 * gstride) {
-		uint4 na, nb;
-		uint32_t npa, npb;
-		load_group(g + 2 * gstride, na, npa);
-		load_group(g + 3 * gstride, nb, npb);
-		process(g, a, pa);
-		process(g + gstride, b, pb);
+	const uint8_t* p = body + ((g0 + tid) << 4);
+	uint4 a = make_uint4(0, 0, 0, 0), b = a;
+	uint32_t pa = 0, pb = 0, iters = 0;
+	if(full) load2(p, a, b, pa, pb);
+	for(uint32_t i = 0; i < full; ++i) {   // the next two rows are in flight while the current two are counted
+		uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+		uint32_t npa = 0, npb = 0;
+		if(i + 1 < full) load2(p + kIterGroups * 16, na, nb, npa, npb);
+		process(a, pa, true);
+		process(b, pb, true);
 		a = na; b = nb; pa = npa; pb = npb;
-		if(pack16 && ++iters == kLaneFlushIters) { iters = 0; drain16(); }   // CTA-uniform: every warp runs the same trip count
+		p += kIterGroups * 16;
+		if(pack16 && ++iters == kLaneFlushIters) { iters = 0; drain16(); }   // CTA-uniform trip count
+	}
+	if(rest) {   // the span's ragged end (CTA-uniform condition; the shuffles need whole warps)
+		const bool la = tid < rest, lb = tid + kRow < rest;
+		a = b = make_uint4(0, 0, 0, 0);
+		if(la) { a = ld_stream_128(p); if(lane == 0) pa = p[-1]; }
+		if(lb) { b = ld_stream_128(p + kRow * 16); if(lane == 0) pb = p[kRow * 16 - 1]; }
+		process(a, pa, la);
+		process(b, pb, lb);
 	}
 	if(blockIdx.x == 0 && tid == 0) {   // unaligned lead-in and the ragged tail: a few bytes, straight to the global table
 		uint32_t prev = prev0;
