@@ -250,15 +250,17 @@ static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st) 
 
 static int upload_dectable(const mh_table* t, mh_dectable* dt, cudaStream_t st) {
 	if(!dt->d_lut) MH_CUDA(cudaMalloc(&dt->d_lut, 65536 * sizeof(uint16_t)));
-	if(!dt->d_walk) MH_CUDA(cudaMalloc(&dt->d_walk, 256 * 512 * sizeof(uint32_t)));
+	// one allocation: walk table [ntab * 512] u32, then the second-level rows [kExtRows * 256] u16
+	const size_t ext_bytes = size_t(kExtRows) * 256 * sizeof(uint16_t);
+	if(!dt->d_walk) MH_CUDA(cudaMalloc(&dt->d_walk, 256 * 512 * sizeof(uint32_t) + ext_bytes));
 	if(!dt->h_lut) MH_CUDA(cudaMallocHost(&dt->h_lut, 65536 * sizeof(uint16_t)));
-	if(!dt->h_walk) MH_CUDA(cudaMallocHost(&dt->h_walk, 256 * 512 * sizeof(uint32_t)));
+	if(!dt->h_walk) MH_CUDA(cudaMallocHost(&dt->h_walk, 256 * 512 * sizeof(uint32_t) + ext_bytes));
 	if(!dt->uploaded) MH_CUDA(cudaEventCreateWithFlags(&dt->uploaded, cudaEventDisableTiming));
 	else MH_CUDA(cudaEventSynchronize(dt->uploaded));
-	t->impl.flatten_dectable(dt->h_lut, dt->h_walk);
 	const size_t ntab = t->impl.trees.size();
+	const uint32_t ext_rows = t->impl.flatten_dectable(dt->h_lut, dt->h_walk, reinterpret_cast<uint16_t*>(dt->h_walk + ntab * 512));
 	MH_CUDA(cudaMemcpyAsync(dt->d_lut, dt->h_lut, ntab * 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-	MH_CUDA(cudaMemcpyAsync(dt->d_walk, dt->h_walk, ntab * 512 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	MH_CUDA(cudaMemcpyAsync(dt->d_walk, dt->h_walk, ntab * 512 * sizeof(uint32_t) + size_t(ext_rows) * 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
 	MH_CUDA(cudaEventRecord(dt->uploaded, st));
 	dt->order = t->impl.order;
 	dt->max_bits = t->impl.max_code_bits();

@@ -31,7 +31,7 @@ namespace {
 // LUT entry (u16), see CodingTable::flatten_dectable:
 //   leaf : symbol << 8 | length (1..8)           deep : node << 7 | 0x10 (internal node at depth 8)
 //   null : ' ' << 8 | 0x20 | 1 (no such table entry: harmless while speculating, an error once verified)
-constexpr uint32_t kDeep = 0x10u, kNull = 0x20u;
+constexpr uint32_t kDeep = 0x10u, kNull = 0x20u, kExt = 0x40u;
 
 // MSB-first bit window over the payload: (hi:lo) holds the bits [pos, loaded) left-aligned, `nextw` is the word
 // after them, fetched one refill ahead so that its latency is off the per-symbol dependency chain.
@@ -74,6 +74,11 @@ struct Cursor {
 		lo <<= nbits;
 		pos += nbits;
 	}
+	__device__ __forceinline__ void take_group(uint32_t nbits) {   // nbits <= 32 (a whole group of four LUT hits)
+		hi = __funnelshift_lc(lo, hi, nbits);
+		asm("shl.b32 %0, %0, %1;" : "+r"(lo) : "r"(nbits));   // PTX shl clamps: 32 -> 0
+		pos += nbits;
+	}
 	__device__ __forceinline__ void top_up() {
 		const uint32_t avail = loaded - pos;
 		if(avail <= 32) {   // all valid bits sit in hi
@@ -104,25 +109,70 @@ __device__ __forceinline__ uint32_t decode_one(Cursor& cur, uint32_t lut_s, cons
 		cur.take(1);
 		sym = ' ';
 	} else {
-		// codeword longer than 8 bits: consume the 8 window bits, then walk the tree bit by bit (src/coding.cpp:129-149)
+		// codeword longer than 8 bits (src/coding.cpp:129-149): consume the 8 window bits; the next 8 bits index the
+		// node's second-level row (ext), which resolves codewords up to 16 bits in one lookup; anything deeper, or a
+		// deep node without a row, is walked bit by bit through the flattened tree.
 		cur.take(8);
+		cur.top_up();   // up to three leaves may precede this symbol in a group: make the next 8 bits valid
 		uint32_t node = e >> 7;
-		const uint32_t* nodes = walk + row_off;   // row_off = ctx * 512 is also the context's offset in the walk table
+		bool walk_it = true;
 		sym = ' ';
-		for(int guard = 0; guard < 256; ++guard) {
-			cur.top_up();
-			const uint32_t bit = cur.hi >> 31;
-			cur.take(1);
-			const uint32_t w = __ldg(nodes + node);
-			const uint32_t child = bit ? (w & 0xffffu) : (w >> 16);
-			if(child & 0x8000u) { sym = child & 255u; break; }
-			node = child;
-			if(guard == 255) clean = false;
+		if(e & kExt) {
+			const uint16_t* ext = reinterpret_cast<const uint16_t*>(walk + (ORDER ? 256 : 1) * 512);
+			const uint32_t e2 = __ldg(ext + (node << 8) + (cur.hi >> 24));
+			if(e2 & kDeep) {
+				cur.take(8);
+				node = e2 >> 7;
+			} else {
+				cur.take(e2 & 15u);
+				sym = e2 >> 8;
+				walk_it = false;
+			}
+		}
+		if(walk_it) {
+			const uint32_t* nodes = walk + row_off;   // row_off = ctx * 512 is also the context's offset in the walk table
+			for(int guard = 0; guard < 256; ++guard) {
+				cur.top_up();
+				const uint32_t bit = cur.hi >> 31;
+				cur.take(1);
+				const uint32_t w = __ldg(nodes + node);
+				const uint32_t child = bit ? (w & 0xffffu) : (w >> 16);
+				if(child & 0x8000u) { sym = child & 255u; break; }
+				node = child;
+				if(guard == 255) clean = false;
+			}
 		}
 		cur.top_up();   // restore the "more than 32 valid bits" invariant the 4-symbol groups rely on
 	}
 	if(ORDER) row_off = sym << 9;
 	return sym;
+}
+
+// Four symbols at once on the fast path. The window is left untouched: symbol j peeks at (hi:lo) << consumed,
+// where `consumed` is the low bits of `acc`, the running SUM of the LUT entries (a leaf entry carries its length
+// in bits [3:0] and nothing in [7:4], so four of them add up to <= 32 in bits [5:0]; the symbol bytes above only
+// make junk that the wrap-around funnel shift ignores). The entries are also ORed together: one test after the
+// group tells whether any of the four was a deep or null entry, in which case nothing is committed and the caller
+// decodes the group one symbol at a time (decode_one). `row` is the shared-space address of the context's row.
+// Returns true when the group was committed; `packed` receives the four symbols, first symbol in the low byte.
+template <int ORDER>
+__device__ __forceinline__ bool decode_four(Cursor& cur, uint32_t lut_s, uint32_t& row, uint32_t& packed) {
+	uint32_t acc = 0, flg = 0, r = row, out = 0;
+#pragma unroll
+	for(int j = 0; j < 4; ++j) {
+		const uint32_t t = __funnelshift_l(cur.lo, cur.hi, acc);
+		uint32_t e;
+		asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(r + ((t >> 24) << 1)));
+		acc += e;
+		flg |= e;
+		out = __byte_perm(out, e, 0x5321);   // shift in byte 1 of e (the symbol)
+		if(ORDER) r = lut_s + ((e & 0xff00u) << 1);
+	}
+	if(flg & (kDeep | kNull)) return false;
+	cur.take_group(acc & 63u);
+	row = r;
+	packed = out;
+	return true;
 }
 
 // Decode every symbol whose first bit lies in [cur.pos, limit), counting them. The window is topped up once per
@@ -147,6 +197,71 @@ __device__ __forceinline__ bool decode_until(Cursor& cur, uint32_t lut_s, const 
 	return clean;
 }
 
+// D1's walker: decode one subsequence of kCp segments in ONE flat loop, so the lanes of a warp only wait for each
+// other at the end of the subsequence, not at every checkpoint. Each iteration decodes four symbols speculatively
+// (as decode_four) and commits those that START before the current segment end `cp_end` (at least one; all four
+// unless the group straddles the checkpoint — the rest is simply decoded again by the next iteration). A lane that
+// has reached `cp_end` records the checkpoint (state at the first codeword boundary at or after it, symbols that
+// started in the segment) in its next iteration. With `compare`, the walk stops at the first checkpoint whose
+// recorded state equals the walker's (the recorded trajectory is then its own). `cp_st` / `cp_cn` point at this
+// subsequence's column of the [kCp][kDecThreads] checkpoint arrays. Returns true when it stopped on a match.
+constexpr int kCp = 8;
+
+__device__ __forceinline__ uint32_t pack_cp(uint32_t rel_bits, uint32_t ctx) { return ((rel_bits > 255u ? 255u : rel_bits) << 8) | ctx; }
+
+template <int ORDER>
+__device__ __forceinline__ bool walk_subsequence(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
+                                                 const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t seg_bits, uint32_t span,
+                                                 uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
+	uint32_t cp_end = sub_begin, cnt = 0;
+	int j = -1;   // segment being decoded; the first pass through the record branch only sets up segment 0
+	bool clean = true;
+	for(;;) {
+		if(j < 0 || cur.pos >= cp_end) {
+			if(j >= 0) {
+				const uint16_t st = uint16_t(pack_cp(cur.pos - cp_end, ORDER ? (row - lut_s) >> 9 : 0u));
+				cp_cn[j * kDecThreads] = uint16_t(cnt);
+				if(compare && cp_st[j * kDecThreads] == st) return true;
+				cp_st[j * kDecThreads] = st;
+				cnt = 0;
+			}
+			if(++j == kCp) return false;
+			cp_end = sub_begin + uint32_t(j + 1) * seg_bits;
+			if(cp_end > span) cp_end = span;
+			continue;
+		}
+		// four speculative LUT hits
+		uint32_t a[5], r[5], flg = 0;
+		a[0] = 0; r[0] = row;
+#pragma unroll
+		for(int i = 0; i < 4; ++i) {
+			const uint32_t t = __funnelshift_l(cur.lo, cur.hi, a[i]);
+			uint32_t e;
+			asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(r[i] + ((t >> 24) << 1)));
+			a[i + 1] = a[i] + e;
+			flg |= e;
+			r[i + 1] = ORDER ? lut_s + ((e & 0xff00u) << 1) : row;
+		}
+		if(flg & (kDeep | kNull)) {   // rare: one symbol through the full path
+			uint32_t row_off = row - lut_s;
+			decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean);
+			row = lut_s + row_off;
+			++cnt;
+		} else if(cur.pos + (a[3] & 63u) < cp_end) {   // the fourth symbol still starts inside the segment
+			cur.take_group(a[4] & 63u);
+			row = r[4];
+			cnt += 4;
+		} else {   // the group straddles the checkpoint: keep the symbols that start before it
+			const uint32_t room = cp_end - cur.pos;
+			const int n = (a[2] & 63u) < room ? 3 : ((a[1] & 63u) < room ? 2 : 1);
+			cur.take_group((n == 3 ? a[3] : (n == 2 ? a[2] : a[1])) & 63u);
+			row = n == 3 ? r[3] : (n == 2 ? r[2] : r[1]);
+			cnt += n;
+		}
+		cur.top_up();
+	}
+}
+
 // Decode exactly `count` symbols and write them to `out`. Single bytes until the address is 8-byte aligned, then
 // eight symbols per aligned 64-bit store — every lane stores in the same iteration — then the ragged tail.
 template <int ORDER>
@@ -161,17 +276,24 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 		cur.top_up();
 	}
 	const uint32_t groups = (count - head) >> 3;
+	uint32_t row = lut_s + row_off;
 	for(uint32_t g = 0; g < groups; ++g) {
-		uint32_t lo = 0, hi = 0;
+		uint32_t w[2];
 #pragma unroll
-		for(int j = 0; j < 4; ++j) lo = __byte_perm(lo, decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean), 0x4321);
-		cur.top_up();
-#pragma unroll
-		for(int j = 0; j < 4; ++j) hi = __byte_perm(hi, decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean), 0x4321);
-		cur.top_up();
-		*reinterpret_cast<uint2*>(out) = make_uint2(lo, hi);
+		for(int h = 0; h < 2; ++h) {
+			if(!decode_four<ORDER>(cur, lut_s, row, w[h])) {   // a deep or null entry among the four: one symbol at a time
+				row_off = row - lut_s;
+				w[h] = 0;
+#pragma unroll 1
+				for(int j = 0; j < 4; ++j) w[h] = __byte_perm(w[h], decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean), 0x4321);
+				row = lut_s + row_off;
+			}
+			cur.top_up();
+		}
+		*reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
 		out += 8;
 	}
+	row_off = row - lut_s;
 	const uint32_t tail = (count - head) & 7;
 	for(uint32_t i = 0; i < tail; ++i) {
 		*out++ = uint8_t(decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean));
@@ -189,10 +311,6 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 // recorded one: from there on the recorded trajectory is its own. Per-segment counts (not running totals) make
 // the records of a partially overwritten subsequence consistent whoever wrote which segment.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kCp = 8;
-
-__device__ __forceinline__ uint32_t pack_cp(uint32_t rel_bits, uint32_t ctx) { return ((rel_bits > 255u ? 255u : rel_bits) << 8) | ctx; }
-
 template <int ORDER>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
@@ -228,26 +346,14 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		const uint64_t span = n_bits - origin;   // bits from the origin to the end of the stream
 		bool active = my_sub >= 0 && my_sub < end_sub;
 
-		// end of segment j of subsequence k, relative to origin, clipped to the end of the stream
-		auto limit_of = [&](int64_t k, int j) -> uint32_t {
-			const uint64_t e = uint64_t(k - origin_sub) * sub_bits + uint64_t(j + 1) * seg_bits;
-			return uint32_t(e < span ? e : span);
-		};
-
-		uint32_t ctx = ' ';
+		const uint32_t span32 = span > 0xffff0000ull ? 0xffff0000u : uint32_t(span);   // a CTA's window is a few Mbit
+		uint32_t row = lut_sa + (ORDER ? uint32_t(' ') << 9 : 0u);
 		int64_t k = my_sub;
 		if(active) {
-			uint32_t pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
-			if(my_sub == 0) ctx = start0 & 255u;   // the stream's own start (exact, or a shard's guess)
+			const uint32_t pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
+			if(ORDER && my_sub == 0) row = lut_sa + ((start0 & 255u) << 9);   // the stream's own start (exact, or a shard's guess)
 			cur.seek(origin + pos, pos);
-#pragma unroll 1
-			for(int j = 0; j < kCp; ++j) {
-				const uint32_t lim = limit_of(k, j);
-				uint32_t cnt = 0;
-				decode_until<ORDER, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt);
-				cp_state[j][tid] = uint16_t(pack_cp(cur.pos - lim, ORDER ? ctx : 0u));
-				cp_count[j][tid] = uint16_t(cnt);
-			}
+			walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, pos, seg_bits, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
 		}
 		__syncthreads();
 		// rounds: walk the successor's checkpoints until my state equals the recorded one
@@ -256,16 +362,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 			if(active && k >= end_sub) active = false;
 			if(active) {
 				const uint32_t slot = uint32_t(k - first_sub);
-#pragma unroll 1
-				for(int j = 0; j < kCp; ++j) {
-					const uint32_t lim = limit_of(k, j);
-					uint32_t cnt = 0;
-					decode_until<ORDER, true>(cur, lut_sa, lut_g, walk, lim, ctx, cnt);
-					const uint16_t st = uint16_t(pack_cp(cur.pos - lim, ORDER ? ctx : 0u));
-					cp_count[j][slot] = uint16_t(cnt);
-					if(cp_state[j][slot] == st) { active = false; break; }
-					cp_state[j][slot] = st;
-				}
+				const uint32_t begin = uint32_t(uint64_t(k - origin_sub) * sub_bits);
+				if(walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, begin, seg_bits, span32, row, &cp_state[0][slot], &cp_count[0][slot], true)) active = false;
 			}
 			if(!__syncthreads_or(active ? 1 : 0)) break;
 		}

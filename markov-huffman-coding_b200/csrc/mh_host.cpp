@@ -373,9 +373,10 @@ void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
 	}
 }
 
-void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
+uint32_t CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk, uint16_t* ext) const {
 	std::fill(lut, lut + trees.size() * 256, uint16_t((' ' << 8) | kLutNull | 1u));
 	std::fill(walk, walk + trees.size() * 512, uint32_t(0));
+	uint32_t rows = 0;
 	for(size_t t = 0; t < trees.size(); ++t) {
 		const CodeTree& tr = trees[t];
 		if(tr.empty()) continue;
@@ -383,7 +384,24 @@ void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
 			const int n = tr.lut(w);
 			if(n == kNoChild) continue;
 			const TreeNode& nd = tr.nodes[n];
-			lut[t * 256 + w] = nd.internal ? uint16_t((n << 7) | kLutDeep) : uint16_t((nd.symbol << 8) | nd.depth);
+			if(!nd.internal) {
+				lut[t * 256 + w] = uint16_t((nd.symbol << 8) | nd.depth);
+			} else if(rows < kExtRows) {
+				// second-level row for this depth-8 node: follow the next 8 bits, MSB first
+				uint16_t* row = ext + size_t(rows) * 256;
+				for(int w2 = 0; w2 < 256; ++w2) {
+					int cur = n, d = 0;
+					while(tr.nodes[cur].internal && d < 8) {
+						cur = ((w2 >> (7 - d)) & 1) ? tr.nodes[cur].right : tr.nodes[cur].left;
+						++d;
+					}
+					row[w2] = tr.nodes[cur].internal ? uint16_t((cur << 7) | kLutDeep) : uint16_t((tr.nodes[cur].symbol << 8) | d);
+				}
+				lut[t * 256 + w] = uint16_t((rows << 7) | kLutExt | kLutDeep);
+				++rows;
+			} else {
+				lut[t * 256 + w] = uint16_t((n << 7) | kLutDeep);
+			}
 		}
 		for(size_t n = 0; n < tr.nodes.size(); ++n) {
 			const TreeNode& nd = tr.nodes[n];
@@ -395,6 +413,7 @@ void CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk) const {
 			walk[t * 512 + n] = (child(nd.left) << 16) | child(nd.right);
 		}
 	}
+	return rows;
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -90,12 +90,20 @@ public:
 	// lut[ctx*256 + w]: leaf : symbol << 8 | length (1..8)
 	//                  deep : node index within the context << 7 | 0x10   (internal node at depth 8)
 	//                  null : ' ' << 8 | 0x20 | 1                         (speculation-safe; an error if verified)
+	//                  deep + ext : ext row << 7 | 0x40 | 0x10            (the first kExtRows deep nodes)
 	// walk[ctx*512 + node] = left << 16 | right, child = 0x8000|symbol for a leaf, else node index
-	void flatten_dectable(uint16_t* lut /* [trees.size() * 256] */, uint32_t* walk /* [trees.size() * 512] */) const;
+	// ext[row*256 + w2], indexed by the NEXT 8 stream bits after a deep entry: leaf within 16 bits:
+	//                  symbol << 8 | extra bits (1..8); else node index (depth 16) << 7 | 0x10 -> bit-by-bit walk.
+	//                  Same result as the reference's walk (src/coding.cpp:129-149), one lookup instead of <= 8 steps.
+	// Returns the number of ext rows used.
+	uint32_t flatten_dectable(uint16_t* lut /* [trees.size() * 256] */, uint32_t* walk /* [trees.size() * 512] */,
+	                          uint16_t* ext /* [kExtRows * 256] */) const;
 };
 
 constexpr uint16_t kLutDeep = 0x10;
 constexpr uint16_t kLutNull = 0x20;
+constexpr uint16_t kLutExt = 0x40;
+constexpr uint32_t kExtRows = 512;
 constexpr uint32_t kWalkLeaf = 0x8000;
 
 }  // namespace mh
