@@ -235,7 +235,16 @@ static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st) 
 	MH_CUDA(cudaMemcpyAsync(cb->d_enc, cb->h_stage, t->impl.trees.size() * 256 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 	cb->order = t->impl.order;
 	cb->max_bits = t->impl.max_code_bits();
-	cb->has_box = cb->max_bits <= kEncBoxMaxBits;
+	// preferred encoder table: rows for the live contexts only (text: a few dozen), next row carried by the entry
+	cb->ctx_rows = 0;
+	if(cb->max_bits <= kEncCtxMaxBits) {
+		if(!cb->d_ctx) MH_CUDA(cudaMalloc(&cb->d_ctx, size_t(kEncCtxMaxRows) * 256 * sizeof(uint32_t)));
+		if(!cb->h_ctx) MH_CUDA(cudaMallocHost(&cb->h_ctx, size_t(kEncCtxMaxRows) * 256 * sizeof(uint32_t)));
+		cb->ctx_rows = t->impl.flatten_ctx(cb->h_ctx, kEncCtxMaxRows);
+		if(cb->ctx_rows) MH_CUDA(cudaMemcpyAsync(cb->d_ctx, cb->h_ctx, size_t(cb->ctx_rows) * 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+	}
+	// the box table is only needed when the context rows are not available (or a test forces another format)
+	cb->has_box = cb->max_bits <= kEncBoxMaxBits && (cb->ctx_rows == 0 || getenv("MH_ENC_FMT") != nullptr);
 	if(cb->has_box) {
 		if(!cb->d_box) MH_CUDA(cudaMalloc(&cb->d_box, 257 * 257 * sizeof(uint32_t)));
 		if(!cb->h_box) MH_CUDA(cudaMallocHost(&cb->h_box, 257 * 257 * sizeof(uint32_t)));
@@ -273,6 +282,8 @@ static void release_book(mh_codebook* cb) {
 	if(cb->h_stage) cudaFreeHost(cb->h_stage);
 	if(cb->d_box) cudaFree(cb->d_box);
 	if(cb->h_box) cudaFreeHost(cb->h_box);
+	if(cb->d_ctx) cudaFree(cb->d_ctx);
+	if(cb->h_ctx) cudaFreeHost(cb->h_ctx);
 	*cb = mh_codebook();
 }
 

@@ -34,6 +34,7 @@ namespace {
 constexpr int FMT_BOX_SMEM = 0;     // u32 box table in shared memory
 constexpr int FMT_BOX_GLOBAL = 1;   // u32 box table gathered from global memory
 constexpr int FMT_WIDE = 2;         // u64 entries (8-bit length | 56-bit code) gathered from global memory
+constexpr int FMT_CTX = 3;          // u32 context rows in shared memory: len << 27 | next row << 16 | code (<= 16 bits)
 
 constexpr uint64_t kAgg = 1ull << 62;   // aggregate word : kAgg | bits of this tile
 constexpr uint64_t kInc = 2ull << 62;   // inclusive word : kInc | bits of all tiles up to and including this one
@@ -93,6 +94,8 @@ struct EncArgs {
 	const unsigned long long* wide;   // FMT_WIDE table: len << 56 | code
 	const uint32_t* box;              // u32 box table with a zero border: (R + 1) x (R + 1), or 256 entries (order 0)
 	uint32_t box_lo, box_r;
+	const uint32_t* ctx;              // FMT_CTX table: ctx_rows x 256 entries, the last row is the null row
+	uint32_t ctx_rows;
 	uint32_t bit0;
 	uint32_t stage_words;
 	uint32_t* out_words;
@@ -223,7 +226,31 @@ struct Packer {
 	__device__ __forceinline__ void finish() { red_or_if(word, hi, fill != 0); }
 };
 
-template <int SPT, int FMT, bool ALIGNED>
+// FMT_CTX packer: `fill` (< 32) pending bits RIGHT-aligned in `pend`; whatever sits above them is garbage that never
+// reaches an emitted word. Appends right-aligned units of len <= 32 bits.
+struct Packer32 {
+	uint32_t word;   // shared-space byte address of the word being filled
+	uint32_t pend, fill;
+	__device__ __forceinline__ void start(uint32_t stage_addr, uint32_t pos) { word = stage_addr + ((pos >> 5) << 2); pend = 0; fill = pos & 31; }
+	__device__ __forceinline__ void put(uint32_t v, uint32_t len) {
+		uint32_t tlo;
+		asm("shl.b32 %0, %1, %2;" : "=r"(tlo) : "r"(pend), "r"(len));   // PTX shifts clamp: len == 32 -> 0
+		tlo |= v;
+		const uint32_t thi = __funnelshift_lc(pend, 0u, len);           // pend >> (32 - len), 0 for len == 0
+		const uint32_t nf = fill + len;                                 // < 64
+		red_or_if(word, __funnelshift_r(tlo, thi, nf), nf >= 32);       // bits [nf - 32, nf) of thi:tlo (shift wraps to nf - 32)
+		word += (nf >> 5) << 2;
+		pend = tlo;
+		fill = nf & 31;
+	}
+	__device__ __forceinline__ void finish() {
+		uint32_t v;
+		asm("shl.b32 %0, %1, %2;" : "=r"(v) : "r"(pend), "r"(32u - fill));
+		red_or_if(word, v, fill != 0);
+	}
+};
+
+template <int SPT, int FMT, bool ALIGNED, int ORDER = 1>
 __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 	constexpr int NWORDS = SPT / 4;
 	extern __shared__ uint32_t smem[];
@@ -238,6 +265,10 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 	if(FMT == FMT_BOX_SMEM) {
 		table_entries = A.order ? (A.box_r + 1) * (A.box_r + 1) : 256u;
 		for(uint32_t i = tid; i < table_entries; i += kEncThreads) table[i] = __ldg(A.box + i);
+	}
+	if(FMT == FMT_CTX) {
+		table_entries = A.ctx_rows * 256u;
+		for(uint32_t i = tid; i < table_entries / 4; i += kEncThreads) reinterpret_cast<uint4*>(table)[i] = __ldg(reinterpret_cast<const uint4*>(A.ctx) + i);
 	}
 	uint32_t* stage = smem + ((table_entries + 3) & ~3u);   // [stage_words + 4]
 	const uint32_t table_sa = uint32_t(__cvta_generic_to_shared(table));
@@ -265,8 +296,10 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 
 		// ================= phase A: load, look up, count (tile `tile`) =================
 		uint32_t tile_bits = 0, pos = 0;
-		uint32_t e32[FMT != FMT_WIDE ? SPT : 1];
+		uint32_t e32[(FMT == FMT_BOX_SMEM || FMT == FMT_BOX_GLOBAL) ? SPT : 1];
 		unsigned long long e64[FMT == FMT_WIDE ? SPT : 1];
+		uint32_t q_hi[FMT == FMT_CTX ? SPT / 4 : 1], q_lo[FMT == FMT_CTX ? SPT / 4 : 1], q_len[FMT == FMT_CTX ? SPT / 4 : 1];
+		bool escape = false;   // FMT_CTX: one of this thread's symbols has a codeword longer than 16 bits
 		if(valid) {
 			uint32_t w[NWORDS];
 #pragma unroll
@@ -289,7 +322,67 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			uint32_t prev = __shfl_up_sync(0xffffffffu, w[NWORDS - 1] >> 24, 1);
 			if(lane == 0 && my < A.n) prev = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
 			uint32_t my_bits = 0;
-			if constexpr(FMT != FMT_WIDE) {
+			if constexpr(FMT == FMT_CTX) {
+				// One shared-memory lookup per symbol; the entry names the next context's row, so the dependent chain
+				// is lookup -> byte select -> multiply-add -> lookup. Codewords are merged on the fly: pairs (<= 32
+				// bits), then quads kept as (hi:lo, length) — a quad longer than 32 bits goes out in two steps.
+				const uint32_t null_row = table_sa + (A.ctx_rows - 1) * 1024u;
+				uint32_t row = table_sa;
+				if(ORDER) row = table_sa + __byte_perm(lds32(null_row + prev * 4), 0, 0x4442) * 1024u;
+				uint32_t floor = 0xffffffffu, ceil = 0;
+				auto lookup = [&](int i, bool checked) -> uint32_t {
+					const uint32_t c = __byte_perm(w[i >> 2], 0, 0x4440 + (i & 3));
+					uint32_t ent = 0;
+					if(!checked || i < live) {
+						ent = lds32(row + c * 4);
+						if(ORDER) row = table_sa + __byte_perm(ent, 0, 0x4442) * 1024u;
+						floor = min(floor, ent);
+						ceil = max(ceil, ent);
+					}
+					return ent;
+				};
+				auto quads = [&](bool checked) {
+#pragma unroll
+					for(int q = 0; q < SPT / 4; ++q) {
+						const uint32_t e0 = lookup(4 * q, checked), e1 = lookup(4 * q + 1, checked), e2 = lookup(4 * q + 2, checked), e3 = lookup(4 * q + 3, checked);
+						const uint32_t l1 = e1 >> 27, l3 = e3 >> 27;
+						const uint32_t lp0 = (e0 >> 27) + l1, lp1 = (e2 >> 27) + l3;
+						const uint32_t p0 = ((e0 & 0xffffu) << l1) | (e1 & 0xffffu);
+						const uint32_t p1 = ((e2 & 0xffffu) << l3) | (e3 & 0xffffu);
+						uint32_t lo;
+						asm("shl.b32 %0, %1, %2;" : "=r"(lo) : "r"(p0), "r"(lp1));   // lp1 may be 32
+						q_lo[q] = lo | p1;
+						q_hi[q] = __funnelshift_lc(p0, 0u, lp1);
+						q_len[q] = lp0 + lp1;
+						my_bits += lp0 + lp1;
+					}
+				};
+				if(live == SPT) quads(false);
+				else quads(true);
+				if((ceil >> 27) == 31u) {   // rare: a codeword longer than 16 bits; this thread redoes its symbols from the wide table
+					escape = true;
+					my_bits = 0;
+					uint32_t p = prev;
+#pragma unroll 1
+					for(int i = 0; i < live; ++i) {
+						const uint32_t c = A.in[my + i];
+						const unsigned long long ent = __ldg(A.wide + ((ORDER ? p : 0u) << 8) + c);
+						if(ent == 0) ++dropped;
+						my_bits += uint32_t(ent >> 56);
+						p = c;
+					}
+				} else if(floor < (1u << 27)) {   // rare: some symbol has no codeword; recount them exactly (context rows again)
+					uint32_t r2 = table_sa;
+					if(ORDER) r2 = table_sa + __byte_perm(lds32(null_row + prev * 4), 0, 0x4442) * 1024u;
+#pragma unroll 1
+					for(int i = 0; i < live; ++i) {
+						const uint32_t c = A.in[my + i];   // re-read: indexing w[] dynamically would push it to local memory
+						const uint32_t ent = lds32(r2 + c * 4);
+						if(ORDER) r2 = table_sa + __byte_perm(ent, 0, 0x4442) * 1024u;
+						dropped += (ent >> 27) == 0 ? 1u : 0u;
+					}
+				}
+			} else if constexpr(FMT != FMT_WIDE) {
 				// entries: length in [31:27], right-aligned code in [26:0]
 				uint32_t floor = 0xffffffffu;
 				// byte address of the current context's row (box formats keep the border row at index R)
@@ -377,9 +470,39 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 
 		// ================= phase C: pack tile `tile` into the staging area =================
 		if(valid) {
+			if constexpr(FMT == FMT_CTX) {
+				if(escape) {
+					Packer pw;
+					pw.start(stage_sa, pos);
+					const int live = A.n - my >= uint64_t(SPT) ? SPT : int(A.n - my);
+					uint32_t p = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
+#pragma unroll 1
+					for(int i = 0; i < live; ++i) {
+						const uint32_t c = A.in[my + i];
+						const unsigned long long ent = __ldg(A.wide + ((ORDER ? p : 0u) << 8) + c);
+						pw.put(ent & 0x00ffffffffffffffull, uint32_t(ent >> 56));
+						p = c;
+					}
+					pw.finish();
+				} else {
+				Packer32 pk;
+				pk.start(stage_sa, pos);
+#pragma unroll
+				for(int q = 0; q < SPT / 4; ++q) {
+					if(q_len[q] <= 32) {
+						pk.put(q_lo[q], q_len[q]);
+					} else {   // a quad of long codewords: the top q_len - 32 bits, then the low word
+						pk.put(q_hi[q], q_len[q] - 32);
+						pk.put(q_lo[q], 32);
+					}
+				}
+				pk.finish();
+				}
+			}
 			Packer pk;
 			pk.start(stage_sa, pos);
-			if constexpr(FMT != FMT_WIDE) {
+			if constexpr(FMT == FMT_CTX) {
+			} else if constexpr(FMT != FMT_WIDE) {
 				// merge pairs -> quads, funnel through the window
 #pragma unroll
 				for(int q = 0; q < SPT / 4; ++q) {
@@ -398,7 +521,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 #pragma unroll
 				for(int i = 0; i < SPT; ++i) pk.put(e64[i] & 0x00ffffffffffffffull, uint32_t(e64[i] >> 56));
 			}
-			pk.finish();
+			if constexpr(FMT != FMT_CTX) pk.finish();
 			__syncthreads();   // staged bits visible
 			if(tid == 0) {     // the tail goes out now: successors need it only when they write their first word
 				const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
@@ -413,9 +536,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 	if(lane == 0 && dropped) atomicAdd(A.result + 1, (unsigned long long) dropped);
 }
 
-template <int SPT, int FMT>
+template <int SPT, int FMT, int ORDER = 1>
 int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStream_t st) {
-	auto kern = aligned ? encode_kernel<SPT, FMT, true> : encode_kernel<SPT, FMT, false>;
+	auto kern = aligned ? encode_kernel<SPT, FMT, true, ORDER> : encode_kernel<SPT, FMT, false, ORDER>;
 	MH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
 	int per_sm = 0;
 	MH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEncThreads, smem_bytes));
@@ -454,6 +577,11 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 		fmt = table_bytes <= size_t(kEncBoxSmemLimit) && force_fmt != FMT_BOX_GLOBAL ? FMT_BOX_SMEM : FMT_BOX_GLOBAL;
 	}
 	if(fmt != FMT_BOX_SMEM) table_bytes = 0;
+	// context rows (live contexts only, <= 16-bit codewords): preferred whenever table + staging fit two CTAs per SM
+	if(cb->ctx_rows && force_fmt < 0 && size_t(cb->ctx_rows) * 1024 + (size_t(kEncThreads) * maxb + 64) * 4 <= size_t(kEncCtxSmemLimit)) {
+		fmt = FMT_CTX;
+		table_bytes = size_t(cb->ctx_rows) * 1024;
+	}
 	// Tile size: the staged bits of one tile must fit the staging area whatever the input, so symbols per tile x
 	// longest codeword bounds it: 32 symbols per thread while that bound stays within kEncStageMaxWords.
 	int spt = 16;
@@ -470,6 +598,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.in = d_in; a.n = n; a.prev0 = prev0; a.order = cb->order;
 	a.wide = reinterpret_cast<const unsigned long long*>(cb->d_enc);
 	a.box = cb->d_box; a.box_lo = cb->box_lo; a.box_r = cb->box_r;
+	a.ctx = cb->d_ctx; a.ctx_rows = cb->ctx_rows;
 	a.bit0 = uint32_t(bit_base & 7);
 	a.stage_words = stage_words;
 	a.out_words = reinterpret_cast<uint32_t*>(d_out);
@@ -483,6 +612,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	const bool aligned = (reinterpret_cast<uint64_t>(d_in) & 15) == 0;
 	const size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 4) * sizeof(uint32_t);
 
+	if(fmt == FMT_CTX) return cb->order ? launch_variant<32, FMT_CTX, 1>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0>(aligned, a, smem, st);
 	if(fmt == FMT_WIDE) return launch_variant<16, FMT_WIDE>(aligned, a, smem, st);
 	if(fmt == FMT_BOX_SMEM) return spt == 32 ? launch_variant<32, FMT_BOX_SMEM>(aligned, a, smem, st) : launch_variant<16, FMT_BOX_SMEM>(aligned, a, smem, st);
 	return spt == 32 ? launch_variant<32, FMT_BOX_GLOBAL>(aligned, a, smem, st) : launch_variant<16, FMT_BOX_GLOBAL>(aligned, a, smem, st);

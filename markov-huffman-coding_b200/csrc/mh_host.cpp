@@ -373,6 +373,33 @@ void CodingTable::flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const {
 	}
 }
 
+uint32_t CodingTable::flatten_ctx(uint32_t* table, uint32_t max_rows) const {
+	int rank[256];
+	uint32_t live = 0;
+	for(int p = 0; p < 256; ++p) {
+		const bool has = order ? !trees[p].empty() : (p == 0 && !trees[0].empty());
+		rank[p] = has ? int(live++) : -1;
+	}
+	const uint32_t rows = live + 1;   // + the null row
+	if(rows > max_rows) return 0;
+	auto next_of = [&](int c) -> uint32_t { return order ? (rank[c] >= 0 ? uint32_t(rank[c]) : live) : 0u; };
+	for(int p = 0; p < 256; ++p) {
+		if(rank[p] < 0) continue;
+		const CodeTree& tr = trees[order ? p : 0];
+		uint32_t* row = table + size_t(rank[p]) * 256;
+		for(int c = 0; c < 256; ++c) {
+			const Codeword& cw = tr.code(c);
+			// codewords longer than 16 bits (rare by construction) carry the marker length 31: the encoder then takes
+			// the symbol from the wide table instead
+			row[c] = cw.length > 16 ? (31u << 27) | (next_of(c) << 16)
+			                        : (uint32_t(cw.length) << 27) | (next_of(c) << 16) | (cw.length ? uint32_t(cw.value) : 0u);
+		}
+	}
+	uint32_t* null_row = table + size_t(live) * 256;
+	for(int c = 0; c < 256; ++c) null_row[c] = next_of(c) << 16;
+	return rows;
+}
+
 uint32_t CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk, uint16_t* ext) const {
 	std::fill(lut, lut + trees.size() * 256, uint16_t((' ' << 8) | kLutNull | 1u));
 	std::fill(walk, walk + trees.size() * 512, uint32_t(0));

@@ -87,6 +87,12 @@ public:
 	// <= 27. Row r and column r are a zero border that out-of-range bytes are clamped onto.
 	// `box` must hold (r + 1) * (r + 1) (order 1) or 256 (order 0) entries.
 	void flatten_box(uint32_t lo, uint32_t r, uint32_t* box) const;
+	// Context-row table for the encoder: one 256-entry row per NON-EMPTY context (ranked in ascending byte order)
+	// plus a final null row. entry = len << 27 | next_row << 16 | code, where next_row is the row of the byte as
+	// the NEXT symbol's context (the null row if that context has no tree). The null row has len 0 everywhere: a
+	// symbol without a codeword is dropped, like the reference's zero-length descriptor (src/coding.cpp:72). A
+	// codeword longer than 16 bits is stored as the marker length 31 (the encoder reads it from the wide table). Returns the number of rows (live contexts + 1), or 0 if there are more than `max_rows`.
+	uint32_t flatten_ctx(uint32_t* table /* [max_rows * 256] */, uint32_t max_rows) const;
 	// lut[ctx*256 + w]: leaf : symbol << 8 | length (1..8)
 	//                  deep : node index within the context << 7 | 0x10   (internal node at depth 8)
 	//                  null : ' ' << 8 | 0x20 | 1                         (speculation-safe; an error if verified)

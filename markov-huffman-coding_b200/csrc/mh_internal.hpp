@@ -37,6 +37,9 @@ constexpr int kEncThreads = 512;
 constexpr int kEncStageMaxWords = 14336;              // at most 56 KiB of staged output bits per tile
 constexpr int kEncBoxSmemLimit = 72 * 1024;           // largest u32 box table staged in shared memory (R <= 135)
 constexpr int kEncBoxMaxBits = 27;                    // u32 entry: 5-bit length | 27-bit right-aligned code
+constexpr int kEncCtxMaxBits = 28;                    // context-row entry: 5-bit length | 8-bit next row | 16-bit code; longer codewords (<= 28) escape to the wide table
+constexpr int kEncCtxMaxRows = 96;                    // live contexts + null row; table + staging must leave room for 2 CTAs/SM
+constexpr int kEncCtxSmemLimit = 112 * 1024;          // table + staging area of one CTA
 constexpr int kDecThreads = 1024;                     // subsequences per chunk (one thread each)
 constexpr int kDecMinSubBits = 256;
 constexpr uint32_t kDecMaxSubBitsMarkov = 8192;       // measured best of 2048..16384 on the 1 GiB Markov text
@@ -77,6 +80,9 @@ struct mh_codebook {
 	uint32_t* d_box = nullptr;     // [(R + 1)^2] with a zero border (order 1) or [256] (order 0): len << 27 | code
 	uint32_t box_lo = 0, box_r = 256;
 	bool has_box = false;
+	uint32_t* d_ctx = nullptr;     // [ctx_rows * 256] len << 27 | next row << 16 | code (max_bits <= 16, few live contexts)
+	uint32_t* h_ctx = nullptr;     // pinned
+	uint32_t ctx_rows = 0;         // 0: no context-row table
 	uint64_t* h_stage = nullptr;   // pinned image the async upload reads from
 	uint32_t* h_box = nullptr;     // pinned
 	cudaEvent_t uploaded = nullptr;
