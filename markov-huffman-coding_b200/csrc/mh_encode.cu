@@ -323,9 +323,11 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			if(lane == 0 && my < A.n) prev = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
 			uint32_t my_bits = 0;
 			if constexpr(FMT == FMT_CTX) {
-				// One shared-memory lookup per symbol; the entry names the next context's row, so the dependent chain
-				// is lookup -> byte select -> multiply-add -> lookup. Codewords are merged on the fly: pairs (<= 32
-				// bits), then quads kept as (hi:lo, length) — a quad longer than 32 bits goes out in two steps.
+				// One shared-memory lookup per symbol; the entry names the next context's row, so inside a quad the
+				// dependent chain is lookup -> byte select -> multiply-add -> lookup. Every quad restarts the chain from
+				// the byte before it (its row comes from the null row), so the eight quads of a thread are independent.
+				// Codewords are merged on the fly: pairs (<= 32 bits), then quads kept as (hi:lo, length) — a quad
+				// longer than 32 bits goes out in two steps.
 				const uint32_t null_row = table_sa + (A.ctx_rows - 1) * 1024u;
 				uint32_t row = table_sa;
 				if(ORDER) row = table_sa + __byte_perm(lds32(null_row + prev * 4), 0, 0x4442) * 1024u;
@@ -344,6 +346,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 				auto quads = [&](bool checked) {
 #pragma unroll
 					for(int q = 0; q < SPT / 4; ++q) {
+						if(ORDER && q) row = table_sa + __byte_perm(lds32(null_row + __byte_perm(w[q - 1], 0, 0x4443) * 4), 0, 0x4442) * 1024u;
 						const uint32_t e0 = lookup(4 * q, checked), e1 = lookup(4 * q + 1, checked), e2 = lookup(4 * q + 2, checked), e3 = lookup(4 * q + 3, checked);
 						const uint32_t l1 = e1 >> 27, l3 = e3 >> 27;
 						const uint32_t lp0 = (e0 >> 27) + l1, lp1 = (e2 >> 27) + l3;
@@ -428,6 +431,12 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			// block exclusive scan; the tile's bit count is published right away
 			pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
 			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
+			// the next ticket is visible since the scan's barrier: pull that tile's input into L2 while this one packs
+			const uint32_t next_tile = s_tile[(it + 1) & 1];
+			if((tid & 3) == 0 && next_tile < A.n_tiles) {
+				const uint64_t off = uint64_t(next_tile) * (kEncThreads * SPT) + uint64_t(tid) * SPT;
+				if(off < A.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.in + off));
+			}
 		}
 
 		// ================= phase B: resolve and write out the pending tile =================
