@@ -75,6 +75,11 @@ int mh_table_max_code_bits(const mh_table* t);
 int mh_table_code_lengths(const mh_table* t, uint8_t* lens, size_t cap);
 /* decoding_lookup(prev, w) (src/coding.h:34): kind 0 null, 1 leaf (value, depth), 2 internal node at depth 8. */
 int mh_table_lookup(const mh_table* t, int prev, int window, int* kind, int* value, int* depth);
+/* The decoder's two-symbol table over the live contexts (derived from decoding_lookup, src/coding.h:34; layout in
+ * csrc/mh_host.hpp, flatten_pairlut): table[rows * 256] u32 entries, maps = rank[256] | live[64] | len1[ctx_rows * 256].
+ * `table` needs 64 * 256 entries, `maps` 256 + 64 * 257 bytes. *rows = 0 when the table has more than 63 live contexts
+ * (the decoder then uses the 8-bit LUT alone). Introspection for tests; the GPU path builds the same image itself. */
+int mh_table_pair_lut(const mh_table* t, uint32_t* table, uint8_t* maps, uint32_t* rows, uint32_t* ctx_rows);
 /* print_table() + print_tree() (src/coding.h:21-22): the `-g` dump, written to the caller's buffer. */
 int mh_table_debug_dump(const mh_table* t, char* out, size_t cap, size_t* n_out);
 void mh_table_destroy(mh_table* t);

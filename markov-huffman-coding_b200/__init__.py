@@ -69,6 +69,7 @@ _SIGNATURES = {
     "mh_table_max_code_bits": (_i, [_vp]),
     "mh_table_code_lengths": (_i, [_vp, _vp, _sz]),
     "mh_table_lookup": (_i, [_vp, _i, _i, _pi, _pi, _pi]),
+    "mh_table_pair_lut": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "mh_table_debug_dump": (_i, [_vp, _vp, _sz, _psz]),
     "mh_table_destroy": (None, [_vp]),
     "mh_codebook_create": (_i, [_vp, _pp]),
@@ -225,6 +226,18 @@ class CodingProvider:
         k, v, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         _check(_lib.mh_table_lookup(self._h, prev, window, ctypes.byref(k), ctypes.byref(v), ctypes.byref(d)), "mh_table_lookup")
         return k.value, v.value, d.value
+
+    def pair_lut(self):
+        """The decoder's two-symbol table: (table u32[rows*256], rank u8[256], live u8[64], len1 u8[ctx_rows*256], rows,
+        ctx_rows) as numpy arrays, or None when the table has more than 63 live contexts."""
+        import numpy as np
+        table = np.zeros(64 * 256, dtype=np.uint32)
+        maps = np.zeros(256 + 64 * 257, dtype=np.uint8)
+        rows, ctx_rows = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        _check(_lib.mh_table_pair_lut(self._h, table.ctypes.data, maps.ctypes.data, ctypes.byref(rows), ctypes.byref(ctx_rows)), "mh_table_pair_lut")
+        if rows.value == 0:
+            return None
+        return (table[: rows.value * 256], maps[:256], maps[256:320], maps[320 : 320 + ctx_rows.value * 256], rows.value, ctx_rows.value)
 
     def debug_dump(self):
         """print_table() followed by print_tree(): the `-g` output."""

@@ -209,6 +209,13 @@ int mh_table_lookup(const mh_table* t, int prev, int window, int* kind, int* val
 	return MH_OK;
 }
 
+int mh_table_pair_lut(const mh_table* t, uint32_t* table, uint8_t* maps, uint32_t* rows, uint32_t* ctx_rows) {
+	if(!t || !table || !maps || !rows || !ctx_rows) return MH_ERR_INVALID_ARG;
+	*ctx_rows = 0;
+	*rows = t->impl.flatten_pairlut(table, maps, kPairMaxRows, ctx_rows);
+	return MH_OK;
+}
+
 int mh_table_debug_dump(const mh_table* t, char* out, size_t cap, size_t* n_out) {
 	if(!t || !n_out) return MH_ERR_INVALID_ARG;
 	std::string s = t->impl.debug_dump();
@@ -270,6 +277,18 @@ static int upload_dectable(const mh_table* t, mh_dectable* dt, cudaStream_t st) 
 	const uint32_t ext_rows = t->impl.flatten_dectable(dt->h_lut, dt->h_walk, reinterpret_cast<uint16_t*>(dt->h_walk + ntab * 512));
 	MH_CUDA(cudaMemcpyAsync(dt->d_lut, dt->h_lut, ntab * 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
 	MH_CUDA(cudaMemcpyAsync(dt->d_walk, dt->h_walk, ntab * 512 * sizeof(uint32_t) + size_t(ext_rows) * 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+	// two-symbol table over the live contexts (text: a few dozen rows), preferred by the decoder when it exists
+	if(!dt->d_pair) MH_CUDA(cudaMalloc(&dt->d_pair, kDecPairBytes));
+	if(!dt->h_pair) MH_CUDA(cudaMallocHost(&dt->h_pair, kDecPairBytes));
+	{
+		static thread_local uint8_t maps[256 + kPairMaxRows * 257];
+		dt->pair_rows = t->impl.flatten_pairlut(dt->h_pair, maps, kPairMaxRows, &dt->pair_ctx_rows);
+		if(dt->pair_rows) {
+			const size_t map_bytes = 256 + kPairMaxRows + size_t(dt->pair_ctx_rows) * 256;
+			memcpy(dt->h_pair + size_t(dt->pair_rows) * 256, maps, map_bytes);
+			MH_CUDA(cudaMemcpyAsync(dt->d_pair, dt->h_pair, size_t(dt->pair_rows) * 1024 + map_bytes, cudaMemcpyHostToDevice, st));
+		}
+	}
 	MH_CUDA(cudaEventRecord(dt->uploaded, st));
 	dt->order = t->impl.order;
 	dt->max_bits = t->impl.max_code_bits();
@@ -293,6 +312,8 @@ static void release_dec(mh_dectable* dt) {
 	if(dt->d_walk) cudaFree(dt->d_walk);
 	if(dt->h_lut) cudaFreeHost(dt->h_lut);
 	if(dt->h_walk) cudaFreeHost(dt->h_walk);
+	if(dt->d_pair) cudaFree(dt->d_pair);
+	if(dt->h_pair) cudaFreeHost(dt->h_pair);
 	*dt = mh_dectable();
 }
 

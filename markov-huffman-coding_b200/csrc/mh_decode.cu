@@ -262,6 +262,217 @@ __device__ __forceinline__ bool walk_subsequence(Cursor& cur, uint32_t lut_s, co
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pair table (CodingTable::flatten_pairlut): u32 entries over the LIVE contexts only, each resolving up to two
+// symbols from the next 8 stream bits. Entry: [5:0] bits consumed (bits 4, 5 = deep / null flags), [9:6] symbols
+// produced, [15:10] next row, [23:16] first symbol, [31:24] second symbol or 0. Four entries are summed like the u16
+// entries above: the low 6 bits of the sum are the bits consumed (<= 32), bits [9:6] the symbols produced (<= 8).
+// A codeword of 9..16 bits is two ordinary entries: a prefix entry (8 bits, no symbol, next row = the prefix row of
+// its depth-8 node) and an entry of that prefix row — no branch. Text has a few dozen live contexts, so the table
+// takes ~50 KiB of shared memory instead of 128 KiB, and one dependent lookup yields ~1.85 symbols. Flagged entries
+// (longer codewords, missing table entries) go through the u16 LUT / walk table in global memory (decode_one).
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPairFlags = kDeep | kNull;
+constexpr uint32_t kPairCount = 0xc0u;   // symbols produced by one entry: 0x40 one, 0x80 two, 0 = prefix entry
+
+struct PairTab {
+	uint32_t tab;    // shared-space address of the table (row r at tab + r * 1024)
+	uint32_t rank;   // shared-space address of rank[256]: row of a byte as context
+	uint32_t live;   // shared-space address of live[64]: context byte of a context row
+	uint32_t len1;   // shared-space address of len1[ctx_rows * 256]: length of an entry's first codeword
+	uint32_t null_row;
+};
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+	uint32_t v;
+	asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+	uint32_t v;
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+__host__ __device__ __forceinline__ uint32_t pair_table_bytes(uint32_t rows, uint32_t ctx_rows) { return rows * 1024u + 256u + 64u + ctx_rows * 256u; }
+
+// Stage the pair table and its byte maps in shared memory (all threads; the caller synchronises).
+__device__ __forceinline__ PairTab stage_pair_table(uint32_t* smem, const uint32_t* __restrict__ pair_g, uint32_t rows, uint32_t ctx_rows) {
+	const uint32_t n16 = pair_table_bytes(rows, ctx_rows) / 16u;
+	const uint4* src = reinterpret_cast<const uint4*>(pair_g);
+	uint4* dst = reinterpret_cast<uint4*>(smem);
+	for(uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+	PairTab T;
+	asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(T.tab) : "l"(smem));
+	T.rank = T.tab + rows * 1024u;
+	T.live = T.rank + 256u;
+	T.len1 = T.live + 64u;
+	T.null_row = T.tab + ctx_rows * 1024u;
+	return T;
+}
+
+template <int ORDER>
+__device__ __forceinline__ uint32_t pair_row_of(const PairTab& T, uint32_t ctx) { return ORDER ? T.tab + (lds_u8(T.rank + ctx) << 10) : T.tab; }
+
+// Four speculative lookups; the window is left untouched. a[i] = sum of the first i entries, r[i] = row after them.
+template <int ORDER>
+__device__ __forceinline__ void pair_lookups(const Cursor& cur, const PairTab& T, uint32_t row, uint32_t (&e)[4], uint32_t (&a)[5], uint32_t (&r)[5]) {
+	a[0] = 0;
+	r[0] = row;
+#pragma unroll
+	for(int i = 0; i < 4; ++i) {
+		const uint32_t t = __funnelshift_l(cur.lo, cur.hi, a[i]);
+		e[i] = lds_u32(r[i] + ((t >> 24) << 2));
+		a[i + 1] = a[i] + e[i];
+		r[i + 1] = T.tab + (e[i] & 0xfc00u);   // order 0: context row 0, or a prefix row
+	}
+}
+
+// One symbol through the reference's path (u16 LUT + walk table in global memory), keeping `row` in step.
+// `row` must be a context row or the null row.
+template <int ORDER>
+__device__ __forceinline__ uint32_t pair_slow_one(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
+                                                  const uint32_t* __restrict__ walk, uint32_t& row, bool& clean) {
+	uint32_t row_off = ORDER ? lds_u8(T.live + ((row - T.tab) >> 10)) << 9 : 0u;
+	const uint32_t sym = decode_one<ORDER, false>(cur, 0u, lut_g, walk, row_off, clean);
+	if(ORDER) row = T.tab + (lds_u8(T.rank + sym) << 10);
+	return sym;
+}
+
+// Exactly one symbol, given the entry e0 the window selects in `row`: a single-symbol entry is taken as it is, a
+// pair gives up its first symbol only (its length comes from len1), a prefix or flagged entry — which only live in
+// context rows — goes through the global tables.
+template <int ORDER>
+__device__ __forceinline__ uint32_t pair_step_one(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
+                                                  const uint32_t* __restrict__ walk, uint32_t e0, uint32_t& row, bool& clean) {
+	if((e0 & kPairFlags) || !(e0 & kPairCount)) return pair_slow_one<ORDER>(cur, T, lut_g, walk, row, clean);
+	const uint32_t sym = (e0 >> 16) & 255u;
+	if(e0 & 0x80u) {
+		cur.take(lds_u8(T.len1 + ((row - T.tab) >> 2) + (cur.hi >> 24)));
+		row = pair_row_of<ORDER>(T, sym);
+	} else {
+		cur.take(e0 & 15u);
+		row = T.tab + (e0 & 0xfc00u);
+	}
+	return sym;
+}
+
+// walk_subsequence over the pair table. A group (or its first 3 / 2 / 1 lookups) is committed when all its bits lie
+// before the segment end — then every symbol in it starts before the end — and it does not stop on a prefix entry,
+// so the walker only ever rests on codeword boundaries; whatever is left before the end goes one symbol at a time.
+// Checkpoints record the ROW (not the context byte): equality is all the comparison needs.
+template <int ORDER>
+__device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
+                                                      const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t seg_bits, uint32_t span,
+                                                      uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
+	uint32_t cp_end = sub_begin, cnt = 0;
+	int j = -1;
+	bool clean = true;
+	for(;;) {
+		if(j < 0 || cur.pos >= cp_end) {
+			if(j >= 0) {
+				const uint16_t st = uint16_t(pack_cp(cur.pos - cp_end, (row - T.tab) >> 10));
+				cp_cn[j * kDecThreads] = uint16_t(cnt);
+				if(compare && cp_st[j * kDecThreads] == st) return true;
+				cp_st[j * kDecThreads] = st;
+				cnt = 0;
+			}
+			if(++j == kCp) return false;
+			cp_end = sub_begin + uint32_t(j + 1) * seg_bits;
+			if(cp_end > span) cp_end = span;
+			continue;
+		}
+		uint32_t e[4], a[5], r[5];
+		pair_lookups<ORDER>(cur, T, row, e, a, r);
+		const uint32_t room = cp_end - cur.pos;
+		const uint32_t f2 = e[0] | e[1], f3 = f2 | e[2], f4 = f3 | e[3];
+		if(!(f4 & kPairFlags) && (a[4] & 63u) <= room && (e[3] & kPairCount)) {
+			cur.take_group(a[4] & 63u);
+			row = r[4];
+			cnt += (a[4] >> 6) & 15u;
+		} else {
+			int n = 0;
+			if(!(f3 & kPairFlags) && (a[3] & 63u) <= room && (e[2] & kPairCount)) n = 3;
+			else if(!(f2 & kPairFlags) && (a[2] & 63u) <= room && (e[1] & kPairCount)) n = 2;
+			else if(!(e[0] & kPairFlags) && (a[1] & 63u) <= room && (e[0] & kPairCount)) n = 1;
+			if(n) {
+				const uint32_t an = n == 3 ? a[3] : (n == 2 ? a[2] : a[1]);
+				cur.take_group(an & 63u);
+				row = n == 3 ? r[3] : (n == 2 ? r[2] : r[1]);
+				cnt += (an >> 6) & 15u;
+			} else {
+				pair_step_one<ORDER>(cur, T, lut_g, walk, e[0], row, clean);
+				++cnt;
+			}
+		}
+		cur.top_up();
+	}
+}
+
+// decode_emit over the pair table: exactly `count` symbols. A committed group is 2..8 symbols: the symbol bytes of
+// its four entries are compacted with two byte permutes and a shift, appended to the < 8 pending bytes, and every
+// completed 8 bytes leave as one aligned 64-bit store. The bytes that precede `out` in its first 8-byte word start
+// out as pending (and are skipped by that word's store); the last group is simply cut off at `count` symbols, unless
+// the exact end position is wanted (`exact_end`: the stream's last subsequence), which steps symbol by symbol.
+template <int ORDER>
+__device__ __forceinline__ bool decode_emit_pair(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
+                                                 const uint32_t* __restrict__ walk, uint32_t count, uint32_t ctx, uint8_t* out, bool exact_end) {
+	bool clean = true;
+	uint32_t row = pair_row_of<ORDER>(T, ctx);
+	uint32_t rem = count;
+	uint32_t skip = uint32_t(reinterpret_cast<uint64_t>(out) & 7);
+	out -= skip;
+	uint32_t p_lo = 0, p_hi = 0, n8 = skip * 8;   // pending bytes (n8 = 8 x their number < 64); the bytes above them are zero
+	while(rem) {
+		uint32_t e[4], a[5], r[5];
+		pair_lookups<ORDER>(cur, T, row, e, a, r);
+		const uint32_t f4 = e[0] | e[1] | e[2] | e[3];
+		uint32_t gc = (a[4] >> 6) & 15u;
+		uint32_t g_lo, g_hi;
+		if(!(f4 & kPairFlags) && !(exact_end && gc > rem)) {
+			// selector by the number of symbols in the first entry of each half: 0 -> 0x3376, 1 -> 0x3762, 2 -> 0x7632
+			const uint32_t sel_a = __funnelshift_rc(0x37623376u, 0x7632u, (e[0] & kPairCount) >> 2);
+			const uint32_t sel_b = __funnelshift_rc(0x37623376u, 0x7632u, (e[2] & kPairCount) >> 2);
+			const uint32_t wa = __byte_perm(e[0], e[1], sel_a);
+			const uint32_t wb = __byte_perm(e[2], e[3], sel_b);
+			const uint32_t ca8 = (a[2] >> 3) & 0x78u;   // 8 x symbols of the first two entries (<= 32)
+			uint32_t up;
+			asm("shl.b32 %0, %1, %2;" : "=r"(up) : "r"(wb), "r"(ca8));   // clamps: 32 -> 0
+			g_lo = wa | up;
+			g_hi = __funnelshift_lc(wb, 0u, ca8);
+			gc = gc < rem ? gc : rem;
+			cur.take_group(a[4] & 63u);
+			row = r[4];
+		} else {
+			g_lo = pair_step_one<ORDER>(cur, T, lut_g, walk, e[0], row, clean);
+			g_hi = 0;
+			gc = 1;
+		}
+		rem -= gc;
+		const uint32_t sft = n8 & 24u;
+		const uint32_t t0 = g_lo << sft, t1 = __funnelshift_l(g_lo, g_hi, sft), t2 = __funnelshift_l(g_hi, 0u, sft);
+		uint32_t r0, r1, r2, r3;
+		if(n8 & 32u) { r0 = p_lo; r1 = p_hi | t0; r2 = t1; r3 = t2; }
+		else { r0 = p_lo | t0; r1 = t1; r2 = t2; r3 = 0; }
+		const uint32_t t8 = n8 + gc * 8;
+		if(t8 >= 64u) {
+			if(skip) {   // the first word of this subsequence: its leading bytes belong to the predecessor
+				for(uint32_t i = skip; i < 8; ++i) out[i] = uint8_t((i < 4 ? r0 : r1) >> (8 * (i & 3)));
+				skip = 0;
+			} else {
+				*reinterpret_cast<uint2*>(out) = make_uint2(r0, r1);
+			}
+			out += 8;
+			p_lo = r2; p_hi = r3; n8 = t8 - 64u;
+		} else {
+			p_lo = r0; p_hi = r1; n8 = t8;
+		}
+		cur.top_up();
+	}
+	for(uint32_t i = skip; i < n8 / 8; ++i) out[i] = uint8_t((i < 4 ? p_lo : p_hi) >> (8 * (i & 3)));
+	return clean;
+}
+
 // Decode exactly `count` symbols and write them to `out`. Single bytes until the address is 8-byte aligned, then
 // eight symbols per aligned 64-bit store — every lane stores in the same iteration — then the ragged tail.
 template <int ORDER>
@@ -311,18 +522,21 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 // recorded one: from there on the recorded trajectory is its own. Per-segment counts (not running totals) make
 // the records of a partially overwritten subsequence consistent whoever wrote which segment.
 // ---------------------------------------------------------------------------------------------------------
-template <int ORDER>
+template <int ORDER, bool PAIR>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
-    const uint32_t* __restrict__ walk, uint32_t* __restrict__ state, uint32_t* __restrict__ count,
-    uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm) {
+    const uint32_t* __restrict__ walk, const uint32_t* __restrict__ pair_g, uint32_t pair_rows, uint32_t pair_ctx_rows,
+    uint32_t* __restrict__ state, uint32_t* __restrict__ count, uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm) {
 	extern __shared__ uint16_t lut_s[];
 	__shared__ uint16_t cp_state[kCp][kDecThreads];   // [checkpoint][slot]: conflict-free across a warp
 	__shared__ uint16_t cp_count[kCp][kDecThreads];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t chunk_subs = kDecThreads - warm;
 	const uint32_t seg_bits = sub_bits / kCp;
-	{
+	PairTab T = {};
+	if(PAIR) {
+		T = stage_pair_table(reinterpret_cast<uint32_t*>(lut_s), pair_g, pair_rows, pair_ctx_rows);
+	} else {
 		const uint32_t n16 = ORDER ? 65536u : 256u;
 		const uint4* src = reinterpret_cast<const uint4*>(lut_g);
 		uint4* dst = reinterpret_cast<uint4*>(lut_s);
@@ -331,6 +545,12 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 	__syncthreads();
 	uint32_t lut_sa;
 	asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(lut_sa) : "l"(lut_s));
+	// start of a speculative decode: the context ' ' (or the first live context when ' ' has no tree)
+	uint32_t guess_row = lut_sa + (ORDER ? uint32_t(' ') << 9 : 0u);
+	if(PAIR) {
+		guess_row = pair_row_of<ORDER>(T, ' ');
+		if(ORDER && guess_row == T.null_row) guess_row = T.tab;
+	}
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = buf_bytes;
@@ -347,13 +567,14 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		bool active = my_sub >= 0 && my_sub < end_sub;
 
 		const uint32_t span32 = span > 0xffff0000ull ? 0xffff0000u : uint32_t(span);   // a CTA's window is a few Mbit
-		uint32_t row = lut_sa + (ORDER ? uint32_t(' ') << 9 : 0u);
+		uint32_t row = guess_row;
 		int64_t k = my_sub;
 		if(active) {
 			const uint32_t pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
-			if(ORDER && my_sub == 0) row = lut_sa + ((start0 & 255u) << 9);   // the stream's own start (exact, or a shard's guess)
+			if(ORDER && my_sub == 0) row = PAIR ? pair_row_of<ORDER>(T, start0 & 255u) : lut_sa + ((start0 & 255u) << 9);   // the stream's own start (exact, or a shard's guess)
 			cur.seek(origin + pos, pos);
-			walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, pos, seg_bits, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
+			if(PAIR) walk_subsequence_pair<ORDER>(cur, T, lut_g, walk, pos, seg_bits, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
+			else walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, pos, seg_bits, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
 		}
 		__syncthreads();
 		// rounds: walk the successor's checkpoints until my state equals the recorded one
@@ -363,12 +584,15 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 			if(active) {
 				const uint32_t slot = uint32_t(k - first_sub);
 				const uint32_t begin = uint32_t(uint64_t(k - origin_sub) * sub_bits);
-				if(walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, begin, seg_bits, span32, row, &cp_state[0][slot], &cp_count[0][slot], true)) active = false;
+				const bool hit = PAIR ? walk_subsequence_pair<ORDER>(cur, T, lut_g, walk, begin, seg_bits, span32, row, &cp_state[0][slot], &cp_count[0][slot], true)
+				                      : walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, begin, seg_bits, span32, row, &cp_state[0][slot], &cp_count[0][slot], true);
+				if(hit) active = false;
 			}
 			if(!__syncthreads_or(active ? 1 : 0)) break;
 		}
 		if(my_sub >= 0 && my_sub < end_sub) {
-			const uint32_t e = cp_state[kCp - 1][tid];
+			uint32_t e = cp_state[kCp - 1][tid];
+			if(PAIR && ORDER) e = (e & 0xff00u) | lds_u8(T.live + (e & 255u));   // checkpoints hold the row: report the context byte
 			if(tid >= warm) {
 				uint32_t total = 0;
 #pragma unroll
@@ -484,17 +708,20 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long
 // ---------------------------------------------------------------------------------------------------------
 // D4: final decode + write
 // ---------------------------------------------------------------------------------------------------------
-template <int ORDER>
+template <int ORDER, bool PAIR>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(   // launched with kDecWriteThreads()
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
-    const uint32_t* __restrict__ walk, const uint32_t* __restrict__ state, const uint32_t* __restrict__ count,
-    const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits, uint64_t n_subs,
-    uint32_t n_chunks, uint32_t chunk_subs, uint32_t skip_subs, uint32_t stream_end, unsigned long long* result) {
+    const uint32_t* __restrict__ walk, const uint32_t* __restrict__ pair_g, uint32_t pair_rows, uint32_t pair_ctx_rows,
+    const uint32_t* __restrict__ state, const uint32_t* __restrict__ count, const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits,
+    uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t skip_subs, uint32_t stream_end, unsigned long long* result) {
 	extern __shared__ uint16_t lut_s[];
 	__shared__ uint32_t warp_tot[32];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if(result[1] != 0) return;   // capacity / convergence error decided by D3: write nothing
-	{
+	PairTab T = {};
+	if(PAIR) {
+		T = stage_pair_table(reinterpret_cast<uint32_t*>(lut_s), pair_g, pair_rows, pair_ctx_rows);
+	} else {
 		const uint32_t n16 = ORDER ? 65536u : 256u;
 		const uint4* src = reinterpret_cast<const uint4*>(lut_g);
 		uint4* dst = reinterpret_cast<uint4*>(lut_s);
@@ -543,7 +770,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(   // launche
 			const uint32_t lim = uint32_t(e - origin);
 			if(c) {
 				cur.seek(origin + pos, pos);
-				clean &= decode_emit<ORDER>(cur, lut_sa, lut_g, walk, c, ctx, out + (chunk_base[chunk] + before + incl - c));
+				uint8_t* dst = out + (chunk_base[chunk] + before + incl - c);
+				clean &= PAIR ? decode_emit_pair<ORDER>(cur, T, lut_g, walk, c, ctx, dst, stream_end && k == n_subs - 1) : decode_emit<ORDER>(cur, lut_sa, lut_g, walk, c, ctx, dst);
 				pos = cur.pos;
 			}
 			// D1 counted the symbols that start before `lim`: decoding that many must land on or after it, and on
@@ -593,7 +821,7 @@ uint64_t decode_max_subs(uint64_t max_payload_bytes) {
 
 namespace {
 
-template <int ORDER>
+template <int ORDER, bool PAIR>
 int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, uint32_t skip_subs, uint32_t stream_end,
                const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws,
                cudaStream_t st, int fix_iters, uint32_t sub_bits) {
@@ -605,11 +833,11 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	const uint64_t chunks64 = (n_subs + chunk_subs - 1) / chunk_subs;
 	if(n_subs > ws->dec_subs_cap || chunks64 > ws->dec_chunks_cap) return MH_ERR_WORKSPACE;
 	const uint32_t n_chunks = uint32_t(chunks64);
-	const size_t lut_bytes = ORDER ? 65536 * 2 : 256 * 2;
+	const size_t lut_bytes = PAIR ? size_t(pair_table_bytes(dt->pair_rows, dt->pair_ctx_rows)) : (ORDER ? 65536 * 2 : 256 * 2);
 	static bool attr_done = false;
 	if(!attr_done) {
-		MH_CUDA(cudaFuncSetAttribute(dec_sync_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lut_bytes)));
-		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lut_bytes)));
+		MH_CUDA(cudaFuncSetAttribute(dec_sync_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR ? kDecPairBytes : int(lut_bytes)));
+		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR ? kDecPairBytes : int(lut_bytes)));
 		attr_done = true;
 	}
 	const int sms = sm_count();
@@ -617,8 +845,8 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	MH_CUDA(cudaMemsetAsync(ws->dec_flags, 0, 8 * sizeof(uint32_t), st));
 	{
 		ProfScope p("dec_sync_kernel", st);
-		dec_sync_kernel<ORDER><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, ws->dec_state,
-		    ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm);
+		dec_sync_kernel<ORDER, PAIR><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, dt->d_pair,
+		    dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm);
 	}
 	count_launch(1);
 	int last_flag = -1;
@@ -648,12 +876,29 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 		const uint32_t wt = decode_write_threads();
 		const uint32_t wslices = (chunk_subs + wt - 1) / wt;
 		const uint64_t wwork = uint64_t(n_chunks) * wslices;
-		dec_write_kernel<ORDER><<<unsigned(wwork < uint64_t(sms) ? wwork : uint64_t(sms)), wt, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, ws->dec_state,
-		    ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, skip_subs, stream_end, d_result);
+		const char* wc_env = getenv("MH_DEC_WRITE_CTAS");   // experiments: resident CTAs per SM
+		const uint64_t wgrid = uint64_t(sms) * uint64_t(wc_env && atoi(wc_env) > 0 ? atoi(wc_env) : 1);
+		dec_write_kernel<ORDER, PAIR><<<unsigned(wwork < wgrid ? wwork : wgrid), wt, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk,
+		    dt->d_pair, dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, skip_subs,
+		    stream_end, d_result);
 	}
 	count_launch(3);
 	MH_CUDA(cudaGetLastError());
 	return MH_OK;
+}
+
+// The pair table is used whenever it exists (<= 63 live contexts); MH_DEC_PAIR=0 forces the u16 LUT (tests, experiments).
+int dispatch_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, uint32_t skip_subs, uint32_t stream_end,
+                    const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws,
+                    cudaStream_t st, int fix_iters, uint32_t sub_bits) {
+	const char* env = getenv("MH_DEC_PAIR");
+	const bool pair = dt->pair_rows != 0 && !(env && atoi(env) == 0);
+	if(dt->order) {
+		if(pair) return run_decode<1, true>(words, n_bits, buf_bytes, start0, skip_subs, stream_end, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
+		return run_decode<1, false>(words, n_bits, buf_bytes, start0, skip_subs, stream_end, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
+	}
+	if(pair) return run_decode<0, true>(words, n_bits, buf_bytes, start0, skip_subs, stream_end, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
+	return run_decode<0, false>(words, n_bits, buf_bytes, start0, skip_subs, stream_end, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
 }
 
 }  // namespace
@@ -673,8 +918,7 @@ int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uin
 	const uint64_t end_bit = n_bits + bit0;
 	const uint64_t buf_bytes = (end_bit + 7) >> 3;
 	const uint32_t sub_bits = decode_sub_bits(dt->order, n_bits);
-	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
-	return run_decode<0>(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
+	return dispatch_decode(words, end_bit, buf_bytes, start0, 0, 1, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
 }
 
 int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start, uint8_t prev0,
@@ -694,8 +938,7 @@ int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bi
 	const uint32_t* words = reinterpret_cast<const uint32_t*>(d_bits);
 	// a shard that does not know its start state guesses the context; its leading skip_subs subsequences are warm-up
 	const uint32_t start0 = (start_bit << 8) | (exact_start ? uint32_t(prev0) : uint32_t(' '));
-	if(dt->order) return run_decode<1>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
-	return run_decode<0>(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
+	return dispatch_decode(words, end_bit, buf_bytes, start0, skip_subs, stream_end ? 1 : 0, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
 }
 
 }  // namespace mh

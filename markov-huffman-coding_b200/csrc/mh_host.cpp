@@ -443,6 +443,79 @@ uint32_t CodingTable::flatten_dectable(uint16_t* lut, uint32_t* walk, uint16_t* 
 	return rows;
 }
 
+uint32_t CodingTable::flatten_pairlut(uint32_t* table, uint8_t* maps, uint32_t max_rows, uint32_t* ctx_rows_out) const {
+	int rank[256];
+	uint32_t live = 0;
+	int dead = -1;
+	for(int p = 0; p < 256; ++p) {
+		const bool has = order ? !trees[p].empty() : (p == 0 && !trees[0].empty());
+		rank[p] = has ? int(live++) : -1;
+		if(!has && dead < 0 && (order || p > 0)) dead = p;
+	}
+	if(max_rows > kPairMaxRows) max_rows = kPairMaxRows;
+	uint32_t rows = live + 1;   // context rows + the null row; prefix rows follow
+	if(rows > max_rows || live == 0) return 0;
+	auto next_of = [&](int c) -> uint32_t { return order ? (rank[c] >= 0 ? uint32_t(rank[c]) : live) : 0u; };
+	uint8_t* len1 = maps + 256 + kPairMaxRows;
+	for(int p = 0; p < 256; ++p) maps[p] = uint8_t(order ? (rank[p] >= 0 ? uint32_t(rank[p]) : live) : 0u);
+	for(uint32_t r = 0; r < kPairMaxRows; ++r) maps[256 + r] = uint8_t(dead < 0 ? 0 : dead);
+	for(int p = 0; p < 256; ++p) {
+		if(rank[p] < 0) continue;
+		maps[256 + rank[p]] = uint8_t(p);
+		const CodeTree& tr = trees[order ? p : 0];
+		uint32_t* row = table + size_t(rank[p]) * 256;
+		uint8_t* l1 = len1 + size_t(rank[p]) * 256;
+		int prefix_node = kNoChild;   // consecutive windows never share a depth-8 node, but keep the lookup explicit
+		uint32_t prefix_row = 0;
+		for(int w = 0; w < 256; ++w) {
+			l1[w] = 0;
+			const int n1 = tr.lut(w);
+			if(n1 == kNoChild) { row[w] = kLutNull; continue; }
+			const TreeNode& a = tr.nodes[n1];
+			if(a.internal) {
+				// depth-8 internal node: a prefix row of its own when every codeword below it ends within 8 more bits
+				row[w] = kLutDeep;
+				if(n1 == prefix_node) { row[w] = 8u | (prefix_row << 10); continue; }
+				if(rows >= max_rows) continue;
+				bool shallow = true;
+				uint32_t* ext = table + size_t(rows) * 256;
+				for(int w2 = 0; w2 < 256 && shallow; ++w2) {
+					int cur = n1, d = 0;
+					while(tr.nodes[cur].internal && d < 8) {
+						cur = ((w2 >> (7 - d)) & 1) ? tr.nodes[cur].right : tr.nodes[cur].left;
+						++d;
+					}
+					if(tr.nodes[cur].internal) shallow = false;
+					else ext[w2] = uint32_t(d) | (1u << 6) | (next_of(tr.nodes[cur].symbol) << 10) | (uint32_t(tr.nodes[cur].symbol) << 16);
+				}
+				if(!shallow) continue;
+				prefix_node = n1;
+				prefix_row = rows++;
+				row[w] = 8u | (prefix_row << 10);   // 8 bits, no symbol yet, continue in the prefix row
+				continue;
+			}
+			const uint32_t d1 = uint32_t(a.depth);
+			l1[w] = uint8_t(d1);
+			uint32_t e = d1 | (1u << 6) | (next_of(a.symbol) << 10) | (uint32_t(a.symbol) << 16);
+			// second symbol: the 8 - d1 bits left in the window must decide it completely
+			const CodeTree& tr2 = trees[order ? a.symbol : 0];
+			if(d1 < 8 && !tr2.empty()) {
+				const int n2 = tr2.lut((w << d1) & 255);
+				if(n2 != kNoChild) {
+					const TreeNode& b = tr2.nodes[n2];
+					if(!b.internal && uint32_t(b.depth) <= 8 - d1)
+						e = (d1 + uint32_t(b.depth)) | (2u << 6) | (next_of(b.symbol) << 10) | (uint32_t(a.symbol) << 16) | (uint32_t(b.symbol) << 24);
+				}
+			}
+			row[w] = e;
+		}
+	}
+	uint32_t* null_row = table + size_t(live) * 256;
+	for(int w = 0; w < 256; ++w) null_row[w] = kLutNull;
+	if(ctx_rows_out) *ctx_rows_out = live;
+	return rows;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // -g debug dump: byte-identical to print_table() + print_tree() on stdout
 // (src/huffman.cpp:52-69, src/markov_huffman.cpp:31-50, src/tree.cpp:11-53, src/utils.cpp:18-42).

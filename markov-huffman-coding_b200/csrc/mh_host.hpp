@@ -104,6 +104,24 @@ public:
 	// Returns the number of ext rows used.
 	uint32_t flatten_dectable(uint16_t* lut /* [trees.size() * 256] */, uint32_t* walk /* [trees.size() * 512] */,
 	                          uint16_t* ext /* [kExtRows * 256] */) const;
+	// Pair table for the decoder: one 256-entry u32 row per NON-EMPTY context (ranked in ascending byte order), a
+	// null row, then PREFIX rows, all indexed by the next 8 stream bits like the reference's LUT
+	// (src/huffman.cpp:110-123). An entry resolves up to TWO symbols when both codewords fit in the 8 bits:
+	//   [5:0]  bits consumed (1..8; bits 4 and 5 are the flags below, so four entries add up to <= 32 here)
+	//   [9:6]  symbols produced (0, 1 or 2; four entries add up to <= 8 here)
+	//   [15:10] next row: the last symbol as the next context (the null row if that context has no tree)
+	//   [23:16] first symbol, [31:24] second symbol (0 when there is none)
+	// A codeword longer than 8 bits is an internal node at depth 8 (src/coding.cpp:129-149). When every codeword
+	// below that node ends within 8 more bits the node gets a prefix row: its entry in the context row consumes the
+	// 8 bits, produces nothing and names the prefix row, whose entries finish the symbol — no branch in the decoder.
+	//   deep (kLutDeep): a longer codeword, or no row left; null (kLutNull): no such table entry — both are decoded
+	//   one symbol at a time through the u16 LUT / walk table.
+	// `maps` receives rank[256] (row of each byte as a context), live[kPairMaxRows] (context byte of each context
+	// row; the null row reports a context without a tree) and len1[ctx rows * 256] (length of the FIRST codeword of
+	// each context-row entry, 0 for deep / null). Returns the total number of rows (<= max_rows <= kPairMaxRows), 0 if
+	// the context rows alone do not fit; *ctx_rows_out = number of context rows (the null row's index).
+	uint32_t flatten_pairlut(uint32_t* table /* [max_rows * 256] */, uint8_t* maps /* [256 + kPairMaxRows * 257] */, uint32_t max_rows,
+	                         uint32_t* ctx_rows_out) const;
 };
 
 constexpr uint16_t kLutDeep = 0x10;
@@ -111,5 +129,6 @@ constexpr uint16_t kLutNull = 0x20;
 constexpr uint16_t kLutExt = 0x40;
 constexpr uint32_t kExtRows = 512;
 constexpr uint32_t kWalkLeaf = 0x8000;
+constexpr uint32_t kPairMaxRows = 64;   // 6-bit row field
 
 }  // namespace mh

@@ -45,6 +45,7 @@ constexpr int kDecMinSubBits = 256;
 constexpr uint32_t kDecMaxSubBitsMarkov = 8192;       // measured best of 2048..16384 on the 1 GiB Markov text
 constexpr uint32_t kDecMaxSubBitsHuffman = 2048;
 constexpr uint64_t kDecTargetSubs = 300000;           // ~2 subsequences per resident thread (148 SMs x 1024)
+constexpr int kDecPairBytes = 64 * 1024 + 256 + 64 + 64 * 256;   // pair table: <= 64 rows x 256 x u32, then rank[256], live[64], len1[<= 64 x 256]
 constexpr int kDecWarmSubs = 8;                       // overlap subsequences re-decoded by the next chunk
 
 // ---- encode look-back descriptors -----------------------------------------------------------------------
@@ -95,6 +96,10 @@ struct mh_dectable {
 	uint32_t* d_walk = nullptr;    // [ntab * 512]
 	uint16_t* h_lut = nullptr;     // pinned
 	uint32_t* h_walk = nullptr;    // pinned
+	uint32_t* d_pair = nullptr;    // [pair_rows * 256] two-symbol entries, then rank[256] + live[64] bytes (see flatten_pairlut)
+	uint32_t* h_pair = nullptr;    // pinned
+	uint32_t pair_rows = 0;        // context rows + null row + prefix rows; 0: no pair table (more than 63 live contexts)
+	uint32_t pair_ctx_rows = 0;    // context rows (= index of the null row)
 	cudaEvent_t uploaded = nullptr;
 	int order = 1;
 	int max_bits = 0;

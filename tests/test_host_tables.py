@@ -140,3 +140,73 @@ def test_no_device_fails_loudly():
     assert e.value.status in (mh.MH_ERR_NO_DEVICE, mh.MH_ERR_CUDA)
     with pytest.raises(mh.MhError):
         mh.compress(b"hello")
+
+
+def _pair_decode(pl, bits, n_bits, prev0, markov, n_symbols):
+    """Decode with the two-symbol table exactly as the kernels do on their fast path (entry by entry, prefix rows
+    included); flagged entries are not expected in these inputs."""
+    table, rank, live, len1, rows, ctx_rows = pl
+    out = bytearray()
+    row = int(rank[prev0]) if markov else 0
+    pos = 0
+    while len(out) < n_symbols:
+        w = 0
+        for k in range(8):
+            p = pos + k
+            bit = (bits[p >> 3] >> (7 - (p & 7))) & 1 if p < n_bits else 0
+            w = (w << 1) | bit
+        e = int(table[row * 256 + w])
+        assert not (e & 0x30), "flagged entry on a stream whose codewords are <= 16 bits"
+        cnt = (e >> 6) & 15
+        assert cnt in (0, 1, 2)
+        if cnt >= 1:
+            out.append((e >> 16) & 255)
+            if row < ctx_rows:
+                l1 = int(len1[row * 256 + w])
+                assert 1 <= l1 <= (e & 15) - (1 if cnt == 2 else 0)
+                if cnt == 1:
+                    assert l1 == (e & 15)
+        if cnt == 2:
+            out.append((e >> 24) & 255)
+        else:
+            assert (e >> 24) == 0
+        pos += e & 15
+        row = (e >> 10) & 63
+        assert row < rows
+    return bytes(out[:n_symbols]), pos
+
+
+@pytest.mark.parametrize("name", ["input_ipsum.txt", "input_wiki_cpp.txt", "input_b.txt"])
+@pytest.mark.parametrize("markov", [True, False], ids=["markov", "huffman"])
+def test_pair_table_decodes_like_the_oracle(name, markov):
+    """flatten_pairlut (the decoder's shared-memory table): decoding the oracle's stream entry by entry through it gives
+    back the input — pairs, single symbols and the prefix rows of 9..16-bit codewords."""
+    data = golden_input(name)
+    p = mh.CodingProvider.from_counts_array(np.ascontiguousarray(_counts(data, markov)), int(markov))
+    pl = p.pair_lut()
+    if markov and len(set(data) | {0x20}) > 63:
+        assert pl is None            # too many live contexts for the 6-bit row field
+        return
+    assert pl is not None
+    table, rank, live, len1, rows, ctx_rows = pl
+    assert ctx_rows < rows <= 64
+    stream, _ = o.compress_from_input(data, markov)
+    payload = stream[1:]
+    n_bits = len(payload) * 8 - (stream[0] & 7)      # header: 0 0 1 1 E R R R, R = padding bits (src/coding.cpp:88)
+    got, pos = _pair_decode(pl, payload, n_bits, 0x20, markov, len(data))
+    assert got == data
+    assert pos == n_bits
+    if markov:
+        for c in range(256):
+            r = int(rank[c])
+            assert r <= ctx_rows
+            if r < ctx_rows:
+                assert int(live[r]) == c
+
+
+def test_pair_table_absent_for_many_contexts():
+    data = golden_input("input_wiki_cpp.html")
+    p = mh.CodingProvider.from_counts_array(np.ascontiguousarray(_counts(data, True)), 1)
+    assert p.pair_lut() is None      # 188 live contexts: the decoder keeps the 8-bit LUT
+    q = mh.CodingProvider.from_counts_array(np.ascontiguousarray(_counts(data, False)), 0)
+    assert q.pair_lut() is not None  # one tree: always available
