@@ -34,36 +34,69 @@ namespace {
 constexpr uint32_t kDeep = 0x10u, kNull = 0x20u, kExt = 0x40u;
 
 // MSB-first bit window over the payload: (hi:lo) holds the bits [pos, loaded) left-aligned, `nextw` is the word
-// after them, fetched one refill ahead so that its latency is off the per-symbol dependency chain.
-// pos / loaded are bit offsets relative to an origin chosen by the caller.
-struct Cursor {
-	const uint32_t* words;   // payload
-	uint64_t n_bytes;        // payload bytes; reads past them return zero (pop_rest pads, src/bitbuffer.cpp:129-140)
-	const uint32_t* p;       // word that held the bit the cursor was seeked to
-	uint32_t safe;           // words from p that lie completely inside the payload (clamped)
-	uint32_t k;              // next word (relative to p) to fetch
-	uint32_t hi, lo, nextw;  // nextw is kept in memory (little-endian) order and byte-swapped only when consumed, so
-	uint32_t pos, loaded;    // that nothing waits on the load until the next refill
+// after them. pos / loaded are bit offsets relative to an origin chosen by the caller.
+//
+// The payload reaches the window through a small ring in shared memory that every thread owns privately:
+// kRingPieces aligned 16-byte chunks, filled by cp.async (global -> shared, no registers, L1 bypassed) as soon as the
+// chunk in that slot has been consumed. A chunk is therefore requested (kRingPieces - 1) x 128 stream bits before its
+// first word is needed — many iterations of the decode loop — so no warp ever waits for the one lane of 32 whose
+// next word happens to miss: with plain loads, one word ahead, almost every iteration of a warp had such a lane.
+// The pieces of the 32 lanes of a warp are interleaved (piece j of lane l at (j * 32 + l) * 16) to spread the banks.
+constexpr uint32_t kRingPieces = 4;
+constexpr uint32_t kRingBytesPerThread = kRingPieces * 16;
 
-	__device__ __forceinline__ uint32_t fetch_raw(uint32_t i) const {
-		if(i < safe) return __ldg(p + i);
-		const uint64_t o = (uint64_t(p - words) + i) << 2;   // ragged end
-		uint32_t v = 0;
-		const uint8_t* b = reinterpret_cast<const uint8_t*>(words);
-		for(int j = 0; j < 4; ++j)
-			if(o + j < n_bytes) v |= uint32_t(b[o + j]) << (8 * j);
-		return v;
+__device__ __forceinline__ void cp_async_16(uint32_t dst_shared, const void* src, uint32_t src_bytes) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_shared), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct Cursor {
+	const uint32_t* words;   // payload (4-byte aligned)
+	uint64_t n_bytes;        // payload bytes; reads past them return zero (pop_rest pads, src/bitbuffer.cpp:129-140)
+	uint32_t ring;           // shared-space address of this thread's piece 0 (set once by the kernel)
+	uint32_t cw;             // next chunk to request, counted from the 16-byte boundary at or before `words`
+	uint32_t rd;             // shared-space address of the next word to pop
+	uint32_t hi, lo, nextw;  // nextw is kept in memory (little-endian) order and byte-swapped only when consumed
+	uint32_t pos, loaded;
+
+	__device__ __forceinline__ void attach(uint32_t ring_base_shared) {
+		ring = ring_base_shared + ((threadIdx.x >> 5) * (kRingPieces * 32u) + (threadIdx.x & 31u)) * 16u;
 	}
-	__device__ __forceinline__ uint32_t fetch(uint32_t i) const { return __byte_perm(fetch_raw(i), 0, 0x0123); }
+	// chunk c -> slot c % kRingPieces; bytes outside the payload are zero-filled by the copy itself
+	__device__ __forceinline__ void request(uint32_t c) {
+		const uint64_t addr = reinterpret_cast<uint64_t>(words);
+		const uint64_t base = addr & ~uint64_t(15);
+		const int64_t left = int64_t((addr & 15) + n_bytes) - (int64_t(c) << 4);   // payload bytes from the chunk's start on
+		const uint32_t n = left >= 16 ? 16u : (left > 0 ? uint32_t(left) : 0u);
+		cp_async_16(ring + (c & (kRingPieces - 1)) * 512u, reinterpret_cast<const void*>(n ? base + (uint64_t(c) << 4) : base), n);
+		cp_async_commit();
+	}
+	__device__ __forceinline__ uint32_t pop() {
+		uint32_t w;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rd) : "memory");
+		rd += 4;
+		if((rd & 12u) == 0) {   // the chunk is used up: refill its slot with the chunk kRingPieces ahead, move on to the next slot
+			request(cw++);
+			rd += 512u - 16u;
+			if(rd >= ring + kRingPieces * 512u) rd -= kRingPieces * 512u;
+			cp_async_wait<kRingPieces - 1>();   // all but the newest requests have landed: the next slot is ready
+		}
+		return w;
+	}
 	__device__ __forceinline__ void seek(uint64_t bit, uint32_t rel) {
-		const uint64_t w = bit >> 5;
-		const uint32_t off = uint32_t(bit & 31);
-		p = words + w;
-		const uint64_t whole = n_bytes >> 2;
-		safe = whole > w ? uint32_t(whole - w > 0x7fffffffull ? 0x7fffffffull : whole - w) : 0u;
-		const uint32_t w0 = fetch(0), w1 = fetch(1);
-		nextw = fetch_raw(2);
-		k = 3;
+		const uint64_t abs_bit = bit + ((reinterpret_cast<uint64_t>(words) & 15) << 3);
+		const uint64_t w = abs_bit >> 5;
+		const uint32_t off = uint32_t(abs_bit & 31);
+		cp_async_wait<0>();   // nothing of a previous subsequence may still land in the ring
+		cw = uint32_t(w >> 2);
+		rd = ring + (cw & (kRingPieces - 1)) * 512u + (uint32_t(w) & 3u) * 4u;
+#pragma unroll
+		for(uint32_t j = 0; j < kRingPieces; ++j) request(cw++);
+		cp_async_wait<kRingPieces - 1>();
+		const uint32_t w0 = __byte_perm(pop(), 0, 0x0123), w1 = __byte_perm(pop(), 0, 0x0123);
+		nextw = pop();
 		hi = __funnelshift_l(w1, w0, off);
 		lo = w1 << off;
 		pos = rel;
@@ -86,7 +119,7 @@ struct Cursor {
 			hi |= __funnelshift_rc(w, 0u, avail);
 			lo = __funnelshift_rc(0u, w, avail);
 			loaded += 32;
-			nextw = fetch_raw(k++);
+			nextw = pop();
 		}
 	}
 };
@@ -409,67 +442,142 @@ __device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab
 	}
 }
 
-// decode_emit over the pair table: exactly `count` symbols. A committed group is 2..8 symbols: the symbol bytes of
-// its four entries are compacted with two byte permutes and a shift, appended to the < 8 pending bytes, and every
-// completed 8 bytes leave as one aligned 64-bit store. The bytes that precede `out` in its first 8-byte word start
-// out as pending (and are skipped by that word's store); the last group is simply cut off at `count` symbols, unless
-// the exact end position is wanted (`exact_end`: the stream's last subsequence), which steps symbol by symbol.
+// ---------------------------------------------------------------------------------------------------------
+// D4 output staging. A thread's symbols are consecutive in memory, but the 32 threads of a warp write 32 different
+// places: as plain stores that is 32 memory transactions per warp instruction, and those transactions — not the
+// decoding — were what D4 spent a third of its time on. So the symbols go through shared memory: every thread owns
+// a 128-byte ring that mirrors global memory (ring byte = address & 127), i.e. two 64-byte units; completed words
+// are stored into it, and every few iterations the warp writes out the units that are complete, four lanes per
+// unit with one 16-byte store each: whole sectors, eight units per warp instruction. The first and last unit of a
+// thread's range are written with byte masks.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kOutRingBytes = 128;
+constexpr uint32_t kFlushEvery = 4;   // iterations between flush rounds: a unit fills in >= 8 iterations (<= 8 symbols each)
+
+__device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool go) {
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(uint32_t(go)) : "memory");
+}
+
+// 16 bytes of a unit to global memory; only bytes [lo, hi) of the piece (0 <= lo, hi <= 16 after clamping) are written
+__device__ __forceinline__ void store_piece(uint8_t* dst, const uint4& v, int lo, int hi) {
+	if(lo <= 0 && hi >= 16) {
+		__stcg(reinterpret_cast<uint4*>(dst), v);
+		return;
+	}
+	const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+	for(int k = 0; k < 16; ++k)
+		if(k >= lo && k < hi) dst[k] = uint8_t(w[k >> 2] >> (8 * (k & 3)));
+}
+
+struct OutStage {
+	uint32_t ring;        // shared-space address of this thread's ring
+	uint32_t ring_warp;   // shared-space address of lane 0's ring
+	uint64_t unit;        // global address of the first unit not yet written out; bits [5:0]: first valid byte in it
+	uint32_t g;           // low 32 bits of the global address of the next symbol
+	uint32_t pend;        // the bytes of the word at g & ~3 produced so far (g & 3 of them)
+
+	__device__ __forceinline__ void begin(uint8_t* out) {
+		const uint64_t a = reinterpret_cast<uint64_t>(out);
+		unit = a;            // (a & ~63) | (a & 63)
+		g = uint32_t(a);
+		pend = 0;
+	}
+	// append cnt (<= 8) symbol bytes, first symbol in the low byte of lo
+	__device__ __forceinline__ void append(uint32_t lo, uint32_t hi, uint32_t cnt) {
+		const uint32_t s = (g & 3u) * 8u;
+		const uint32_t t0 = lo << s, t1 = __funnelshift_l(lo, hi, s), t2 = __funnelshift_l(hi, 0u, s);
+		const uint32_t x0 = pend | t0;
+		const uint32_t tb = (g & 3u) + cnt;   // <= 11 bytes: up to two complete words
+		sts_u32_if(ring + (g & 124u), x0, tb >= 4u);
+		sts_u32_if(ring + ((g + 4u) & 124u), t1, tb >= 8u);
+		pend = tb >= 8u ? t2 : (tb >= 4u ? t1 : x0);
+		g += cnt;
+	}
+	// Warp-wide: write out every lane's complete unit (tail == false), or what is left of its last unit (tail == true).
+	__device__ __forceinline__ void flush(bool tail) {
+		const uint32_t lane = threadIdx.x & 31u;
+		__syncwarp();
+		const uint32_t u32 = uint32_t(unit);
+		// complete: the next symbol lies beyond the unit; tail: some byte of the unit has been produced
+		const bool ready = tail ? (g != u32) : ((g >> 6) != (u32 >> 6));
+		const uint32_t mask = __ballot_sync(0xffffffffu, ready);
+		if(mask) {
+#pragma unroll
+			for(uint32_t j = 0; j < 4; ++j) {
+				if(!(mask & (0x11111111u << j))) continue;
+				const uint32_t src = (lane & ~3u) + j;
+				const uint32_t a_lo = __shfl_sync(0xffffffffu, uint32_t(unit), src);
+				const uint32_t a_hi = __shfl_sync(0xffffffffu, uint32_t(unit >> 32), src);
+				const uint32_t s_g = __shfl_sync(0xffffffffu, g, src);
+				if((mask >> src) & 1u) {
+					const uint32_t piece = (lane & 3u) * 16u;
+					uint4 v;
+					asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_warp + src * kOutRingBytes + (a_lo & 64u) + piece) : "memory");
+					uint8_t* dst = reinterpret_cast<uint8_t*>(((uint64_t(a_hi) << 32) | (a_lo & ~63u)) + piece);
+					const int first = int(a_lo & 63u) - int(piece);
+					const int last = tail ? int(s_g - (a_lo & ~63u)) - int(piece) : 16;   // tail: the unit ends at the next symbol's address
+					store_piece(dst, v, first, last);
+				}
+			}
+			if(ready) unit = (unit & ~uint64_t(63)) + 64;
+		}
+		__syncwarp();
+	}
+	// after the last symbol: the incomplete word, the complete unit (if any), the rest
+	__device__ __forceinline__ void finish() {
+		sts_u32_if(ring + (g & 124u), pend, (g & 3u) != 0);
+		flush(false);
+		flush(true);
+	}
+};
+
+// decode_emit over the pair table, warp-collective: every lane of the warp calls it (count == 0: nothing to decode)
+// and decodes exactly `count` symbols to `out`. A committed group is 2..8 symbols: the symbol bytes of its four
+// entries are compacted with two byte permutes and a shift and appended to the thread's output ring. The last group
+// is simply cut off at `count` symbols, unless the exact end position is wanted (`exact_end`: the stream's last
+// subsequence), which steps symbol by symbol.
 template <int ORDER>
 __device__ __forceinline__ bool decode_emit_pair(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
-                                                 const uint32_t* __restrict__ walk, uint32_t count, uint32_t ctx, uint8_t* out, bool exact_end) {
+                                                 const uint32_t* __restrict__ walk, uint32_t count, uint32_t ctx, uint8_t* out, bool exact_end,
+                                                 OutStage& os) {
 	bool clean = true;
 	uint32_t row = pair_row_of<ORDER>(T, ctx);
 	uint32_t rem = count;
-	uint32_t skip = uint32_t(reinterpret_cast<uint64_t>(out) & 7);
-	out -= skip;
-	uint32_t p_lo = 0, p_hi = 0, n8 = skip * 8;   // pending bytes (n8 = 8 x their number < 64); the bytes above them are zero
-	while(rem) {
-		uint32_t e[4], a[5], r[5];
-		pair_lookups<ORDER>(cur, T, row, e, a, r);
-		const uint32_t f4 = e[0] | e[1] | e[2] | e[3];
-		uint32_t gc = (a[4] >> 6) & 15u;
-		uint32_t g_lo, g_hi;
-		if(!(f4 & kPairFlags) && !(exact_end && gc > rem)) {
-			// selector by the number of symbols in the first entry of each half: 0 -> 0x3376, 1 -> 0x3762, 2 -> 0x7632
-			const uint32_t sel_a = __funnelshift_rc(0x37623376u, 0x7632u, (e[0] & kPairCount) >> 2);
-			const uint32_t sel_b = __funnelshift_rc(0x37623376u, 0x7632u, (e[2] & kPairCount) >> 2);
-			const uint32_t wa = __byte_perm(e[0], e[1], sel_a);
-			const uint32_t wb = __byte_perm(e[2], e[3], sel_b);
-			const uint32_t ca8 = (a[2] >> 3) & 0x78u;   // 8 x symbols of the first two entries (<= 32)
-			uint32_t up;
-			asm("shl.b32 %0, %1, %2;" : "=r"(up) : "r"(wb), "r"(ca8));   // clamps: 32 -> 0
-			g_lo = wa | up;
-			g_hi = __funnelshift_lc(wb, 0u, ca8);
-			gc = gc < rem ? gc : rem;
-			cur.take_group(a[4] & 63u);
-			row = r[4];
-		} else {
-			g_lo = pair_step_one<ORDER>(cur, T, lut_g, walk, e[0], row, clean);
-			g_hi = 0;
-			gc = 1;
-		}
-		rem -= gc;
-		const uint32_t sft = n8 & 24u;
-		const uint32_t t0 = g_lo << sft, t1 = __funnelshift_l(g_lo, g_hi, sft), t2 = __funnelshift_l(g_hi, 0u, sft);
-		uint32_t r0, r1, r2, r3;
-		if(n8 & 32u) { r0 = p_lo; r1 = p_hi | t0; r2 = t1; r3 = t2; }
-		else { r0 = p_lo | t0; r1 = t1; r2 = t2; r3 = 0; }
-		const uint32_t t8 = n8 + gc * 8;
-		if(t8 >= 64u) {
-			if(skip) {   // the first word of this subsequence: its leading bytes belong to the predecessor
-				for(uint32_t i = skip; i < 8; ++i) out[i] = uint8_t((i < 4 ? r0 : r1) >> (8 * (i & 3)));
-				skip = 0;
+	os.begin(out);
+	for(uint32_t it = 0; __any_sync(0xffffffffu, rem != 0); ++it) {
+		if(rem) {
+			uint32_t e[4], a[5], r[5];
+			pair_lookups<ORDER>(cur, T, row, e, a, r);
+			const uint32_t f4 = e[0] | e[1] | e[2] | e[3];
+			uint32_t gc = (a[4] >> 6) & 15u;
+			uint32_t g_lo, g_hi;
+			if(!(f4 & kPairFlags) && !(exact_end && gc > rem)) {
+				// selector by the number of symbols in the first entry of each half: 0 -> 0x3376, 1 -> 0x3762, 2 -> 0x7632
+				const uint32_t sel_a = __funnelshift_rc(0x37623376u, 0x7632u, (e[0] & kPairCount) >> 2);
+				const uint32_t sel_b = __funnelshift_rc(0x37623376u, 0x7632u, (e[2] & kPairCount) >> 2);
+				const uint32_t wa = __byte_perm(e[0], e[1], sel_a);
+				const uint32_t wb = __byte_perm(e[2], e[3], sel_b);
+				const uint32_t ca8 = (a[2] >> 3) & 0x78u;   // 8 x symbols of the first two entries (<= 32)
+				uint32_t up;
+				asm("shl.b32 %0, %1, %2;" : "=r"(up) : "r"(wb), "r"(ca8));   // clamps: 32 -> 0
+				g_lo = wa | up;
+				g_hi = __funnelshift_lc(wb, 0u, ca8);
+				gc = gc < rem ? gc : rem;
+				cur.take_group(a[4] & 63u);
+				row = r[4];
 			} else {
-				*reinterpret_cast<uint2*>(out) = make_uint2(r0, r1);
+				g_lo = pair_step_one<ORDER>(cur, T, lut_g, walk, e[0], row, clean);
+				g_hi = 0;
+				gc = 1;
 			}
-			out += 8;
-			p_lo = r2; p_hi = r3; n8 = t8 - 64u;
-		} else {
-			p_lo = r0; p_hi = r1; n8 = t8;
+			rem -= gc;
+			os.append(g_lo, g_hi, gc);
+			cur.top_up();
 		}
-		cur.top_up();
+		if((it & (kFlushEvery - 1)) == kFlushEvery - 1) os.flush(false);
 	}
-	for(uint32_t i = skip; i < n8 / 8; ++i) out[i] = uint8_t((i < 4 ? p_lo : p_hi) >> (8 * (i & 3)));
+	os.finish();
 	return clean;
 }
 
@@ -501,7 +609,7 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 			}
 			cur.top_up();
 		}
-		*reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
+		__stcg(reinterpret_cast<uint2*>(out), make_uint2(w[0], w[1]));   // L2 only: the output must not push payload lines out of L1
 		out += 8;
 	}
 	row_off = row - lut_s;
@@ -526,8 +634,8 @@ template <int ORDER, bool PAIR>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ pair_g, uint32_t pair_rows, uint32_t pair_ctx_rows,
-    uint32_t* __restrict__ state, uint32_t* __restrict__ count, uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm) {
-	extern __shared__ uint16_t lut_s[];
+    uint32_t* __restrict__ state, uint32_t* __restrict__ count, uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm, uint32_t lut_smem_bytes) {
+	extern __shared__ __align__(16) uint16_t lut_s[];   // table, then the payload rings (kRingBytesPerThread each)
 	__shared__ uint16_t cp_state[kCp][kDecThreads];   // [checkpoint][slot]: conflict-free across a warp
 	__shared__ uint16_t cp_count[kCp][kDecThreads];
 	const uint32_t tid = threadIdx.x;
@@ -554,6 +662,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = buf_bytes;
+	cur.attach(lut_sa + lut_smem_bytes);
 
 	for(uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
 		// thread t handles subsequence first_sub + t where first_sub may be negative for chunk 0
@@ -614,6 +723,7 @@ template <int ORDER>
 __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, const uint16_t* __restrict__ lut_g,
                                 const uint32_t* __restrict__ walk, uint32_t* state, uint32_t* count, uint32_t* seam,
                                 uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t phase, uint32_t* flag) {
+	__shared__ __align__(16) uint8_t seam_ring[128 * kRingBytesPerThread];   // launched with 128 threads
 	const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x + 1;
 	if(chunk >= n_chunks) return;
 	const uint64_t first = uint64_t(chunk) * chunk_subs;
@@ -625,6 +735,7 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = buf_bytes;
+	cur.attach(uint32_t(__cvta_generic_to_shared(seam_ring)));
 	uint32_t pos = recorded >> 8, ctx = recorded & 255u;
 	cur.seek(origin + pos, pos);
 	bool merged = false;
@@ -709,12 +820,13 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long
 // D4: final decode + write
 // ---------------------------------------------------------------------------------------------------------
 template <int ORDER, bool PAIR>
-__global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(   // launched with kDecWriteThreads()
+__global__ void __launch_bounds__(PAIR ? kDecWriteMaxThreads : kDecThreads, 1) dec_write_kernel(   // launched with decode_write_threads()
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ pair_g, uint32_t pair_rows, uint32_t pair_ctx_rows,
     const uint32_t* __restrict__ state, const uint32_t* __restrict__ count, const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits,
-    uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t skip_subs, uint32_t stream_end, unsigned long long* result) {
-	extern __shared__ uint16_t lut_s[];
+    uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t skip_subs, uint32_t stream_end, unsigned long long* result,
+    uint32_t lut_smem_bytes) {
+	extern __shared__ __align__(16) uint16_t lut_s[];   // table, then the payload rings
 	__shared__ uint32_t warp_tot[32];
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if(result[1] != 0) return;   // capacity / convergence error decided by D3: write nothing
@@ -733,6 +845,10 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(   // launche
 	Cursor cur;
 	cur.words = words;
 	cur.n_bytes = buf_bytes;
+	cur.attach(lut_sa + lut_smem_bytes);
+	OutStage os;
+	os.ring_warp = lut_sa + lut_smem_bytes + blockDim.x * kRingBytesPerThread + warp * 32u * kOutRingBytes;
+	os.ring = os.ring_warp + lane * kOutRingBytes;
 	bool clean = true;
 	// A chunk (the unit D3 scanned) is written in slices of blockDim.x subsequences; fewer resident threads than D1
 	// keep every thread's current payload line in L1.
@@ -760,20 +876,26 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(   // launche
 		uint32_t before = carry;
 		for(uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
 		__syncthreads();
+		// every lane goes through the emitter (the pair path writes out warp-wide); lanes without symbols pass count 0
+		const uint32_t start = !mine ? 0u : (k == 0 ? (start0 & 255u) : state[k - 1]);
+		const uint64_t origin = k * sub_bits + (start0 >> 8);
+		uint64_t e = origin + sub_bits;
+		if(e > n_bits) e = n_bits;
+		uint32_t pos = start >> 8;
+		const uint32_t ctx = start & 255u;
+		const uint32_t lim = uint32_t(e - origin);
+		uint8_t* dst = out;
+		if(c) {
+			cur.seek(origin + pos, pos);
+			dst = out + (chunk_base[chunk] + before + incl - c);
+		}
+		if(PAIR) {
+			clean &= decode_emit_pair<ORDER>(cur, T, lut_g, walk, c, ctx, dst, stream_end && k == n_subs - 1, os);
+		} else if(c) {
+			clean &= decode_emit<ORDER>(cur, lut_sa, lut_g, walk, c, ctx, dst);
+		}
 		if(mine) {
-			const uint32_t start = k == 0 ? (start0 & 255u) : state[k - 1];
-			const uint64_t origin = k * sub_bits + (start0 >> 8);
-			uint64_t e = origin + sub_bits;
-			if(e > n_bits) e = n_bits;
-			uint32_t pos = start >> 8;
-			const uint32_t ctx = start & 255u;
-			const uint32_t lim = uint32_t(e - origin);
-			if(c) {
-				cur.seek(origin + pos, pos);
-				uint8_t* dst = out + (chunk_base[chunk] + before + incl - c);
-				clean &= PAIR ? decode_emit_pair<ORDER>(cur, T, lut_g, walk, c, ctx, dst, stream_end && k == n_subs - 1) : decode_emit<ORDER>(cur, lut_sa, lut_g, walk, c, ctx, dst);
-				pos = cur.pos;
-			}
+			if(c) pos = cur.pos;
 			// D1 counted the symbols that start before `lim`: decoding that many must land on or after it, and on
 			// the very end of the payload for the last subsequence (else the last codeword runs past the stream)
 			if(pos < lim) clean = false;
@@ -788,7 +910,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_write_kernel(   // launche
 static uint32_t decode_write_threads() {
 	const char* env = getenv("MH_DEC_WRITE_THREADS");   // experiments
 	const int v = env ? atoi(env) : 512;
-	return (v >= 64 && v <= kDecThreads && v % 32 == 0) ? uint32_t(v) : 512u;
+	return (v >= 64 && v <= kDecWriteMaxThreads && v % 32 == 0) ? uint32_t(v) : 512u;
 }
 
 uint32_t decode_sub_bits(int order, uint64_t n_bits) {
@@ -836,8 +958,10 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	const size_t lut_bytes = PAIR ? size_t(pair_table_bytes(dt->pair_rows, dt->pair_ctx_rows)) : (ORDER ? 65536 * 2 : 256 * 2);
 	static bool attr_done = false;
 	if(!attr_done) {
-		MH_CUDA(cudaFuncSetAttribute(dec_sync_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR ? kDecPairBytes : int(lut_bytes)));
-		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR ? kDecPairBytes : int(lut_bytes)));
+		const int ring_bytes = kDecThreads * int(kRingBytesPerThread);
+		MH_CUDA(cudaFuncSetAttribute(dec_sync_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (PAIR ? kDecPairBytes : int(lut_bytes)) + ring_bytes));
+		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		                             (PAIR ? kDecPairBytes + kDecWriteMaxThreads * int(kRingBytesPerThread + kOutRingBytes) : int(lut_bytes) + ring_bytes)));
 		attr_done = true;
 	}
 	const int sms = sm_count();
@@ -845,8 +969,8 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	MH_CUDA(cudaMemsetAsync(ws->dec_flags, 0, 8 * sizeof(uint32_t), st));
 	{
 		ProfScope p("dec_sync_kernel", st);
-		dec_sync_kernel<ORDER, PAIR><<<grid, kDecThreads, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, dt->d_pair,
-		    dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm);
+		dec_sync_kernel<ORDER, PAIR><<<grid, kDecThreads, lut_bytes + size_t(kDecThreads) * kRingBytesPerThread, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, dt->d_pair,
+		    dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm, uint32_t(lut_bytes));
 	}
 	count_launch(1);
 	int last_flag = -1;
@@ -878,9 +1002,9 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 		const uint64_t wwork = uint64_t(n_chunks) * wslices;
 		const char* wc_env = getenv("MH_DEC_WRITE_CTAS");   // experiments: resident CTAs per SM
 		const uint64_t wgrid = uint64_t(sms) * uint64_t(wc_env && atoi(wc_env) > 0 ? atoi(wc_env) : 1);
-		dec_write_kernel<ORDER, PAIR><<<unsigned(wwork < wgrid ? wwork : wgrid), wt, lut_bytes, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk,
+		dec_write_kernel<ORDER, PAIR><<<unsigned(wwork < wgrid ? wwork : wgrid), wt, lut_bytes + size_t(wt) * (kRingBytesPerThread + (PAIR ? kOutRingBytes : 0u)), st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk,
 		    dt->d_pair, dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, skip_subs,
-		    stream_end, d_result);
+		    stream_end, d_result, uint32_t(lut_bytes));
 	}
 	count_launch(3);
 	MH_CUDA(cudaGetLastError());

@@ -459,39 +459,22 @@ uint32_t CodingTable::flatten_pairlut(uint32_t* table, uint8_t* maps, uint32_t m
 	uint8_t* len1 = maps + 256 + kPairMaxRows;
 	for(int p = 0; p < 256; ++p) maps[p] = uint8_t(order ? (rank[p] >= 0 ? uint32_t(rank[p]) : live) : 0u);
 	for(uint32_t r = 0; r < kPairMaxRows; ++r) maps[256 + r] = uint8_t(dead < 0 ? 0 : dead);
+	struct DeepNode { uint32_t weight; int ctx, window, node; };
+	std::vector<DeepNode> deep;
 	for(int p = 0; p < 256; ++p) {
 		if(rank[p] < 0) continue;
 		maps[256 + rank[p]] = uint8_t(p);
 		const CodeTree& tr = trees[order ? p : 0];
 		uint32_t* row = table + size_t(rank[p]) * 256;
 		uint8_t* l1 = len1 + size_t(rank[p]) * 256;
-		int prefix_node = kNoChild;   // consecutive windows never share a depth-8 node, but keep the lookup explicit
-		uint32_t prefix_row = 0;
 		for(int w = 0; w < 256; ++w) {
 			l1[w] = 0;
 			const int n1 = tr.lut(w);
 			if(n1 == kNoChild) { row[w] = kLutNull; continue; }
 			const TreeNode& a = tr.nodes[n1];
-			if(a.internal) {
-				// depth-8 internal node: a prefix row of its own when every codeword below it ends within 8 more bits
+			if(a.internal) {   // depth-8 internal node: a prefix row if one is left (below), else the slow path
 				row[w] = kLutDeep;
-				if(n1 == prefix_node) { row[w] = 8u | (prefix_row << 10); continue; }
-				if(rows >= max_rows) continue;
-				bool shallow = true;
-				uint32_t* ext = table + size_t(rows) * 256;
-				for(int w2 = 0; w2 < 256 && shallow; ++w2) {
-					int cur = n1, d = 0;
-					while(tr.nodes[cur].internal && d < 8) {
-						cur = ((w2 >> (7 - d)) & 1) ? tr.nodes[cur].right : tr.nodes[cur].left;
-						++d;
-					}
-					if(tr.nodes[cur].internal) shallow = false;
-					else ext[w2] = uint32_t(d) | (1u << 6) | (next_of(tr.nodes[cur].symbol) << 10) | (uint32_t(tr.nodes[cur].symbol) << 16);
-				}
-				if(!shallow) continue;
-				prefix_node = n1;
-				prefix_row = rows++;
-				row[w] = 8u | (prefix_row << 10);   // 8 bits, no symbol yet, continue in the prefix row
+				deep.push_back({uint32_t(a.weight), p, w, n1});
 				continue;
 			}
 			const uint32_t d1 = uint32_t(a.depth);
@@ -509,6 +492,28 @@ uint32_t CodingTable::flatten_pairlut(uint32_t* table, uint8_t* maps, uint32_t m
 			}
 			row[w] = e;
 		}
+	}
+	// Prefix rows go to the heaviest depth-8 nodes first (the node weight is the number of symbols coded below it;
+	// a table loaded from a file has no weights and takes them in table order). A node qualifies when every codeword
+	// below it ends within 8 more bits.
+	std::stable_sort(deep.begin(), deep.end(), [](const DeepNode& x, const DeepNode& y) { return x.weight > y.weight; });
+	for(const DeepNode& dn : deep) {
+		if(rows >= max_rows) break;
+		const CodeTree& tr = trees[order ? dn.ctx : 0];
+		uint32_t* ext = table + size_t(rows) * 256;
+		bool shallow = true;
+		for(int w2 = 0; w2 < 256 && shallow; ++w2) {
+			int cur = dn.node, d = 0;
+			while(tr.nodes[cur].internal && d < 8) {
+				cur = ((w2 >> (7 - d)) & 1) ? tr.nodes[cur].right : tr.nodes[cur].left;
+				++d;
+			}
+			if(tr.nodes[cur].internal) shallow = false;
+			else ext[w2] = uint32_t(d) | (1u << 6) | (next_of(tr.nodes[cur].symbol) << 10) | (uint32_t(tr.nodes[cur].symbol) << 16);
+		}
+		if(!shallow) continue;
+		table[size_t(rank[dn.ctx]) * 256 + dn.window] = 8u | (rows << 10);   // 8 bits, no symbol yet, continue in the prefix row
+		++rows;
 	}
 	uint32_t* null_row = table + size_t(live) * 256;
 	for(int w = 0; w < 256; ++w) null_row[w] = kLutNull;
