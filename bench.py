@@ -270,6 +270,7 @@ def main():
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     state = {}
+    host_us = {"trees": 0.0, "codebook": 0.0, "dectable": 0.0}   # host work on the step's critical path (timed steps)
 
     def step(timed):
         """compress then extract of the resident shard; returns (ms_encode_phase, ms_decode_phase)."""
@@ -292,10 +293,13 @@ def main():
             sharding.fix_seam_pairs(all_counts, msgs[:, 65536], msgs[:, 65537])
             if rank > 0:
                 prev0 = int(msgs[rank - 1, 65537])
+        th0 = time.perf_counter()
         provider = mh.CodingProvider.from_counts_array(sharding.global_counts(all_counts), 1)     # identical on every rank
+        th1 = time.perf_counter()
         if book is None:
             book, dectab = mh.Codebook(provider), mh.DecodeTable(provider)
         book.update(provider, stream)
+        th2 = time.perf_counter()
         expect_bits = None
         if world > 1:   # every rank derives every shard's global bit offset from the gathered histograms
             base, shard_bits = sharding.shard_bit_bases(all_counts, provider.code_lengths())
@@ -303,11 +307,15 @@ def main():
         mh.gpu_encode(d_in.data_ptr(), n, prev0, book, bit_base, d_payload.data_ptr(), payload_cap, d_res_enc.data_ptr(), ws, stream)
         h_res[:4].copy_(d_res_enc, non_blocking=True)
         ev[1].record()
+        th3 = time.perf_counter()
+        dectab.update(provider, stream)     # the decoder's tables are flattened on the host while the encoder runs
+        th4 = time.perf_counter()
         torch.cuda.current_stream().synchronize()
         bits = int(h_res[0])
         assert int(h_res[2]) == 0, "encode: capacity"
         assert expect_bits is None or bits == expect_bits, "shard payload size differs from sum(count x length)"
-        dectab.update(provider, stream)
+        if timed:
+            host_us["trees"] += (th1 - th0) * 1e6; host_us["codebook"] += (th2 - th1) * 1e6; host_us["dectable"] += (th4 - th3) * 1e6
         if world > 1:
             # one stream, decoded by bit ranges: halo exchange, speculative start + warm-up, seam handshake over NCCL
             got = shard_decoder.decode(d_local, base, shard_bits, dectab, d_out, n, d_res_dec, ws, stream)
@@ -429,7 +437,7 @@ def main():
                    "sharding": ("encode: byte-range shards, NCCL all-gather of histograms, exclusive scan of per-GPU bit totals; decode: bit-range shards, "
                                 "NCCL halo exchange, speculative start with warm-up, seam handshake (%d extra rounds)" % state.get("seam_rounds", 0)) if world > 1 else "single GPU"},
         "encode_gbs": n * world * args.steps / (t_enc * 1e-3) / 1e9, "decode_gbs": n * world * args.steps / (t_dec * 1e-3) / 1e9,
-        "gpu_launches": int(launches), "kernels_ms_per_launch": kern, "phases": phase,
+        "gpu_launches": int(launches), "kernels_ms_per_launch": kern, "phases": phase, "host_us_per_step": {k: round(v / args.steps, 1) for k, v in host_us.items()},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(dominant, n),
                      "peak_source": peak_src, "algorithmic_bytes": algo.get(dominant, 0), "ms_per_launch": dom_ms},
         "clocks": clock_info,

@@ -177,7 +177,14 @@ __device__ __forceinline__ uint32_t predecessor_tail(uint32_t tile, uint32_t nea
 	return t_tail;
 }
 
-// Block-wide exclusive scan (one value per thread). One barrier; `total` is the block sum.
+// Named barriers. 0: the whole CTA (__syncthreads); 1: the worker warps; 2, 3: "tile index and bit count of iteration i
+// are in shared memory" (workers arrive, the scanner warp waits); 4, 5: "the prefix of the tile packed in iteration i is
+// in shared memory" (the scanner arrives, the workers wait). Arrive / sync pairs order the shared-memory hand-over.
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, %0;" ::"n"(kEncThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kEncCtaThreads) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kEncCtaThreads) : "memory"); }
+
+// Block-wide exclusive scan over the worker threads (one value per thread). One barrier; `total` is the block sum.
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
 	constexpr int NW = kEncThreads / 32;
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -188,11 +195,11 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 		if(lane >= uint32_t(d)) incl += t;
 	}
 	if(lane == 31) warp_sums[warp] = incl;
-	__syncthreads();
+	bar_workers();
 	const uint32_t ws = lane < NW ? warp_sums[lane] : 0u;   // every warp scans the warp totals itself
 	uint32_t wincl = ws;
 #pragma unroll
-	for(int d = 1; d < NW; d <<= 1) {
+	for(int d = 1; d < 16; d <<= 1) {
 		const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, d);
 		if(lane >= uint32_t(d)) wincl += t;
 	}
@@ -251,30 +258,55 @@ struct Packer32 {
 };
 
 template <int SPT, int FMT, bool ALIGNED, int ORDER = 1>
-__global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
+__global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A) {
 	constexpr int NWORDS = SPT / 4;
 	extern __shared__ uint32_t smem[];
 	uint32_t* table = smem;   // FMT_BOX_SMEM: [(R + 1)^2] or [256]
 	__shared__ uint32_t warp_sums[kEncThreads / 32];
 	__shared__ uint32_t s_tile[2];
-	__shared__ unsigned long long s_prefix_bits;
-	__shared__ uint32_t s_prefix_tail;
+	__shared__ volatile uint32_t s_pub_tile[2], s_pub_bits[2];    // workers -> scanner: tile and bit count of iteration i
+	__shared__ volatile unsigned long long s_prefix_bits[2];      // scanner -> workers: bits before that tile ...
+	__shared__ volatile uint32_t s_prefix_tail[2];                // ... and the last 31 of them
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint32_t table_entries = 0;
 	if(FMT == FMT_BOX_SMEM) {
 		table_entries = A.order ? (A.box_r + 1) * (A.box_r + 1) : 256u;
-		for(uint32_t i = tid; i < table_entries; i += kEncThreads) table[i] = __ldg(A.box + i);
+		for(uint32_t i = tid; i < table_entries; i += kEncCtaThreads) table[i] = __ldg(A.box + i);
 	}
 	if(FMT == FMT_CTX) {
 		table_entries = A.ctx_rows * 256u;
-		for(uint32_t i = tid; i < table_entries / 4; i += kEncThreads) reinterpret_cast<uint4*>(table)[i] = __ldg(reinterpret_cast<const uint4*>(A.ctx) + i);
+		for(uint32_t i = tid; i < table_entries / 4; i += kEncCtaThreads) reinterpret_cast<uint4*>(table)[i] = __ldg(reinterpret_cast<const uint4*>(A.ctx) + i);
 	}
 	uint32_t* stage = smem + ((table_entries + 3) & ~3u);   // [stage_words + 4]
 	const uint32_t table_sa = uint32_t(__cvta_generic_to_shared(table));
 	const uint32_t stage_sa = uint32_t(__cvta_generic_to_shared(stage));
-	for(uint32_t i = tid; i < A.stage_words + 4; i += kEncThreads) stage[i] = 0;
+	for(uint32_t i = tid; i < A.stage_words + 4; i += kEncCtaThreads) stage[i] = 0;
 	if(tid == 0) s_tile[0] = atomicAdd(A.ticket, 1u);
+	__syncthreads();
+
+	// ---- the scanner warp: resolves every tile's global bit offset as soon as its bit count is known, one iteration
+	// before the workers need it, so that nobody ever waits for the chained scan ----
+	if(tid >= kEncThreads) {
+		for(uint32_t it = 0;; ++it) {
+			bar_wait(2 + (it & 1));
+			const uint32_t tile = s_pub_tile[it & 1];
+			if(tile >= A.n_tiles) break;
+			const uint32_t bits = s_pub_bits[it & 1];
+			unsigned long long excl_bits;
+			uint32_t nearest_bits;
+			look_back(tile, bits, A, excl_bits, nearest_bits);
+			if(lane == 0) {
+				s_prefix_bits[it & 1] = excl_bits;
+				s_prefix_tail[it & 1] = predecessor_tail(tile, nearest_bits, A);
+				if(tile == A.n_tiles - 1) A.result[0] = excl_bits + bits;
+				__threadfence_block();
+			}
+			__syncwarp();
+			bar_arrive(4 + (it & 1));
+		}
+		return;
+	}
 	const uint32_t R = A.box_r, lo = A.box_lo, pitch = R + 1;
 	uint32_t dropped = 0;
 
@@ -286,10 +318,16 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 	bool pending = false;          // a packed tile is waiting in the staging area
 	uint32_t p_tile = 0, p_bits = 0;
 	for(uint32_t it = 0;; ++it) {
-		__syncthreads();
+		bar_workers();
 		const uint32_t tile = s_tile[it & 1];
 		const bool valid = tile < A.n_tiles;
-		if(!valid && !pending) break;
+		if(!valid && !pending) {
+			if(it == 0) {   // this CTA never got a tile (another one took two tickets first): release the scanner
+				if(tid == 0) s_pub_tile[0] = 0xffffffffu;
+				bar_arrive(2);
+			}
+			break;
+		}
 		if(valid && tid == 0) s_tile[(it + 1) & 1] = atomicAdd(A.ticket, 1u);   // next ticket, off the critical path
 		else if(!valid && tid == 0) s_tile[(it + 1) & 1] = tile;
 		const uint64_t my = uint64_t(tile) * (kEncThreads * SPT) + uint64_t(tid) * SPT;
@@ -430,7 +468,12 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			}
 			// block exclusive scan; the tile's bit count is published right away
 			pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
-			if(tid == 0) st_relaxed(A.agg + tile, kAgg | tile_bits);
+			if(tid == 0) {
+				st_relaxed(A.agg + tile, kAgg | tile_bits);
+				s_pub_tile[it & 1] = tile;
+				s_pub_bits[it & 1] = tile_bits;
+			}
+			bar_arrive(2 + (it & 1));   // the scanner takes it from here
 			// the next ticket is visible since the scan's barrier: pull that tile's input into L2 while this one packs
 			const uint32_t next_tile = s_tile[(it + 1) & 1];
 			if((tid & 3) == 0 && next_tile < A.n_tiles) {
@@ -439,21 +482,18 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			}
 		}
 
-		// ================= phase B: resolve and write out the pending tile =================
+		if(!valid) {   // no tile left: tell the scanner, then write out the pending one
+			if(tid == 0) s_pub_tile[it & 1] = 0xffffffffu;
+			bar_arrive(2 + (it & 1));
+		}
+
+		// ================= phase B: write out the pending tile (packed in iteration it - 1) =================
 		if(pending) {
-			if(warp == 0) {
-				unsigned long long excl_bits;
-				uint32_t nearest_bits;
-				look_back(p_tile, p_bits, A, excl_bits, nearest_bits);
-				if(lane == 0) {
-					s_prefix_bits = excl_bits;
-					s_prefix_tail = predecessor_tail(p_tile, nearest_bits, A);
-					if(p_tile == A.n_tiles - 1) A.result[0] = excl_bits + p_bits;
-				}
-			}
-			__syncthreads();
+			bar_wait(4 + ((it - 1) & 1));   // normally passed at once: the scanner had a whole iteration
+			const unsigned long long prefix_bits = s_prefix_bits[(it - 1) & 1];
+			const uint32_t prefix_tail = s_prefix_tail[(it - 1) & 1];
 			// funnel-shift copy-out
-			const unsigned long long g0 = A.bit0 + s_prefix_bits;     // global bit index of the tile's first bit
+			const unsigned long long g0 = A.bit0 + prefix_bits;     // global bit index of the tile's first bit
 			const unsigned long long g1 = g0 + p_bits;
 			const uint32_t s = uint32_t(g0 & 31);
 			const unsigned long long w0 = g0 >> 5;
@@ -463,17 +503,17 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 			if(w1 > A.out_capacity_words) {
 				if(tid == 0) A.result[2] = 1;                         // capacity error; this tile writes nothing
 			} else {
-				const uint32_t carry = s ? (s_prefix_tail & ((1u << s) - 1u)) : 0u;   // predecessor bits that open word w0
+				const uint32_t carry = s ? (prefix_tail & ((1u << s) - 1u)) : 0u;   // predecessor bits that open word w0
 				for(uint32_t j = tid; j < nw; j += kEncThreads) {
 					const uint32_t hi = j ? stage[j - 1] : carry;
 					const uint32_t v = __funnelshift_r(stage[j], hi, s);
 					A.out_words[w0 + j] = __byte_perm(v, 0, 0x0123);
 				}
 			}
-			__syncthreads();
+			bar_workers();
 			const uint32_t used = (p_bits + 31) / 32 + 1;
 			for(uint32_t j = tid; j < used; j += kEncThreads) stage[j] = 0;
-			__syncthreads();   // the staging area is clean before the next tile is packed into it
+			bar_workers();   // the staging area is clean before the next tile is packed into it
 			pending = false;
 		}
 
@@ -531,7 +571,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_kernel(const EncArgs A) {
 				for(int i = 0; i < SPT; ++i) pk.put(e64[i] & 0x00ffffffffffffffull, uint32_t(e64[i] >> 56));
 			}
 			if constexpr(FMT != FMT_CTX) pk.finish();
-			__syncthreads();   // staged bits visible
+			bar_workers();   // staged bits visible
 			if(tid == 0) {     // the tail goes out now: successors need it only when they write their first word
 				const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
 				st_relaxed32(A.tail + tile, kTailValid | stage_bits(stage, tile_bits - tcount, tcount));
@@ -550,13 +590,13 @@ int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStr
 	auto kern = aligned ? encode_kernel<SPT, FMT, true, ORDER> : encode_kernel<SPT, FMT, false, ORDER>;
 	MH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
 	int per_sm = 0;
-	MH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEncThreads, smem_bytes));
+	MH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEncCtaThreads, smem_bytes));
 	if(per_sm < 1) per_sm = 1;
 	uint64_t grid = uint64_t(sm_count()) * per_sm;
 	if(grid > args.n_tiles) grid = args.n_tiles;
 	{
 		ProfScope p("encode_kernel", st);
-		kern<<<unsigned(grid), kEncThreads, smem_bytes, st>>>(args);
+		kern<<<unsigned(grid), kEncCtaThreads, smem_bytes, st>>>(args);
 	}
 	count_launch(1);
 	MH_CUDA(cudaGetLastError());

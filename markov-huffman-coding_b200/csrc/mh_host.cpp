@@ -39,6 +39,7 @@ class WeightHeap {
 	std::vector<Slot> a_;
 public:
 	size_t size() const { return a_.size(); }
+	void reserve(size_t n) { a_.reserve(n); }
 	void push(int32_t weight, int node) {
 		a_.push_back({weight, node});
 		size_t i = a_.size() - 1;
@@ -76,8 +77,13 @@ inline int32_t wrap_add(int32_t x, int32_t y) { return int32_t(uint32_t(x) + uin
 void CodeTree::build_from_counts(const int32_t* counts) {
 	nodes.clear();
 	root = kNoChild;
-	nodes.reserve(511);
+	derived.reset();
+	int live = 0;
+	for(int s = 0; s < 256; ++s) live += counts[s] != 0;
+	if(live == 0) return;   // empty table (most contexts of a text): nothing to allocate
+	nodes.reserve(size_t(2 * live + 2));
 	WeightHeap heap;
+	heap.reserve(size_t(live));
 	for(int s = 0; s < 256; ++s) {          // ascending symbol order fixes the initial heap layout (src/huffman.cpp:134-138)
 		if(counts[s] == 0) continue;        // the reference tests `if(counts[i])`: a wrapped-negative count is still a leaf
 		TreeNode leaf;

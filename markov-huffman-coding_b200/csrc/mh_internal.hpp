@@ -33,7 +33,8 @@ int sm_count();          // multiprocessors of the current device (cached)
 int max_smem_optin();    // bytes of opt-in dynamic shared memory per block (cached)
 
 // ---- tunables (env overrides exist for experiments; defaults are what DESIGN.md documents) ------------
-constexpr int kEncThreads = 512;
+constexpr int kEncThreads = 480;                      // worker threads per CTA: a tile is kEncThreads x SPT input bytes
+constexpr int kEncCtaThreads = kEncThreads + 32;      // + the scanner warp (decoupled look-back, one iteration ahead of the workers)
 constexpr int kEncStageMaxWords = 14336;              // at most 56 KiB of staged output bits per tile
 constexpr int kEncBoxSmemLimit = 72 * 1024;           // largest u32 box table staged in shared memory (R <= 135)
 constexpr int kEncBoxMaxBits = 27;                    // u32 entry: 5-bit length | 27-bit right-aligned code
