@@ -375,6 +375,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 	ws->dec_chunks_cap = ws->dec_subs_cap / (kDecThreads - kDecWarmSubs) + 2;
 	WS_CUDA(cudaMalloc(&ws->dec_state, ws->dec_subs_cap * sizeof(uint32_t)));
 	WS_CUDA(cudaMalloc(&ws->dec_count, ws->dec_subs_cap * sizeof(uint32_t)));
+	WS_CUDA(cudaMalloc(&ws->dec_prefix, ws->dec_subs_cap * sizeof(uint32_t)));
 	WS_CUDA(cudaMalloc(&ws->dec_seam, ws->dec_chunks_cap * sizeof(uint32_t)));
 	WS_CUDA(cudaMalloc(&ws->dec_chunk_total, ws->dec_chunks_cap * sizeof(uint64_t)));
 	WS_CUDA(cudaMalloc(&ws->dec_chunk_base, (ws->dec_chunks_cap + 1) * sizeof(uint64_t)));
@@ -387,7 +388,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 void mh_workspace_destroy(mh_workspace* ws) {
 	if(!ws) return;
 	void* ptrs[] = {ws->enc_desc, ws->counters, ws->hist_params, ws->dec_state,
-	                ws->dec_count, ws->dec_seam, ws->dec_chunk_total, ws->dec_chunk_base, ws->dec_flags};
+	                ws->dec_count, ws->dec_prefix, ws->dec_seam, ws->dec_chunk_total, ws->dec_chunk_base, ws->dec_flags};
 	for(void* p : ptrs)
 		if(p) cudaFree(p);
 	delete ws;

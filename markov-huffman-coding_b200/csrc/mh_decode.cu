@@ -758,21 +758,35 @@ __global__ void dec_seam_kernel(const uint32_t* __restrict__ words, uint64_t n_b
 // D3: per-chunk totals and their exclusive scan
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dec_total_kernel(const uint32_t* __restrict__ count, uint64_t n_subs, uint32_t chunk_subs,
-                                                         uint32_t skip_subs, unsigned long long* __restrict__ chunk_total) {
-	__shared__ unsigned long long part[8];
+                                                         uint32_t skip_subs, unsigned long long* __restrict__ chunk_total,
+                                                         uint32_t* __restrict__ prefix) {
+	// one CTA per chunk: the chunk's symbol total, and for every subsequence the symbols of the chunk before it
+	// (D4 adds the chunk's base and has its output offset without any scan of its own)
+	__shared__ uint32_t part[8];
+	__shared__ uint32_t carry_s;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint64_t first = uint64_t(blockIdx.x) * chunk_subs;
 	const uint64_t last = first + chunk_subs < n_subs ? first + chunk_subs : n_subs;
-	unsigned long long s = 0;
-	for(uint64_t k = first + threadIdx.x; k < last; k += 256)
-		if(k >= skip_subs) s += count[k];   // a shard's leading warm-up subsequences belong to its predecessor
-	for(int d = 16; d; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
-	if((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+	if(threadIdx.x == 0) carry_s = 0;
 	__syncthreads();
-	if(threadIdx.x == 0) {
-		unsigned long long t = 0;
-		for(int i = 0; i < 8; ++i) t += part[i];
-		chunk_total[blockIdx.x] = t;
+	for(uint64_t base = first; base < last; base += 256) {
+		const uint64_t k = base + threadIdx.x;
+		const uint32_t c = (k < last && k >= skip_subs) ? count[k] : 0u;   // a shard's leading warm-up subsequences belong to its predecessor
+		uint32_t incl = c;
+		for(int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+			if(lane >= uint32_t(d)) incl += t;
+		}
+		if(lane == 31) part[warp] = incl;
+		__syncthreads();
+		uint32_t before = carry_s;
+		for(uint32_t w = 0; w < warp; ++w) before += part[w];
+		if(k < last) prefix[k] = before + incl - c;
+		__syncthreads();
+		if(threadIdx.x == 255) carry_s = before + incl;
+		__syncthreads();
 	}
+	if(threadIdx.x == 0) chunk_total[blockIdx.x] = carry_s;
 }
 
 __global__ void __launch_bounds__(1024) dec_scan_kernel(const unsigned long long* __restrict__ chunk_total,
@@ -823,11 +837,10 @@ template <int ORDER, bool PAIR>
 __global__ void __launch_bounds__(PAIR ? kDecWriteMaxThreads : kDecThreads, 1) dec_write_kernel(   // launched with decode_write_threads()
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ pair_g, uint32_t pair_rows, uint32_t pair_ctx_rows,
-    const uint32_t* __restrict__ state, const uint32_t* __restrict__ count, const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits,
-    uint64_t n_subs, uint32_t n_chunks, uint32_t chunk_subs, uint32_t skip_subs, uint32_t stream_end, unsigned long long* result,
-    uint32_t lut_smem_bytes) {
-	extern __shared__ __align__(16) uint16_t lut_s[];   // table, then the payload rings
-	__shared__ uint32_t warp_tot[32];
+    const uint32_t* __restrict__ state, const uint32_t* __restrict__ count, const uint32_t* __restrict__ prefix,
+    const unsigned long long* __restrict__ chunk_base, uint8_t* __restrict__ out, uint32_t sub_bits, uint64_t n_subs, uint32_t chunk_subs,
+    uint32_t skip_subs, uint32_t stream_end, unsigned long long* result, unsigned long long* ticket, uint32_t lut_smem_bytes) {
+	extern __shared__ __align__(16) uint16_t lut_s[];   // table, then the payload rings, then the output rings
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	if(result[1] != 0) return;   // capacity / convergence error decided by D3: write nothing
 	PairTab T = {};
@@ -850,32 +863,17 @@ __global__ void __launch_bounds__(PAIR ? kDecWriteMaxThreads : kDecThreads, 1) d
 	os.ring_warp = lut_sa + lut_smem_bytes + blockDim.x * kRingBytesPerThread + warp * 32u * kOutRingBytes;
 	os.ring = os.ring_warp + lane * kOutRingBytes;
 	bool clean = true;
-	// A chunk (the unit D3 scanned) is written in slices of blockDim.x subsequences; fewer resident threads than D1
-	// keep every thread's current payload line in L1.
-	const uint32_t slices = (chunk_subs + blockDim.x - 1) / blockDim.x;
-	for(uint32_t work = blockIdx.x; work < n_chunks * slices; work += gridDim.x) {
-		const uint32_t chunk = work / slices, slice = work - chunk * slices;
-		const uint32_t in_chunk = slice * blockDim.x + tid;
-		const uint64_t k = uint64_t(chunk) * chunk_subs + in_chunk;
-		const bool mine = in_chunk < chunk_subs && k < n_subs && k >= skip_subs;
-		// symbols of the chunk's earlier slices: their counts are summed by every thread's warp-strided pass
-		uint32_t carry = 0;
-		for(uint32_t j = lane; j < slice * blockDim.x; j += 32) {
-			const uint64_t kk = uint64_t(chunk) * chunk_subs + j;
-			if(kk >= skip_subs && kk < n_subs) carry += count[kk];
-		}
-		for(int d = 16; d; d >>= 1) carry += __shfl_xor_sync(0xffffffffu, carry, d);
+	// Work is handed out per warp, 32 consecutive subsequences at a time, from an atomic counter: no barrier in
+	// the loop, no tail wait for the slowest warp of a CTA. A subsequence's output offset is its chunk's base (D3's
+	// scan) plus the symbols of the chunk before it (D3's prefix).
+	for(;;) {
+		unsigned long long base = 0;
+		if(lane == 0) base = atomicAdd(ticket, 32ull);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if(base >= n_subs) break;
+		const uint64_t k = base + lane;
+		const bool mine = k < n_subs && k >= skip_subs;
 		const uint32_t c = mine ? count[k] : 0u;
-		uint32_t incl = c;
-		for(int d = 1; d < 32; d <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-			if(lane >= uint32_t(d)) incl += t;
-		}
-		if(lane == 31) warp_tot[warp] = incl;
-		__syncthreads();
-		uint32_t before = carry;
-		for(uint32_t w = 0; w < warp; ++w) before += warp_tot[w];
-		__syncthreads();
 		// every lane goes through the emitter (the pair path writes out warp-wide); lanes without symbols pass count 0
 		const uint32_t start = !mine ? 0u : (k == 0 ? (start0 & 255u) : state[k - 1]);
 		const uint64_t origin = k * sub_bits + (start0 >> 8);
@@ -887,7 +885,7 @@ __global__ void __launch_bounds__(PAIR ? kDecWriteMaxThreads : kDecThreads, 1) d
 		uint8_t* dst = out;
 		if(c) {
 			cur.seek(origin + pos, pos);
-			dst = out + (chunk_base[chunk] + before + incl - c);
+			dst = out + (chunk_base[k / chunk_subs] + prefix[k]);
 		}
 		if(PAIR) {
 			clean &= decode_emit_pair<ORDER>(cur, T, lut_g, walk, c, ctx, dst, stream_end && k == n_subs - 1, os);
@@ -909,8 +907,8 @@ __global__ void __launch_bounds__(PAIR ? kDecWriteMaxThreads : kDecThreads, 1) d
 
 static uint32_t decode_write_threads() {
 	const char* env = getenv("MH_DEC_WRITE_THREADS");   // experiments
-	const int v = env ? atoi(env) : 512;
-	return (v >= 64 && v <= kDecWriteMaxThreads && v % 32 == 0) ? uint32_t(v) : 512u;
+	const int v = env ? atoi(env) : kDecWriteMaxThreads;
+	return (v >= 64 && v <= kDecWriteMaxThreads && v % 32 == 0) ? uint32_t(v) : uint32_t(kDecWriteMaxThreads);
 }
 
 uint32_t decode_sub_bits(int order, uint64_t n_bits) {
@@ -967,6 +965,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	const int sms = sm_count();
 	const uint32_t grid = n_chunks < uint32_t(sms) ? n_chunks : uint32_t(sms);
 	MH_CUDA(cudaMemsetAsync(ws->dec_flags, 0, 8 * sizeof(uint32_t), st));
+	MH_CUDA(cudaMemsetAsync(ws->counters + 4, 0, sizeof(unsigned long long), st));   // D4's work ticket
 	{
 		ProfScope p("dec_sync_kernel", st);
 		dec_sync_kernel<ORDER, PAIR><<<grid, kDecThreads, lut_bytes + size_t(kDecThreads) * kRingBytesPerThread, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, dt->d_pair,
@@ -988,7 +987,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	}
 	{
 		ProfScope p("dec_total_kernel", st);
-		dec_total_kernel<<<n_chunks, 256, 0, st>>>(ws->dec_count, n_subs, chunk_subs, skip_subs, (unsigned long long*) ws->dec_chunk_total);
+		dec_total_kernel<<<n_chunks, 256, 0, st>>>(ws->dec_count, n_subs, chunk_subs, skip_subs, (unsigned long long*) ws->dec_chunk_total, ws->dec_prefix);
 	}
 	{
 		ProfScope p("dec_scan_kernel", st);
@@ -997,14 +996,16 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	}
 	{
 		ProfScope p("dec_write_kernel", st);
-		const uint32_t wt = decode_write_threads();
-		const uint32_t wslices = (chunk_subs + wt - 1) / wt;
-		const uint64_t wwork = uint64_t(n_chunks) * wslices;
-		const char* wc_env = getenv("MH_DEC_WRITE_CTAS");   // experiments: resident CTAs per SM
-		const uint64_t wgrid = uint64_t(sms) * uint64_t(wc_env && atoi(wc_env) > 0 ? atoi(wc_env) : 1);
-		dec_write_kernel<ORDER, PAIR><<<unsigned(wwork < wgrid ? wwork : wgrid), wt, lut_bytes + size_t(wt) * (kRingBytesPerThread + (PAIR ? kOutRingBytes : 0u)), st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk,
-		    dt->d_pair, dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits, n_subs, n_chunks, chunk_subs, skip_subs,
-		    stream_end, d_result, uint32_t(lut_bytes));
+		// threads per CTA: as many warps as the table and the per-thread rings leave room for, one CTA per SM
+		const size_t per_thread = kRingBytesPerThread + (PAIR ? kOutRingBytes : 0u);
+		uint32_t wt = decode_write_threads();
+		while(wt > 128 && lut_bytes + size_t(wt) * per_thread + 1024 > size_t(max_smem_optin())) wt -= 128;
+		const uint64_t warps_needed = (n_subs + 31) / 32;
+		uint64_t wgrid = (warps_needed + wt / 32 - 1) / (wt / 32);
+		if(wgrid > uint64_t(sms)) wgrid = uint64_t(sms);
+		dec_write_kernel<ORDER, PAIR><<<unsigned(wgrid), wt, lut_bytes + size_t(wt) * per_thread, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk,
+		    dt->d_pair, dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, ws->dec_prefix, (const unsigned long long*) ws->dec_chunk_base, d_out, sub_bits,
+		    n_subs, chunk_subs, skip_subs, stream_end, d_result, reinterpret_cast<unsigned long long*>(ws->counters + 4), uint32_t(lut_bytes));
 	}
 	count_launch(3);
 	MH_CUDA(cudaGetLastError());

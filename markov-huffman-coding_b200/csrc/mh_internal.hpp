@@ -70,6 +70,7 @@ struct mh_workspace {
 	// decode
 	uint32_t* dec_state = nullptr;        // [dec_subs_cap] end state of each subsequence: rel_bits << 8 | context
 	uint32_t* dec_count = nullptr;        // [dec_subs_cap] symbols that start in each subsequence
+	uint32_t* dec_prefix = nullptr;       // [dec_subs_cap] symbols of the same chunk before each subsequence
 	uint64_t dec_subs_cap = 0;
 	uint32_t* dec_seam = nullptr;         // [dec_chunks_cap] boundary state as seen by the next chunk's warm-up
 	uint64_t* dec_chunk_total = nullptr;  // [dec_chunks_cap]
