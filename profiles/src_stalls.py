@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-source-line stall samples of an ncu report: python scratch/src_stalls.py X.ncu-rep [top]"""
+"""Per-source-line stall samples of an ncu report: python profiles/src_stalls.py X.ncu-rep [top]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout

@@ -44,6 +44,11 @@ def stalls(rep, top=14):
     return p.stdout
 
 
+def src_stalls(rep, top=14):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "src_stalls.py"), rep, str(top)], stdout=subprocess.PIPE, text=True)
+    return p.stdout
+
+
 def launch_list(path):
     rows = list(csv.reader(open(path)))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -72,13 +77,14 @@ def main():
             fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n")
             fh.write("# command: python bench.py --steps 1 --warmup 3 --bytes 268435456 --no-cpu-baseline --no-e2e\n")
             fh.write(launch_list(ll) + "\n")
-    for k in ("hist_kernel", "encode_kernel", "dec_sync_kernel", "dec_write_kernel"):
+    for k in ("hist_lane_kernel", "hist_kernel", "encode_kernel", "dec_sync_kernel", "dec_write_kernel"):
         rep = os.path.join(OUT, "%s_%s.ncu-rep" % (tag, k))
         if not os.path.exists(rep):
             continue
         with open(os.path.join(ROOT, "profiles", "%s_%s.txt" % (tag, k)), "w") as fh:
             fh.write("# ncu --set full --clock-control none --import-source on, 1 launch, 256 MiB Markov text\n")
-            fh.write(raw_metrics(rep) + "\n\n# warp stall samples (source page)\n" + stalls(rep))
+            fh.write(raw_metrics(rep) + "\n\n# warp stall samples by SASS instruction\n" + stalls(rep))
+            fh.write("\n# warp stall samples by source line (-lineinfo)\n" + src_stalls(rep))
         print("wrote", k)
 
 
