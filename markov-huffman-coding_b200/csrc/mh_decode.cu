@@ -452,7 +452,9 @@ __device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab
 // thread's range are written with byte masks.
 // ---------------------------------------------------------------------------------------------------------
 constexpr uint32_t kOutRingBytes = 128;
-constexpr uint32_t kFlushEvery = 4;   // iterations between flush rounds: a unit fills in >= 8 iterations (<= 8 symbols each)
+constexpr uint32_t kFlushEvery = 8;   // iterations between flush rounds. At a round a thread's current unit holds < 64 bytes and
+                                      // everything before it has left; 8 iterations add <= 64 bytes, so the thread cannot reach the
+                                      // ring half of that unit again before the next round has written it out
 
 __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool go) {
 	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(uint32_t(go)) : "memory");
@@ -959,7 +961,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 		const int ring_bytes = kDecThreads * int(kRingBytesPerThread);
 		MH_CUDA(cudaFuncSetAttribute(dec_sync_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (PAIR ? kDecPairBytes : int(lut_bytes)) + ring_bytes));
 		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		                             (PAIR ? kDecPairBytes + kDecWriteMaxThreads * int(kRingBytesPerThread + kOutRingBytes) : int(lut_bytes) + ring_bytes)));
+		                             PAIR ? max_smem_optin() - 1024 : int(lut_bytes) + ring_bytes));   // pair path: the launcher fits the thread count
 		attr_done = true;
 	}
 	const int sms = sm_count();
@@ -999,7 +1001,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 		// threads per CTA: as many warps as the table and the per-thread rings leave room for, one CTA per SM
 		const size_t per_thread = kRingBytesPerThread + (PAIR ? kOutRingBytes : 0u);
 		uint32_t wt = decode_write_threads();
-		while(wt > 128 && lut_bytes + size_t(wt) * per_thread + 1024 > size_t(max_smem_optin())) wt -= 128;
+		while(wt > 128 && lut_bytes + size_t(wt) * per_thread + 1024 > size_t(max_smem_optin())) wt -= 32;
 		const uint64_t warps_needed = (n_subs + 31) / 32;
 		uint64_t wgrid = (warps_needed + wt / 32 - 1) / (wt / 32);
 		if(wgrid > uint64_t(sms)) wgrid = uint64_t(sms);

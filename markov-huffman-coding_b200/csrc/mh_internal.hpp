@@ -42,7 +42,7 @@ constexpr int kEncCtxMaxBits = 28;                    // context-row entry: 5-bi
 constexpr int kEncCtxMaxRows = 96;                    // live contexts + null row; table + staging must leave room for 2 CTAs/SM
 constexpr int kEncCtxSmemLimit = 112 * 1024;          // table + staging area of one CTA
 constexpr int kDecThreads = 1024;                     // subsequences per chunk (one thread each)
-constexpr int kDecWriteMaxThreads = 768;              // D4 threads per CTA: table + 192 B of rings per thread must fit one SM
+constexpr int kDecWriteMaxThreads = 768;              // D4 threads per CTA (measured best of 512..960): table + 192 B of rings per thread
 constexpr int kDecMinSubBits = 256;
 constexpr uint32_t kDecMaxSubBitsMarkov = 8192;       // measured best of 2048..16384 on the 1 GiB Markov text
 constexpr uint32_t kDecMaxSubBitsHuffman = 2048;
