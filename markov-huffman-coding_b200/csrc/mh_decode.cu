@@ -37,16 +37,24 @@ constexpr uint32_t kDeep = 0x10u, kNull = 0x20u, kExt = 0x40u;
 // after them. pos / loaded are bit offsets relative to an origin chosen by the caller.
 //
 // The payload reaches the window through a small ring in shared memory that every thread owns privately:
-// kRingPieces aligned 16-byte chunks, filled by cp.async (global -> shared, no registers, L1 bypassed) as soon as the
-// chunk in that slot has been consumed. A chunk is therefore requested (kRingPieces - 1) x 128 stream bits before its
-// first word is needed — many iterations of the decode loop — so no warp ever waits for the one lane of 32 whose
-// next word happens to miss: with plain loads, one word ahead, almost every iteration of a warp had such a lane.
+// kRingPieces aligned 16-byte chunks, filled by cp.async (global -> shared, no registers, L1 bypassed). With plain
+// loads, one word ahead, almost every iteration of a warp had one lane of 32 whose next word missed, and the warp
+// waited for it. The ring is topped up on a fixed cadence — every kRefillEvery-th top_up(), i.e. at the same
+// iteration for all lanes of a warp, with predicated copies — because a refill that each lane triggers when IT
+// crosses a chunk boundary is rare per lane but happens in most iterations of the warp, and then the whole warp
+// steps through the refill code for a handful of lanes (measured: 78 % of D1's iterations, 6 lanes active).
+// Between two top_up() calls at most 32 bits are consumed, so a round sees at most one chunk (four words) used up;
+// a chunk is requested two rounds (>= 256 stream bits) before its first word can be popped, and each round waits
+// for the copies of the round before it.
 // The pieces of the 32 lanes of a warp are interleaved (piece j of lane l at (j * 32 + l) * 16) to spread the banks.
 constexpr uint32_t kRingPieces = 4;
 constexpr uint32_t kRingBytesPerThread = kRingPieces * 16;
+constexpr uint32_t kRefillEvery = 4;
 
-__device__ __forceinline__ void cp_async_16(uint32_t dst_shared, const void* src, uint32_t src_bytes) {
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_shared), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async_16_if(uint32_t dst_shared, const void* src, uint32_t src_bytes, bool go) {
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(dst_shared), "l"(src), "r"(src_bytes),
+	             "r"(uint32_t(go))
+	             : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -57,32 +65,34 @@ struct Cursor {
 	uint64_t n_bytes;        // payload bytes; reads past them return zero (pop_rest pads, src/bitbuffer.cpp:129-140)
 	uint32_t ring;           // shared-space address of this thread's piece 0 (set once by the kernel)
 	uint32_t cw;             // next chunk to request, counted from the 16-byte boundary at or before `words`
-	uint32_t rd;             // shared-space address of the next word to pop
+	uint32_t rw;             // next word to pop, counted from the same boundary
+	uint32_t ticks;          // top_up() calls since the last seek
 	uint32_t hi, lo, nextw;  // nextw is kept in memory (little-endian) order and byte-swapped only when consumed
 	uint32_t pos, loaded;
 
 	__device__ __forceinline__ void attach(uint32_t ring_base_shared) {
 		ring = ring_base_shared + ((threadIdx.x >> 5) * (kRingPieces * 32u) + (threadIdx.x & 31u)) * 16u;
 	}
-	// chunk c -> slot c % kRingPieces; bytes outside the payload are zero-filled by the copy itself
-	__device__ __forceinline__ void request(uint32_t c) {
+	// chunk c -> slot c % kRingPieces (if `go`); bytes outside the payload are zero-filled by the copy itself
+	__device__ __forceinline__ void request_if(uint32_t c, bool go) {
 		const uint64_t addr = reinterpret_cast<uint64_t>(words);
 		const uint64_t base = addr & ~uint64_t(15);
 		const int64_t left = int64_t((addr & 15) + n_bytes) - (int64_t(c) << 4);   // payload bytes from the chunk's start on
 		const uint32_t n = left >= 16 ? 16u : (left > 0 ? uint32_t(left) : 0u);
-		cp_async_16(ring + (c & (kRingPieces - 1)) * 512u, reinterpret_cast<const void*>(n ? base + (uint64_t(c) << 4) : base), n);
+		cp_async_16_if(ring + (c & (kRingPieces - 1)) * 512u, reinterpret_cast<const void*>(n ? base + (uint64_t(c) << 4) : base), n, go);
+	}
+	// keep kRingPieces chunks requested from the one being read on: at most one is missing per round (<= 4 pops)
+	__device__ __forceinline__ void refill_round() {
+		const bool go = int32_t((rw >> 2) + kRingPieces - cw) > 0;
+		request_if(cw, go);
+		cw += go ? 1u : 0u;
 		cp_async_commit();
+		cp_async_wait<2>();   // a chunk is first popped three rounds after its request: two rounds may stay in flight
 	}
 	__device__ __forceinline__ uint32_t pop() {
 		uint32_t w;
-		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rd) : "memory");
-		rd += 4;
-		if((rd & 12u) == 0) {   // the chunk is used up: refill its slot with the chunk kRingPieces ahead, move on to the next slot
-			request(cw++);
-			rd += 512u - 16u;
-			if(rd >= ring + kRingPieces * 512u) rd -= kRingPieces * 512u;
-			cp_async_wait<kRingPieces - 1>();   // all but the newest requests have landed: the next slot is ready
-		}
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(ring + ((rw << 7) & ((kRingPieces - 1) << 9)) + ((rw << 2) & 12u)) : "memory");
+		++rw;
 		return w;
 	}
 	__device__ __forceinline__ void seek(uint64_t bit, uint32_t rel) {
@@ -90,13 +100,18 @@ struct Cursor {
 		const uint64_t w = abs_bit >> 5;
 		const uint32_t off = uint32_t(abs_bit & 31);
 		cp_async_wait<0>();   // nothing of a previous subsequence may still land in the ring
-		cw = uint32_t(w >> 2);
-		rd = ring + (cw & (kRingPieces - 1)) * 512u + (uint32_t(w) & 3u) * 4u;
+		rw = uint32_t(w);
+		cw = rw >> 2;
+		ticks = 0;
 #pragma unroll
-		for(uint32_t j = 0; j < kRingPieces; ++j) request(cw++);
-		cp_async_wait<kRingPieces - 1>();
+		for(uint32_t j = 0; j < kRingPieces; ++j) request_if(cw++, true);
+		cp_async_commit();
+		cp_async_wait<0>();
 		const uint32_t w0 = __byte_perm(pop(), 0, 0x0123), w1 = __byte_perm(pop(), 0, 0x0123);
 		nextw = pop();
+		request_if(cw, (rw >> 2) + kRingPieces != cw);   // the three pops may have finished the first chunk
+		cw = (rw >> 2) + kRingPieces;
+		cp_async_commit();
 		hi = __funnelshift_l(w1, w0, off);
 		lo = w1 << off;
 		pos = rel;
@@ -112,6 +127,7 @@ struct Cursor {
 		asm("shl.b32 %0, %0, %1;" : "+r"(lo) : "r"(nbits));   // PTX shl clamps: 32 -> 0
 		pos += nbits;
 	}
+	// Called at least once per 32 bits consumed.
 	__device__ __forceinline__ void top_up() {
 		const uint32_t avail = loaded - pos;
 		if(avail <= 32) {   // all valid bits sit in hi
@@ -121,6 +137,7 @@ struct Cursor {
 			loaded += 32;
 			nextw = pop();
 		}
+		if((++ticks & (kRefillEvery - 1)) == 0) refill_round();
 	}
 };
 
