@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 	bool pending = false;          // a packed tile is waiting in the staging area
 	uint32_t p_tile = 0, p_bits = 0;
 	for(uint32_t it = 0;; ++it) {
-		bar_workers();
+		// no barrier here: every iteration ends with one (after the pack, or after re-zeroing the staging area), and the
+		// ticket read below was written before it
 		const uint32_t tile = s_tile[it & 1];
 		const bool valid = tile < A.n_tiles;
 		if(!valid && !pending) {
