@@ -9,8 +9,8 @@ tag=${1:-r01}
 mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || { echo "bench failed"; tail -5 gpurun_out/bench_$tag.err; exit 1; }
 echo "bench: $(cut -c1-160 gpurun_out/bench_$tag.json)"
-SHORT="python bench.py --steps 1 --warmup 3 --bytes 268435456 --no-cpu-baseline --no-e2e"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $SHORT > gpurun_out/ncu_list.log 2>&1
+FULL="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $FULL > gpurun_out/ncu_list.log 2>&1
 echo "launch list: $(grep -c gpu__time_duration gpurun_out/launches_$tag.csv) rows"
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'hist_lane_kernel|encode_kernel|dec_sync_kernel|dec_write_kernel' \
     --csv --log-file gpurun_out/traffic_$tag.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_traffic.log 2>&1

@@ -75,7 +75,7 @@ def main():
     if os.path.exists(ll):
         with open(os.path.join(ROOT, "profiles", "%s_launches.txt" % tag), "w") as fh:
             fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n")
-            fh.write("# command: python bench.py --steps 1 --warmup 3 --bytes 268435456 --no-cpu-baseline --no-e2e\n")
+            fh.write("# command: python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e (1 GiB)\n")
             fh.write(launch_list(ll) + "\n")
     for k in ("hist_lane_kernel", "hist_kernel", "encode_kernel", "dec_sync_kernel", "dec_write_kernel"):
         rep = os.path.join(OUT, "%s_%s.ncu-rep" % (tag, k))
