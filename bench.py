@@ -294,7 +294,8 @@ def main():
             if rank > 0:
                 prev0 = int(msgs[rank - 1, 65537])
         th0 = time.perf_counter()
-        provider = mh.CodingProvider.from_counts_array(sharding.global_counts(all_counts), 1)     # identical on every rank
+        total_counts = sharding.global_counts(all_counts)
+        provider = mh.CodingProvider.from_counts_array(total_counts, 1)     # identical on every rank
         th1 = time.perf_counter()
         if book is None:
             book, dectab = mh.Codebook(provider), mh.DecodeTable(provider)
@@ -302,7 +303,7 @@ def main():
         th2 = time.perf_counter()
         expect_bits = None
         if world > 1:   # every rank derives every shard's global bit offset from the gathered histograms
-            base, shard_bits = sharding.shard_bit_bases(all_counts, provider.code_lengths())
+            base, shard_bits = sharding.shard_bit_bases(all_counts, provider.code_lengths(np.uint8), total_counts)
             bit_base, expect_bits = int(base[rank]), int(shard_bits[rank])
         mh.gpu_encode(d_in.data_ptr(), n, prev0, book, bit_base, d_payload.data_ptr(), payload_cap, d_res_enc.data_ptr(), ws, stream)
         h_res[:4].copy_(d_res_enc, non_blocking=True)

@@ -213,13 +213,14 @@ class CodingProvider:
     def max_code_bits(self):
         return _lib.mh_table_max_code_bits(self._h)
 
-    def code_lengths(self):
-        """numpy uint64 array of all code lengths: [65536] indexed 256*prev + c (order 1) or [256] (order 0)."""
+    def code_lengths(self, dtype=None):
+        """numpy array of all code lengths: [65536] indexed 256*prev + c (order 1) or [256] (order 0); uint64 unless
+        another dtype is asked for (uint8 is what the library hands out)."""
         import numpy as np
         n = 65536 if self.get_type() else 256
         lens = np.zeros(n, dtype=np.uint8)
         _check(_lib.mh_table_code_lengths(self._h, lens.ctypes.data, n), "mh_table_code_lengths")
-        return lens.astype(np.uint64)
+        return lens.astype(np.uint64 if dtype is None else dtype, copy=False)
 
     def decoding_lookup(self, prev, window):
         """(kind, value, depth): kind 0 null, 1 leaf, 2 internal node at depth 8."""

@@ -18,15 +18,19 @@ def global_counts(all_counts):
     a = np.asarray(all_counts, dtype=np.uint64)
     if a.ndim == 1 or a.shape[0] == 1:
         return np.ascontiguousarray(a.reshape(-1))
-    return np.ascontiguousarray(a.sum(axis=0, dtype=np.uint64))
+    out = a[0] + a[1]                       # row-wise adds run along the contiguous axis (a [world, bins] reduction over
+    for r in range(2, a.shape[0]):          # axis 0 is ~5x slower in numpy, and this sits between histogram and encoder)
+        out += a[r]
+    return out
 
 
-def shard_bits(all_counts, code_lengths):
-    """Payload bits of every shard: uint64 [world]. Only the (prev, c) pairs that have a codeword contribute."""
-    lens = np.asarray(code_lengths, dtype=np.uint64)
-    live = np.flatnonzero(lens)
+def shard_bits(all_counts, code_lengths, total=None):
+    """Payload bits of every shard: uint64 [world]. Only the (prev, c) pairs that have a codeword contribute.
+    (`total` is accepted for symmetry with global_counts; the code lengths already say which pairs are live.)"""
     a = np.asarray(all_counts, dtype=np.uint64)
-    return (a[:, live] * lens[live][None, :]).sum(axis=1, dtype=np.uint64)
+    lens = np.asarray(code_lengths)
+    live = np.flatnonzero(lens)             # fastest on the uint8 lengths the library hands out
+    return np.take(a, live, axis=1) @ lens[live].astype(np.uint64)
 
 
 def fix_seam_pairs(all_counts, first_bytes, last_bytes, guess=0x20):
@@ -39,9 +43,9 @@ def fix_seam_pairs(all_counts, first_bytes, last_bytes, guess=0x20):
     return all_counts
 
 
-def shard_bit_bases(all_counts, code_lengths):
+def shard_bit_bases(all_counts, code_lengths, total=None):
     """(bit_base [world], bits [world]): exclusive scan of the shard payload sizes."""
-    bits = shard_bits(all_counts, code_lengths)
+    bits = shard_bits(all_counts, code_lengths, total)
     base = np.zeros_like(bits)
     if len(bits) > 1:
         base[1:] = np.cumsum(bits[:-1], dtype=np.uint64)

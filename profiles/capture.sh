@@ -7,6 +7,6 @@ kernels=${@:-hist_lane_kernel encode_kernel dec_sync_kernel dec_write_kernel}
 mkdir -p gpurun_out
 for k in $kernels; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/${tag}_$k \
-    python bench.py --steps 1 --warmup 3 --bytes 268435456 --no-cpu-baseline --no-e2e > gpurun_out/ncu_${tag}_$k.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_${tag}_$k.log 2>&1
   echo "$k: $(grep -c 'Profiling' gpurun_out/ncu_${tag}_$k.log) launch profiled"
 done

@@ -3,7 +3,7 @@
 #   1. the default bench line, no profiler attached                    -> gpurun_out/bench_<tag>.json
 #   2. the launch list of a short run (per-kernel share of the step)   -> gpurun_out/launches_<tag>.csv
 #   3. DRAM traffic of the main kernels at the bench's full size       -> gpurun_out/traffic_<tag>.csv
-#   4. one `ncu --set full` capture per main kernel (256 MiB input)    -> gpurun_out/<tag>_<kernel>.ncu-rep
+#   4. one `ncu --set full` capture per main kernel (bench size)    -> gpurun_out/<tag>_<kernel>.ncu-rep
 # Then, back in the container:  python profiles/summarize.py <tag> && python profiles/traffic.py <tag>
 tag=${1:-r01}
 mkdir -p gpurun_out

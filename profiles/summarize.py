@@ -82,7 +82,7 @@ def main():
         if not os.path.exists(rep):
             continue
         with open(os.path.join(ROOT, "profiles", "%s_%s.txt" % (tag, k)), "w") as fh:
-            fh.write("# ncu --set full --clock-control none --import-source on, 1 launch, 256 MiB Markov text\n")
+            fh.write("# ncu --set full --clock-control none --import-source on, 1 launch after warm-up, the bench workload (1 GiB Markov text)\n")
             fh.write(raw_metrics(rep) + "\n\n# warp stall samples by SASS instruction\n" + stalls(rep))
             fh.write("\n# warp stall samples by source line (-lineinfo)\n" + src_stalls(rep))
         print("wrote", k)
