@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 	__shared__ uint32_t s_tile[2];
 	__shared__ volatile uint32_t s_pub_tile[2], s_pub_bits[2];    // workers -> scanner: tile and bit count of iteration i
 	__shared__ volatile unsigned long long s_prefix_bits[2];      // scanner -> workers: bits before that tile ...
-	__shared__ volatile uint32_t s_prefix_tail[2];                // ... and the last 31 of them
+	__shared__ volatile uint32_t s_head[2];                       // workers -> scanner: the first staged word of that tile
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint32_t table_entries = 0;
@@ -288,22 +288,46 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 	// ---- the scanner warp: resolves every tile's global bit offset as soon as its bit count is known, one iteration
 	// before the workers need it, so that nobody ever waits for the chained scan ----
 	if(tid >= kEncThreads) {
+		// The output word a tile shares with its predecessor (the predecessor's last bits, then this tile's first bits)
+		// is written by the scanner, one iteration later: it is the only thing that needs the predecessor's tail, which
+		// is published when the predecessor has been PACKED — waiting for that in the workers kept every CTA in step
+		// with the slowest tile before it.
+		bool have_prev = false;
+		uint32_t q_tile = 0, q_bits = 0, q_near = 0;
+		unsigned long long q_excl = 0;
+		auto boundary_word = [&](uint32_t head) {   // lane 0: the first output word of tile q_tile, if it shares it
+			const unsigned long long g0 = A.bit0 + q_excl, g1 = g0 + q_bits;
+			const uint32_t s = uint32_t(g0 & 31);
+			const unsigned long long w0 = g0 >> 5;
+			unsigned long long w1 = g1 >> 5;
+			if(q_tile == A.n_tiles - 1 && (g1 & 31)) ++w1;
+			if(s == 0 || w1 == w0 || w1 > A.out_capacity_words) return;   // the workers' word / nothing completed / capacity error
+			const uint32_t carry = predecessor_tail(q_tile, q_near, A) & ((1u << s) - 1u);
+			A.out_words[w0] = __byte_perm(__funnelshift_r(head, carry, s), 0, 0x0123);
+		};
 		for(uint32_t it = 0;; ++it) {
 			bar_wait(2 + (it & 1));
 			const uint32_t tile = s_pub_tile[it & 1];
-			if(tile >= A.n_tiles) break;
-			const uint32_t bits = s_pub_bits[it & 1];
-			unsigned long long excl_bits;
-			uint32_t nearest_bits;
-			look_back(tile, bits, A, excl_bits, nearest_bits);
-			if(lane == 0) {
-				s_prefix_bits[it & 1] = excl_bits;
-				s_prefix_tail[it & 1] = predecessor_tail(tile, nearest_bits, A);
-				if(tile == A.n_tiles - 1) A.result[0] = excl_bits + bits;
-				__threadfence_block();
+			const uint32_t head = s_head[(it - 1) & 1];   // of the tile packed in iteration it - 1 (read before the workers can reuse the slot)
+			if(tile < A.n_tiles) {
+				const uint32_t bits = s_pub_bits[it & 1];
+				unsigned long long excl_bits;
+				uint32_t nearest_bits;
+				look_back(tile, bits, A, excl_bits, nearest_bits);
+				if(lane == 0) {
+					s_prefix_bits[it & 1] = excl_bits;
+					if(tile == A.n_tiles - 1) A.result[0] = excl_bits + bits;
+					__threadfence_block();
+				}
+				__syncwarp();
+				bar_arrive(4 + (it & 1));
+				if(lane == 0 && have_prev) boundary_word(head);
+				__syncwarp();   // the warp meets the next barrier converged
+				have_prev = true; q_tile = tile; q_bits = bits; q_near = nearest_bits; q_excl = excl_bits;
+			} else {
+				if(lane == 0 && have_prev) boundary_word(head);
+				break;
 			}
-			__syncwarp();
-			bar_arrive(4 + (it & 1));
 		}
 		return;
 	}
@@ -492,7 +516,6 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 		if(pending) {
 			bar_wait(4 + ((it - 1) & 1));   // normally passed at once: the scanner had a whole iteration
 			const unsigned long long prefix_bits = s_prefix_bits[(it - 1) & 1];
-			const uint32_t prefix_tail = s_prefix_tail[(it - 1) & 1];
 			// funnel-shift copy-out
 			const unsigned long long g0 = A.bit0 + prefix_bits;     // global bit index of the tile's first bit
 			const unsigned long long g1 = g0 + p_bits;
@@ -504,9 +527,9 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 			if(w1 > A.out_capacity_words) {
 				if(tid == 0) A.result[2] = 1;                         // capacity error; this tile writes nothing
 			} else {
-				const uint32_t carry = s ? (prefix_tail & ((1u << s) - 1u)) : 0u;   // predecessor bits that open word w0
-				for(uint32_t j = tid; j < nw; j += kEncThreads) {
-					const uint32_t hi = j ? stage[j - 1] : carry;
+				// a word shared with the predecessor (s != 0: its last s bits open word w0) is the scanner's
+				for(uint32_t j = tid + (s ? 1u : 0u); j < nw; j += kEncThreads) {
+					const uint32_t hi = j ? stage[j - 1] : 0u;
 					const uint32_t v = __funnelshift_r(stage[j], hi, s);
 					A.out_words[w0 + j] = __byte_perm(v, 0, 0x0123);
 				}
@@ -576,6 +599,7 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 			if(tid == 0) {     // the tail goes out now: successors need it only when they write their first word
 				const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
 				st_relaxed32(A.tail + tile, kTailValid | stage_bits(stage, tile_bits - tcount, tcount));
+				s_head[it & 1] = stage[0];   // for the scanner: the bits that share an output word with the predecessor
 			}
 			pending = true;
 			p_tile = tile;
