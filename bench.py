@@ -259,6 +259,7 @@ def main():
     d_res_enc = torch.zeros(4, dtype=torch.int64, device=dev)
     d_res_dec = torch.zeros(4, dtype=torch.int64, device=dev)
     h_counts = torch.empty(MSG * world, dtype=torch.int64, pin_memory=True)
+    h_total = torch.empty(65536, dtype=torch.int64, pin_memory=True)     # the summed histogram (world > 1: reduced on the GPU)
     h_res = torch.empty(8, dtype=torch.int64, pin_memory=True)
     ws = mh.Workspace(n, payload_cap)
     book = dectab = None
@@ -284,6 +285,7 @@ def main():
             d_msg[65536:] = d_in[edge_idx]
             dist.all_gather_into_tensor(gathered, d_msg)
             h_counts.copy_(gathered, non_blocking=True)
+            h_total.copy_(gathered.view(world, MSG)[:, :65536].sum(0), non_blocking=True)   # the host only fixes the seam pairs
         else:
             h_counts[:MSG].copy_(d_msg, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -294,7 +296,11 @@ def main():
             if rank > 0:
                 prev0 = int(msgs[rank - 1, 65537])
         th0 = time.perf_counter()
-        total_counts = sharding.global_counts(all_counts)
+        if world > 1:
+            total_counts = h_total.numpy().view(np.uint64)
+            sharding.fix_seam_total(total_counts, msgs[:, 65536], msgs[:, 65537])
+        else:
+            total_counts = sharding.global_counts(all_counts)
         provider = mh.CodingProvider.from_counts_array(total_counts, 1)     # identical on every rank
         th1 = time.perf_counter()
         if book is None:

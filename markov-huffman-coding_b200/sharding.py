@@ -43,6 +43,16 @@ def fix_seam_pairs(all_counts, first_bytes, last_bytes, guess=0x20):
     return all_counts
 
 
+def fix_seam_total(total, first_bytes, last_bytes, guess=0x20):
+    """The same correction as fix_seam_pairs, applied to the SUM of the local histograms (uint64 [65536], in place):
+    used when the sum was reduced on the GPU before the seam bytes were known."""
+    for g in range(1, len(first_bytes)):
+        f, true_prev = int(first_bytes[g]), int(last_bytes[g - 1])
+        total[256 * guess + f] -= 1
+        total[256 * true_prev + f] += 1
+    return total
+
+
 def shard_bit_bases(all_counts, code_lengths, total=None):
     """(bit_base [world], bits [world]): exclusive scan of the shard payload sizes."""
     bits = shard_bits(all_counts, code_lengths, total)

@@ -209,8 +209,12 @@ def test_seam_pair_fixup_and_shard_sizes_from_histograms():
     d = golden_input("input_wiki_cpp.html")
     cuts = [0, 100000, 200001, len(d)]
     ac = np.stack([o.histogram(d[a:b], True, 0x20).astype(np.int64).astype(np.uint64) for a, b in zip(cuts[:-1], cuts[1:])])
+    raw_total = ac.sum(axis=0, dtype=np.uint64)        # what a reduction on the GPU delivers before the seams are known
     sharding.fix_seam_pairs(ac, [d[a] for a in cuts[:-1]], [d[b - 1] for b in cuts[1:]])
     assert np.array_equal(sharding.global_counts(ac), o.histogram(d, True).astype(np.int64).astype(np.uint64))
+    assert np.array_equal(sharding.fix_seam_total(raw_total, [d[a] for a in cuts[:-1]], [d[b - 1] for b in cuts[1:]]), sharding.global_counts(ac))
+    assert np.array_equal(sharding.shard_bits(ac, mh.CodingProvider.from_counts_array(sharding.global_counts(ac), 1).code_lengths(np.uint8)),
+                          sharding.shard_bits(ac, mh.CodingProvider.from_counts_array(sharding.global_counts(ac), 1).code_lengths()))
     provider = mh.CodingProvider.from_counts_array(sharding.global_counts(ac), 1)
     base, bits = sharding.shard_bit_bases(ac, provider.code_lengths())
     table = o.Table.from_counts(o.histogram(d, True), True)
