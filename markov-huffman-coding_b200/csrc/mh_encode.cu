@@ -535,8 +535,8 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 				}
 			}
 			bar_workers();
-			const uint32_t used = (p_bits + 31) / 32 + 1;
-			for(uint32_t j = tid; j < used; j += kEncThreads) stage[j] = 0;
+			const uint32_t used4 = ((p_bits + 31) / 32 + 1 + 3) / 4;   // 16 bytes per store; the staging area has the slack
+			for(uint32_t j = tid; j < used4; j += kEncThreads) reinterpret_cast<uint4*>(stage)[j] = make_uint4(0, 0, 0, 0);
 			bar_workers();   // the staging area is clean before the next tile is packed into it
 			pending = false;
 		}
