@@ -180,11 +180,14 @@ def test_encoder_table_formats_agree(session, ipsum_counts, fmt, monkeypatch):
         assert session.compress(data, order)[0] == want[order]
 
 
+@pytest.mark.parametrize("pair", ["1", "0"], ids=["pair-table", "lut8"])
 @pytest.mark.parametrize("sub_bits", ["256", "1024", "8192"])
-def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, monkeypatch):
-    """The subsequence size only changes how the work is cut, never the bytes."""
+def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, pair, monkeypatch):
+    """The subsequence size only changes how the work is cut, never the bytes — through the two-symbol pair table
+    (text has few live contexts) and, forced, through the reference's 8-bit LUT + tree walk."""
     monkeypatch.setenv("MH_DEC_SUB_BITS_MARKOV", sub_bits)
     monkeypatch.setenv("MH_DEC_SUB_BITS_HUFFMAN", sub_bits)
+    monkeypatch.setenv("MH_DEC_PAIR", pair)
     s = mh.Session(8 << 20)
     try:
         text = o.synth_markov(ipsum_counts, 9, 4096, 0, (2 << 20) + 123)
