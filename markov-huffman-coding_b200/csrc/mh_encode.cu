@@ -278,10 +278,10 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 		table_entries = A.ctx_rows * 256u;
 		for(uint32_t i = tid; i < table_entries / 4; i += kEncCtaThreads) reinterpret_cast<uint4*>(table)[i] = __ldg(reinterpret_cast<const uint4*>(A.ctx) + i);
 	}
-	uint32_t* stage = smem + ((table_entries + 3) & ~3u);   // [stage_words + 4]
+	uint32_t* stage = smem + ((table_entries + 3) & ~3u) + 4;   // [stage_words + 4], after four zero words: stage[-1] reads as "no bits"
 	const uint32_t table_sa = uint32_t(__cvta_generic_to_shared(table));
 	const uint32_t stage_sa = uint32_t(__cvta_generic_to_shared(stage));
-	for(uint32_t i = tid; i < A.stage_words + 4; i += kEncCtaThreads) stage[i] = 0;
+	for(uint32_t i = tid; i < A.stage_words + 8; i += kEncCtaThreads) stage[int(i) - 4] = 0;
 	if(tid == 0) s_tile[0] = atomicAdd(A.ticket, 1u);
 	__syncthreads();
 
@@ -528,11 +528,11 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 				if(tid == 0) A.result[2] = 1;                         // capacity error; this tile writes nothing
 			} else {
 				// a word shared with the predecessor (s != 0: its last s bits open word w0) is the scanner's
-				for(uint32_t j = tid + (s ? 1u : 0u); j < nw; j += kEncThreads) {
-					const uint32_t hi = j ? stage[j - 1] : 0u;
-					const uint32_t v = __funnelshift_r(stage[j], hi, s);
-					A.out_words[w0 + j] = __byte_perm(v, 0, 0x0123);
-				}
+				uint32_t j = tid + (s ? 1u : 0u);
+				uint32_t* dp = A.out_words + w0 + j;
+				const uint32_t* sp = stage + j;
+				for(; j < nw; j += kEncThreads, dp += kEncThreads, sp += kEncThreads)
+					*dp = __byte_perm(__funnelshift_r(sp[0], sp[-1], s), 0, 0x0123);   // sp[-1] of word 0 is the zero word in front
 			}
 			bar_workers();
 			const uint32_t used4 = ((p_bits + 31) / 32 + 1 + 3) / 4;   // 16 bytes per store; the staging area has the slack
@@ -684,7 +684,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.result = d_result;
 	a.n_tiles = uint32_t(tiles);
 	const bool aligned = (reinterpret_cast<uint64_t>(d_in) & 15) == 0;
-	const size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 4) * sizeof(uint32_t);
+	const size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 8) * sizeof(uint32_t);
 
 	if(fmt == FMT_CTX) return cb->order ? launch_variant<32, FMT_CTX, 1>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0>(aligned, a, smem, st);
 	if(fmt == FMT_WIDE) return launch_variant<16, FMT_WIDE>(aligned, a, smem, st);
