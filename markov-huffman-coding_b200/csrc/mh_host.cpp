@@ -283,12 +283,17 @@ int CodingTable::from_counts(const uint64_t* counts, int order, CodingTable& out
 	out.trees.resize(ntab);
 	for(int t = 0; t < ntab; ++t) {
 		int32_t c32[256];
-		for(int s = 0; s < 256; ++s) {
-			const uint64_t c = counts[size_t(t) * 256 + s];
+		const uint64_t* row = counts + size_t(t) * 256;
+		uint64_t any = 0;
+		uint32_t wrapped = 0;
+		for(int s = 0; s < 256; ++s) {            // branch-free: most rows of a text table are all zero
+			const uint64_t c = row[s];
 			c32[s] = int32_t(uint32_t(c));      // the reference counts in `int` (src/main.cpp:166,174): keep the low 32 bits
-			if(c != 0 && c32[s] == 0) return MH_ERR_COUNT_WRAPPED;   // the reference would silently lose a live symbol
+			any |= c;
+			wrapped |= uint32_t(c != 0) & uint32_t(uint32_t(c) == 0);
 		}
-		out.trees[t].build_from_counts(c32);    // src/markov_huffman.cpp:9-13
+		if(wrapped) return MH_ERR_COUNT_WRAPPED;   // the reference would silently lose a live symbol
+		if(any) out.trees[t].build_from_counts(c32);    // src/markov_huffman.cpp:9-13 (an all-zero row leaves the tree empty)
 	}
 	return MH_OK;
 }
