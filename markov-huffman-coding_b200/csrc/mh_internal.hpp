@@ -46,7 +46,7 @@ constexpr int kDecWriteMaxThreads = 768;              // D4 threads per CTA (mea
 constexpr int kDecMinSubBits = 256;
 constexpr uint32_t kDecMaxSubBitsMarkov = 8192;       // measured best of 2048..16384 on the 1 GiB Markov text
 constexpr uint32_t kDecMaxSubBitsHuffman = 2048;
-constexpr uint64_t kDecTargetSubs = 300000;           // ~2 subsequences per resident thread (148 SMs x 1024)
+constexpr uint64_t kDecTargetSubs = 80000;            // fewest subsequences worth having: measured best of 1024..8192 bits at 30 MB, 100 MB, 300 MB, 1 GiB
 constexpr int kDecPairBytes = 64 * 1024 + 256 + 64 + 64 * 256;   // pair table: <= 64 rows x 256 x u32, then rank[256], live[64], len1[<= 64 x 256]
 constexpr int kDecWarmSubs = 8;                       // overlap subsequences re-decoded by the next chunk
 
