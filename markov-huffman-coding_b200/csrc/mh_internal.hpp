@@ -45,7 +45,7 @@ constexpr int kDecThreads = 1024;                     // subsequences per chunk 
 constexpr int kDecWriteMaxThreads = 768;              // D4 threads per CTA (measured best of 512..960): table + 192 B of rings per thread
 constexpr int kDecMinSubBits = 256;
 constexpr uint32_t kDecMaxSubBitsMarkov = 8192;       // measured best of 2048..16384 on the 1 GiB Markov text
-constexpr uint32_t kDecMaxSubBitsHuffman = 2048;
+constexpr uint32_t kDecMaxSubBitsHuffman = 8192;      // 1 GiB text with -h: D1 1.48 ms at 2048, 1.23 at 4096, 1.05 at 8192
 constexpr uint64_t kDecTargetSubs = 80000;            // fewest subsequences worth having: measured best of 1024..8192 bits at 30 MB, 100 MB, 300 MB, 1 GiB
 constexpr int kDecPairBytes = 64 * 1024 + 256 + 64 + 64 * 256;   // pair table: <= 64 rows x 256 x u32, then rank[256], live[64], len1[<= 64 x 256]
 constexpr int kDecWarmSubs = 8;                       // overlap subsequences re-decoded by the next chunk
