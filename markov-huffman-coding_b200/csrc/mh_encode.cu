@@ -258,7 +258,7 @@ struct Packer32 {
 };
 
 template <int SPT, int FMT, bool ALIGNED, int ORDER = 1>
-__global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A) {
+__global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode_kernel(const EncArgs A) {   // context rows: two CTAs per SM (<= 64 registers)
 	constexpr int NWORDS = SPT / 4;
 	extern __shared__ uint32_t smem[];
 	uint32_t* table = smem;   // FMT_BOX_SMEM: [(R + 1)^2] or [256]
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 		uint32_t e32[(FMT == FMT_BOX_SMEM || FMT == FMT_BOX_GLOBAL) ? SPT : 1];
 		unsigned long long e64[FMT == FMT_WIDE ? SPT : 1];
 		uint32_t q_hi[FMT == FMT_CTX ? SPT / 4 : 1], q_lo[FMT == FMT_CTX ? SPT / 4 : 1], q_len[FMT == FMT_CTX ? SPT / 4 : 1];
-		bool escape = false;   // FMT_CTX: one of this thread's symbols has a codeword longer than 16 bits
+		uint32_t esc_mask = 0;   // FMT_CTX: quads of this thread that hold a codeword longer than 16 bits
 		if(valid) {
 			uint32_t w[NWORDS];
 #pragma unroll
@@ -425,19 +425,32 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 				};
 				if(live == SPT) quads(false);
 				else quads(true);
-				if((ceil >> 27) == 31u) {   // rare: a codeword longer than 16 bits; this thread redoes its symbols from the wide table
-					escape = true;
-					my_bits = 0;
-					uint32_t p = prev;
-#pragma unroll 1
-					for(int i = 0; i < live; ++i) {
-						const uint32_t c = A.in[my + i];
-						const unsigned long long ent = __ldg(A.wide + ((ORDER ? p : 0u) << 8) + c);
-						if(ent == 0) ++dropped;
-						my_bits += uint32_t(ent >> 56);
-						p = c;
+				if((ceil >> 27) == 31u) {   // rare: a codeword longer than 16 bits (length marker 31) somewhere in this thread
+					// Only a quad whose merged length reaches 31 can hold the marker; those quads take their lengths from
+					// the wide table and are packed symbol by symbol below. The other quads keep their merged codewords.
+#pragma unroll
+					for(int q = 0; q < SPT / 4; ++q) {
+						if(q_len[q] >= 31u) {
+							uint32_t p = q ? __byte_perm(w[q ? q - 1 : 0], 0, 0x4443) : prev, sum = 0;
+							bool big = false;
+#pragma unroll
+							for(int i = 0; i < 4; ++i) {
+								if(4 * q + i < live) {
+									const uint32_t c = __byte_perm(w[q], 0, 0x4440 + i);
+									const uint32_t len = uint32_t(__ldg(A.wide + ((ORDER ? p : 0u) << 8) + c) >> 56);
+									big |= len > 16u;
+									sum += len;
+									p = c;
+								}
+							}
+							if(big) {
+								esc_mask |= 1u << q;
+								my_bits += sum - q_len[q];
+							}
+						}
 					}
-				} else if(floor < (1u << 27)) {   // rare: some symbol has no codeword; recount them exactly (context rows again)
+				}
+				if(floor < (1u << 27)) {   // rare: some symbol has no codeword; count them exactly (context rows again)
 					uint32_t r2 = table_sa;
 					if(ORDER) r2 = table_sa + __byte_perm(lds32(null_row + prev * 4), 0, 0x4442) * 1024u;
 #pragma unroll 1
@@ -544,25 +557,21 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 		// ================= phase C: pack tile `tile` into the staging area =================
 		if(valid) {
 			if constexpr(FMT == FMT_CTX) {
-				if(escape) {
-					Packer pw;
-					pw.start(stage_sa, pos);
-					const int live = A.n - my >= uint64_t(SPT) ? SPT : int(A.n - my);
-					uint32_t p = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
-#pragma unroll 1
-					for(int i = 0; i < live; ++i) {
-						const uint32_t c = A.in[my + i];
-						const unsigned long long ent = __ldg(A.wide + ((ORDER ? p : 0u) << 8) + c);
-						pw.put(ent & 0x00ffffffffffffffull, uint32_t(ent >> 56));
-						p = c;
-					}
-					pw.finish();
-				} else {
 				Packer32 pk;
 				pk.start(stage_sa, pos);
 #pragma unroll
 				for(int q = 0; q < SPT / 4; ++q) {
-					if(q_len[q] <= 32) {
+					if(esc_mask & (1u << q)) {   // rare: the quad holds a codeword of 17..28 bits: one unit per symbol, from the wide table
+						const uint64_t at = my + 4 * q;
+						uint32_t p = at == 0 ? A.prev0 : uint32_t(A.in[at - 1]);
+#pragma unroll 1
+						for(int i = 0; i < 4 && at + i < A.n; ++i) {
+							const uint32_t c = A.in[at + i];
+							const unsigned long long ent = __ldg(A.wide + ((ORDER ? p : 0u) << 8) + c);
+							pk.put(uint32_t(ent), uint32_t(ent >> 56));
+							p = c;
+						}
+					} else if(q_len[q] <= 32) {
 						pk.put(q_lo[q], q_len[q]);
 					} else {   // a quad of long codewords: the top q_len - 32 bits, then the low word
 						pk.put(q_hi[q], q_len[q] - 32);
@@ -570,7 +579,6 @@ __global__ void __launch_bounds__(kEncCtaThreads) encode_kernel(const EncArgs A)
 					}
 				}
 				pk.finish();
-				}
 			}
 			Packer pk;
 			pk.start(stage_sa, pos);
