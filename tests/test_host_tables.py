@@ -210,3 +210,37 @@ def test_pair_table_absent_for_many_contexts():
     assert p.pair_lut() is None      # 188 live contexts: the decoder keeps the 8-bit LUT
     q = mh.CodingProvider.from_counts_array(np.ascontiguousarray(_counts(data, False)), 0)
     assert q.pair_lut() is not None  # one tree: always available
+
+
+def test_pair_table_entry_kinds_follow_the_8bit_lut():
+    """With long codewords (counts spread over six orders of magnitude) the pair table runs out of prefix rows: every
+    context-row entry must then be exactly one of leaf entry (LUT leaf), prefix entry or deep flag (LUT internal node at
+    depth 8), null flag (no LUT entry), and the prefix rows must have gone to the heaviest deep nodes."""
+    data = golden_input("input_ipsum.txt")
+    counts = _counts(data, True).astype(np.float64)
+    live = counts > 0
+    counts[live] = np.maximum(1, (counts[live] ** 2.2)).astype(np.float64)      # stretch the distribution: deep trees
+    counts = counts.astype(np.uint64)
+    p = mh.CodingProvider.from_counts_array(np.ascontiguousarray(counts), 1)
+    assert p.max_code_bits() > 12
+    table, rank, live_ctx, len1, rows, ctx_rows = p.pair_lut()
+    t = table.reshape(rows, 256)
+    flagged_weight, prefix_weight = [], []
+    n_prefix = 0
+    for prev in range(256):
+        r = int(rank[prev])
+        if r >= ctx_rows:
+            continue
+        for w in range(256):
+            kind, value, depth = p.decoding_lookup(prev, w)
+            e = int(t[r, w])
+            if kind == 0:
+                assert e & 0x20
+            elif kind == 1:
+                assert not (e & 0x30) and ((e >> 6) & 15) in (1, 2) and ((e >> 16) & 255) == value and int(len1[r * 256 + w]) == depth
+            else:
+                assert (e & 0x10) or (((e >> 6) & 15) == 0 and (e & 63) == 8 and ctx_rows < ((e >> 10) & 63) < rows)
+                if not (e & 0x10):
+                    n_prefix += 1
+    assert n_prefix == rows - ctx_rows - 1 > 0      # every prefix row is reached from exactly one deep node
+    assert rows <= 64
