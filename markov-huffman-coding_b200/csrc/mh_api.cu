@@ -432,6 +432,7 @@ struct mh_session {
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	uint64_t max_input = 0;      // capacity of d_raw (grows on demand when extracting)
+	uint64_t enc_chunk = 0;      // bytes one histogram / encode launch may take (what the workspace was sized for)
 	uint64_t payload_cap = 0;
 	uint64_t pending_out = 0;    // decoded bytes waiting in d_raw for mh_session_fetch
 	uint8_t* d_raw = nullptr;       // uncompressed side
@@ -464,6 +465,7 @@ int mh_session_create_sized(int device, uint64_t max_input_bytes, uint64_t max_s
 	if(!s) return MH_ERR_INVALID_ARG;
 	s->device = device;
 	s->max_input = max_input_bytes;
+	s->enc_chunk = max_input_bytes;
 	s->payload_cap = ((max_stream_bytes + 64 + 15) / 16) * 16;
 	auto fail = [&](int rc) { mh_session_destroy(s); return rc; };
 #define S_CUDA(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(cuda_fail(e_, #call)); } while(0)
@@ -498,11 +500,18 @@ void mh_session_destroy(mh_session* s) {
 	delete s;
 }
 
+static int session_histogram_chunked(mh_session* s, const uint8_t* in, uint64_t n, int order, std::vector<uint64_t>& total);
+
 int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order, uint64_t* counts) {
-	if(!s || !counts || (!in && n)) return MH_ERR_INVALID_ARG;
-	if(n > s->max_input) return MH_ERR_CAPACITY;
+	if(!s || !counts || (!in && n) || (order != 0 && order != 1)) return MH_ERR_INVALID_ARG;
 	s->pending_out = 0;
 	MH_CUDA(cudaSetDevice(s->device));
+	if(n > s->enc_chunk || n > s->max_input) {   // larger than the device buffer: the counts add up over chunks
+		std::vector<uint64_t> total;
+		int rc = session_histogram_chunked(s, in, n, order, total);
+		if(rc == MH_OK) memcpy(counts, total.data(), total.size() * sizeof(uint64_t));
+		return rc;
+	}
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
 	if(rc != MH_OK) return rc;
@@ -539,12 +548,84 @@ static int session_encode(mh_session* s, const mh_table* t, uint64_t n, uint8_t*
 	return MH_OK;
 }
 
+// ---- inputs larger than the session's device buffer (streaming with carried state) -----------------------
+// The input goes through the device buffer in chunks. The histogram adds up over the chunks, each seeded with the
+// byte before it; then every chunk is encoded at its global bit offset (bit_base) and its payload lands in the host
+// stream at the byte it shares with its neighbour, OR-merged — the same arithmetic that shards one stream over
+// several GPUs, applied in sequence on one.
+static int session_histogram_chunked(mh_session* s, const uint8_t* in, uint64_t n, int order, std::vector<uint64_t>& total) {
+	const size_t bins = order ? 65536 : 256;
+	total.assign(bins, 0);
+	if(s->enc_chunk == 0) return MH_ERR_CAPACITY;
+	for(uint64_t off = 0; off < n; off += s->enc_chunk) {
+		const uint64_t len = n - off < s->enc_chunk ? n - off : s->enc_chunk;
+		MH_CUDA(cudaMemcpyAsync(s->d_raw, in + off, len, cudaMemcpyHostToDevice, s->stream));
+		int rc = launch_histogram(s->d_raw, len, off ? in[off - 1] : uint8_t(MH_PREV0), order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
+		if(rc != MH_OK) return rc;
+		MH_CUDA(cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+		MH_CUDA(cudaStreamSynchronize(s->stream));
+		for(size_t i = 0; i < bins; ++i) total[i] += s->h_counts[i];
+	}
+	return MH_OK;
+}
+
+static int session_encode_chunked(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_capacity,
+                                  uint64_t* out_len, uint64_t* dropped) {
+	if(out_capacity < 1 || s->enc_chunk == 0) return MH_ERR_CAPACITY;
+	int rc = upload_codebook(t, &s->book, s->stream);
+	if(rc != MH_OK) return rc;
+	uint64_t bit_base = 0, drop = 0;
+	for(uint64_t off = 0; off < n; off += s->enc_chunk) {
+		const uint64_t len = n - off < s->enc_chunk ? n - off : s->enc_chunk;
+		MH_CUDA(cudaMemcpyAsync(s->d_raw, in + off, len, cudaMemcpyHostToDevice, s->stream));
+		rc = launch_encode(s->d_raw, len, off ? in[off - 1] : uint8_t(MH_PREV0), &s->book, bit_base, s->d_payload, s->payload_cap,
+		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
+		if(rc != MH_OK) return rc;
+		MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+		MH_CUDA(cudaStreamSynchronize(s->stream));
+		if(s->h_result[2]) return MH_ERR_CAPACITY;
+		const uint64_t bits = s->h_result[0];
+		drop += s->h_result[1];
+		const uint32_t phase = uint32_t(bit_base & 7);
+		const uint64_t nbytes = (phase + bits + 7) / 8, first = 1 + (bit_base >> 3);
+		if(first + nbytes > out_capacity) return MH_ERR_CAPACITY;
+		if(nbytes) {
+			uint8_t seam = 0;
+			if(phase) {   // the chunk's first byte is the previous chunk's last: keep that one's bits, add ours
+				MH_CUDA(cudaMemcpyAsync(&seam, s->d_payload, 1, cudaMemcpyDeviceToHost, s->stream));
+				if(nbytes > 1) MH_CUDA(cudaMemcpyAsync(out + first + 1, s->d_payload + 1, nbytes - 1, cudaMemcpyDeviceToHost, s->stream));
+			} else {
+				MH_CUDA(cudaMemcpyAsync(out + first, s->d_payload, nbytes, cudaMemcpyDeviceToHost, s->stream));
+			}
+			MH_CUDA(cudaStreamSynchronize(s->stream));
+			if(phase) out[first] = uint8_t(out[first] | (seam & (0xFFu >> phase)));
+		}
+		bit_base += bits;
+	}
+	if(dropped) *dropped = drop;
+	*out_len = 1 + (bit_base + 7) / 8;
+	// header: 0 0 1 1 E R R R, E = inverse of the coder type, RRR = unused bits of the last byte (src/coding.cpp:88)
+	out[0] = uint8_t(0x30 | ((~t->impl.order & 1) << 3) | ((8 - bit_base % 8) % 8));
+	return MH_OK;
+}
+
 int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order, uint8_t* out, uint64_t out_capacity,
                         uint64_t* out_len, mh_table** table_out) {
 	if(!s || !out || !out_len || (!in && n) || (order != 0 && order != 1)) return MH_ERR_INVALID_ARG;
-	if(n > s->max_input) return MH_ERR_CAPACITY;
 	s->pending_out = 0;
 	MH_CUDA(cudaSetDevice(s->device));
+	if(n > s->enc_chunk || n > s->max_input) {   // larger than the device buffer: stream it through in chunks
+		std::vector<uint64_t> total;
+		int rc = session_histogram_chunked(s, in, n, order, total);
+		if(rc != MH_OK) return rc;
+		mh_table* t = nullptr;
+		rc = mh_table_from_counts(total.data(), order, &t);
+		if(rc != MH_OK) return rc;
+		rc = session_encode_chunked(s, t, in, n, out, out_capacity, out_len, nullptr);
+		if(rc == MH_OK && table_out) *table_out = t;
+		else mh_table_destroy(t);
+		return rc;
+	}
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
 	if(rc != MH_OK) return rc;
@@ -563,9 +644,9 @@ int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
 int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n, uint8_t* out,
                                    uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped) {
 	if(!s || !t || !out || !out_len || (!in && n)) return MH_ERR_INVALID_ARG;
-	if(n > s->max_input) return MH_ERR_CAPACITY;
 	s->pending_out = 0;
 	MH_CUDA(cudaSetDevice(s->device));
+	if(n > s->enc_chunk || n > s->max_input) return session_encode_chunked(s, t, in, n, out, out_capacity, out_len, dropped);
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	return session_encode(s, t, n, out, out_capacity, out_len, dropped);
 }

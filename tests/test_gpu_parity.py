@@ -198,3 +198,25 @@ def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, pair, monkeypat
                 assert s.decompress(provider, stream) == data
     finally:
         s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [1, 0], ids=["markov", "huffman"])
+@pytest.mark.parametrize("kind", ["text", "fib"])
+def test_session_streams_inputs_larger_than_its_buffer(ipsum_counts, order, kind):
+    """an input that does not fit the session's device buffer goes through it in chunks — histogram counts add
+    up with the byte before each chunk as its context, every chunk is encoded at its global bit offset and OR-merged at
+    the byte it shares with its neighbour. Same bytes as one pass."""
+    n = 1_000_003
+    data = o.synth_markov(ipsum_counts, 11, 4096, 0, n) if kind == "text" else o.synth_fibonacci(40, 48, 99, 0, n)
+    want_stream, want_table = o.compress_from_input(data, bool(order))
+    s = mh.Session(100_003)          # ten ragged chunks, seams in the middle of bytes
+    try:
+        assert np.array_equal(s.histogram(data, order), o.histogram(data, bool(order)).astype(np.int64).astype(np.uint64))
+        stream, provider = s.compress(data, order)
+        assert stream == want_stream
+        assert provider.write_coding_tree() == want_table
+        again, dropped = s.compress_with_table(provider, data)
+        assert again == want_stream and dropped == 0
+    finally:
+        s.close()
