@@ -45,6 +45,9 @@ typedef void* mh_stream_t;         /* a cudaStream_t, or NULL for the default st
 const char* mh_status_string(int status);
 const char* mh_last_error(void);   /* thread-local detail of the last MH_ERR_CUDA */
 int mh_device_count(void);
+/* Free and total memory of a device in bytes (cudaMemGetInfo): a host driver sizes its session from it and lets the
+ * session stream larger files through in chunks. */
+int mh_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes);
 int mh_version(void);
 
 /* ---------------------------------------------------------------------------------------------------------

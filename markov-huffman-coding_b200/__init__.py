@@ -59,6 +59,7 @@ _SIGNATURES = {
     "mh_status_string": (ctypes.c_char_p, [_i]),
     "mh_last_error": (ctypes.c_char_p, []),
     "mh_device_count": (_i, []),
+    "mh_device_memory": (_i, [_i, _pu64, _pu64]),
     "mh_version": (_i, []),
     "mh_table_from_counts": (_i, [_vp, _i, _pp]),
     "mh_table_from_bytes": (_i, [_vp, _sz, _pp]),
@@ -311,8 +312,15 @@ class Session:
         rc = _lib.mh_session_decompress(self._h, provider._h, addr, n, None, 0, ctypes.byref(out_len))   # decode on the device, learn the size
         if rc not in (MH_OK, MH_ERR_CORRUPT_STREAM):
             raise MhError(rc, "mh_session_decompress")
-        buf = np.empty(max(1, out_len.value), dtype=np.uint8)
+        need = out_len.value
+        buf = np.empty(max(1, need), dtype=np.uint8)
         _check(_lib.mh_session_fetch(self._h, buf.ctypes.data, buf.size, ctypes.byref(out_len)), "mh_session_fetch")
+        if out_len.value != need:
+            # a stream larger than the session's device buffer was decoded in chunks: the first call only counted,
+            # nothing stays resident to fetch — decode again, chunk by chunk, into the host buffer
+            rc = _lib.mh_session_decompress(self._h, provider._h, addr, n, buf.ctypes.data, buf.size, ctypes.byref(out_len))
+            if rc not in (MH_OK, MH_ERR_CORRUPT_STREAM):
+                raise MhError(rc, "mh_session_decompress")
         if rc != MH_OK:
             raise MhError(rc, "mh_session_decompress")
         return buf[: out_len.value].tobytes()

@@ -173,8 +173,18 @@ int main(int argc, char* argv[]) {
 
 	// Device buffers. Compressing: the input bounds both sides. Extracting: the stream bounds the compressed side; the
 	// decoded size is not stored in the stream, so the session grows its uncompressed-side buffer after the count pass.
-	int rc = extract ? mh_session_create_sized(0, in_bytes.size() * 3 + 4096, in_bytes.size() + 64, &session)
-	                 : mh_session_create(0, in_bytes.size() + 64, &session);
+	// A file that does not fit the GPU goes through the session in chunks (histogram counts add up, every chunk is coded
+	// at its global bit offset / decoded from the exact state its predecessor ended in), so the buffers are capped at a
+	// fifth of the free device memory; MH_CLI_MAX_BYTES lowers the cap (tests).
+	uint64_t cap = ~uint64_t(0), free_b = 0, total_b = 0;
+	if(mh_device_memory(0, &free_b, &total_b) == MH_OK && free_b / 5 > (1u << 20)) cap = free_b / 5;
+	if(const char* env = getenv("MH_CLI_MAX_BYTES")) {
+		const unsigned long long v = strtoull(env, nullptr, 10);
+		if(v >= 4096) cap = v;
+	}
+	auto capped = [&](uint64_t want) { return want < cap ? want : cap; };
+	int rc = extract ? mh_session_create_sized(0, capped(in_bytes.size() * 3 + 4096), capped(in_bytes.size() + 64), &session)
+	                 : mh_session_create(0, capped(in_bytes.size() + 64), &session);
 	if(rc != MH_OK) die_status("creating the GPU session", rc);
 
 	bool built_here = false;
@@ -222,9 +232,14 @@ int main(int argc, char* argv[]) {
 		uint64_t n_out = 0;
 		rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), nullptr, 0, &n_out);   // decode, learn the size
 		if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
+		const uint64_t need = n_out;
 		result.resize(n_out ? n_out : 1);
 		rc = mh_session_fetch(session, result.data(), result.size(), &n_out);
 		if(rc != MH_OK) die_status("extracting", rc);
+		if(n_out != need) {   // a stream larger than the device buffer: the first pass only counted; decode again into the host buffer
+			rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), result.data(), result.size(), &n_out);
+			if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
+		}
 		result.resize(n_out);
 		if(n_out && fwrite(result.data(), 1, n_out, output_fd) != n_out) {
 			eprintf("Error occurred while writing file.\n");

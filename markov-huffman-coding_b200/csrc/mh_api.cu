@@ -91,6 +91,19 @@ const char* mh_status_string(int status) {
 
 const char* mh_last_error(void) { return t_last_error.c_str(); }
 
+int mh_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes) {
+	if(!free_bytes || !total_bytes) return MH_ERR_INVALID_ARG;
+	int ndev = 0;
+	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); t_last_error = "no usable CUDA device"; return MH_ERR_NO_DEVICE; }
+	if(device < 0 || device >= ndev) return MH_ERR_INVALID_ARG;
+	MH_CUDA(cudaSetDevice(device));
+	size_t f = 0, t = 0;
+	MH_CUDA(cudaMemGetInfo(&f, &t));
+	*free_bytes = f;
+	*total_bytes = t;
+	return MH_OK;
+}
+
 int mh_device_count(void) {
 	int n = 0;
 	if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -651,6 +664,69 @@ int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8
 	return session_encode(s, t, n, out, out_capacity, out_len, dropped);
 }
 
+// A payload larger than the session's device buffer is decoded in chunks of bit ranges: every chunk starts from the
+// exact state (bit position, previous symbol) its predecessor ended in — the decoder's shard interface with a known
+// start — and keeps 64 bytes of the stream behind its range for the codeword that straddles the end. The decoded
+// bytes leave for the host chunk by chunk; without `out` the pass only counts (nothing stays resident to fetch).
+static int session_decompress_chunked(mh_session* s, const mh_table* t, const uint8_t* payload, uint64_t payload_bytes, uint64_t n_bits,
+                                      uint8_t* out, uint64_t out_capacity, uint64_t* out_len) {
+	const uint64_t cap = s->payload_cap & ~uint64_t(3);
+	if(cap < 4096) return MH_ERR_CAPACITY;
+	int rc = upload_dectable(t, &s->dec, s->stream);
+	if(rc != MH_OK) return rc;
+	uint64_t p = 0, produced = 0;
+	uint8_t ctx = MH_PREV0;
+	int corrupt = 0;
+	bool fits = true;
+	while(p < n_bits) {
+		const uint64_t b0 = (p >> 3) & ~uint64_t(3);
+		const uint32_t start_bit = uint32_t(p - 8 * b0);
+		const uint64_t load = payload_bytes - b0 < cap ? payload_bytes - b0 : cap;
+		const bool last = b0 + load >= payload_bytes;
+		const uint64_t nb = last ? n_bits - p : (load - 64) * 8 - start_bit;
+		MH_CUDA(cudaMemcpyAsync(s->d_payload, payload + b0, load, cudaMemcpyHostToDevice, s->stream));
+		int iters = 2;
+		for(;;) {
+			rc = launch_decode_shard(s->d_payload, start_bit, nb, load, 1, ctx, 0, last ? 1 : 0, &s->dec, s->d_raw, s->max_input,
+			                         reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
+			if(rc != MH_OK) return rc;
+			MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+			MH_CUDA(cudaStreamSynchronize(s->stream));
+			const int64_t dev_status = int64_t(s->h_result[1]);
+			if(dev_status == MH_ERR_NOT_CONVERGED && iters < (1 << 20)) { iters *= 4; continue; }
+			if(dev_status == MH_ERR_CAPACITY) {   // this chunk decodes to more than the uncompressed-side buffer holds: grow it
+				const uint64_t need = s->h_result[0];
+				cudaFree(s->d_raw);
+				s->d_raw = nullptr;
+				s->max_input = 0;
+				MH_CUDA(cudaMalloc(&s->d_raw, need + 64));
+				s->max_input = need;
+				continue;
+			}
+			if(dev_status != 0) return int(dev_status);
+			break;
+		}
+		const uint64_t count = s->h_result[0];
+		if(int64_t(s->h_result[2]) != 0) corrupt = int(int64_t(s->h_result[2]));
+		if(out && fits) {
+			if(produced + count > out_capacity) fits = false;
+			else if(count) {
+				MH_CUDA(cudaMemcpyAsync(out + produced, s->d_raw, count, cudaMemcpyDeviceToHost, s->stream));
+				MH_CUDA(cudaStreamSynchronize(s->stream));
+			}
+		}
+		produced += count;
+		if(last) break;
+		const uint32_t end = uint32_t(s->h_result[3] & 0xffffffffull);   // where the chunk's last codeword ended, and that symbol
+		p += nb + (end >> 8);
+		ctx = uint8_t(end & 255u);
+	}
+	*out_len = produced;
+	s->pending_out = 0;
+	if(out && !fits) return MH_ERR_CAPACITY;
+	return corrupt;
+}
+
 int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* stream, uint64_t stream_len, uint8_t* out,
                           uint64_t out_capacity, uint64_t* out_len) {
 	if(!s || !t || !stream || !out_len) return MH_ERR_INVALID_ARG;
@@ -662,8 +738,11 @@ int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* strea
 	const uint64_t remainder = header & 7;
 	// src/coding.cpp:115 in 64-bit; a negative length makes the reference's loop (:124) decode nothing
 	const uint64_t n_bits = payload_bytes * 8 < remainder ? 0 : payload_bytes * 8 - remainder;
-	if(payload_bytes > s->payload_cap) return MH_ERR_CAPACITY;
 	MH_CUDA(cudaSetDevice(s->device));
+	if(payload_bytes > s->payload_cap) {   // larger than the device buffer: decode it in chunks
+		s->pending_out = 0;
+		return session_decompress_chunked(s, t, stream + 1, payload_bytes, n_bits, out, out_capacity, out_len);
+	}
 	int rc = upload_dectable(t, &s->dec, s->stream);
 	if(rc != MH_OK) return rc;
 	if(payload_bytes) MH_CUDA(cudaMemcpyAsync(s->d_payload, stream + 1, payload_bytes, cudaMemcpyHostToDevice, s->stream));

@@ -112,3 +112,25 @@ def test_cli_extract_grows_its_output_buffer(tmp_path):
     assert os.path.getsize(c) == 1 + (3_000_001 + 7) // 8
     assert run([c, "-o", d, "-x", "-e", t]).returncode == 0
     assert open(d, "rb").read() == open(src, "rb").read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("simple", [False, True], ids=["markov", "huffman"])
+def test_cli_streams_files_larger_than_its_device_buffers(tmp_path, simple, monkeypatch):
+    """with the device buffers capped far below the file size (MH_CLI_MAX_BYTES; by default a fifth of the free
+    device memory) the CLI streams the file through in chunks and still writes the reference's bytes."""
+    if not os.path.exists(o.REF_STOCK):
+        pytest.skip("oracle/_ref not present")
+    src = os.path.join(INPUTS, "input_wiki_cpp.html")      # 343 KB
+    mode = ["-h"] if simple else []
+    ref_c, ref_e = str(tmp_path / "ref.c"), str(tmp_path / "ref.e")
+    assert run([src, "-o", ref_c] + mode + ["-d", ref_e], exe=o.REF_STOCK).returncode == 0
+    monkeypatch.setenv("MH_CLI_MAX_BYTES", "40000")
+    out_c, out_e, out_d = str(tmp_path / "mine.c"), str(tmp_path / "mine.e"), str(tmp_path / "mine.d")
+    p = subprocess.run([CLI, src, "-o", out_c] + mode + ["-d", out_e], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr
+    assert open(out_c, "rb").read() == open(ref_c, "rb").read()
+    assert open(out_e, "rb").read() == open(ref_e, "rb").read()
+    p = subprocess.run([CLI, out_c, "-o", out_d, "-xh" if simple else "-x", "-e", out_e], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr
+    assert open(out_d, "rb").read() == open(src, "rb").read()

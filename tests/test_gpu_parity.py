@@ -206,7 +206,7 @@ def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, pair, monkeypat
 def test_session_streams_inputs_larger_than_its_buffer(ipsum_counts, order, kind):
     """an input that does not fit the session's device buffer goes through it in chunks — histogram counts add
     up with the byte before each chunk as its context, every chunk is encoded at its global bit offset and OR-merged at
-    the byte it shares with its neighbour. Same bytes as one pass."""
+    the byte it shares with its neighbour. Same bytes as one pass. Extraction of a stream larger than the buffer likewise."""
     n = 1_000_003
     data = o.synth_markov(ipsum_counts, 11, 4096, 0, n) if kind == "text" else o.synth_fibonacci(40, 48, 99, 0, n)
     want_stream, want_table = o.compress_from_input(data, bool(order))
@@ -218,5 +218,8 @@ def test_session_streams_inputs_larger_than_its_buffer(ipsum_counts, order, kind
         assert provider.write_coding_tree() == want_table
         again, dropped = s.compress_with_table(provider, data)
         assert again == want_stream and dropped == 0
+        # ... and back: the stream is larger than the compressed-side buffer too, so it is decoded in bit-range chunks,
+        # each from the exact state (bit position, previous symbol) its predecessor ended in
+        assert s.decompress(provider, stream) == data
     finally:
         s.close()
