@@ -29,7 +29,13 @@ def shard_bits(all_counts, code_lengths, total=None):
     (`total` is accepted for symmetry with global_counts; the code lengths already say which pairs are live.)"""
     a = np.asarray(all_counts, dtype=np.uint64)
     lens = np.asarray(code_lengths)
-    live = np.flatnonzero(lens)             # fastest on the uint8 lengths the library hands out
+    if lens.size == 65536:                  # order 1: look for the live pairs only in the rows of live contexts (a few
+        l2 = lens.reshape(256, 256)         # dozen for text) instead of scanning 65536 entries
+        rows = np.flatnonzero(l2.any(axis=1))
+        sub = l2[rows]
+        r, c = np.nonzero(sub)
+        return np.take(a, rows[r] * 256 + c, axis=1) @ sub[r, c].astype(np.uint64)
+    live = np.flatnonzero(lens)
     return np.take(a, live, axis=1) @ lens[live].astype(np.uint64)
 
 
