@@ -305,6 +305,16 @@ class Session:
                "mh_session_compress_with_table")
         return buf[: out_len.value].tobytes(), dropped.value
 
+    def decompress_into(self, provider, stream, capacity):
+        """i_coding_provider::decompress straight into a host buffer of `capacity` bytes (one call; large streams are
+        decoded in chunks with the copies of neighbouring chunks overlapping the kernels). Returns the bytes."""
+        import numpy as np
+        keep, addr, n = _as_buffer(stream)
+        buf = np.empty(max(1, int(capacity)), dtype=np.uint8)
+        out_len = ctypes.c_uint64(0)
+        _check(_lib.mh_session_decompress(self._h, provider._h, addr, n, buf.ctypes.data, buf.size, ctypes.byref(out_len)), "mh_session_decompress")
+        return buf[: out_len.value].tobytes()
+
     def decompress(self, provider, stream):
         import numpy as np
         keep, addr, n = _as_buffer(stream)

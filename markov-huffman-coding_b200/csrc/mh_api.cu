@@ -457,6 +457,9 @@ struct mh_session {
 	mh_workspace* ws = nullptr;
 	mh_codebook book;
 	mh_dectable dec;
+	// pipelined extract: copy streams and their events (created on first use)
+	cudaStream_t h2d = nullptr, d2h = nullptr;
+	cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 extern "C" {
@@ -510,6 +513,12 @@ void mh_session_destroy(mh_session* s) {
 	release_dec(&s->dec);
 	mh_workspace_destroy(s->ws);
 	if(s->stream) cudaStreamDestroy(s->stream);
+	if(s->h2d) cudaStreamDestroy(s->h2d);
+	if(s->d2h) cudaStreamDestroy(s->d2h);
+	for(int i = 0; i < 2; ++i) {
+		if(s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+		if(s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
+	}
 	delete s;
 }
 
@@ -727,6 +736,95 @@ static int session_decompress_chunked(mh_session* s, const mh_table* t, const ui
 	return corrupt;
 }
 
+// Extract straight into a host buffer, pipelined: the payload is cut into bit-range chunks (as above); while chunk k is
+// decoded, chunk k + 1 travels to the device and the bytes of chunk k - 1 travel back — PCIe is full duplex, so the
+// 2.4x larger D2H side hides both the H2D copies and the kernels. Two halves of the payload buffer and of the
+// uncompressed-side buffer alternate. Returns MH_ERR_WORKSPACE when the buffers are too small for it (the caller then
+// takes the sequential path); needs pinned host memory to actually overlap.
+static uint64_t env_bytes(const char* name, uint64_t fallback) {
+	const char* e = getenv(name);
+	if(!e) return fallback;
+	const unsigned long long v = strtoull(e, nullptr, 10);
+	return v ? uint64_t(v) : fallback;
+}
+
+static int session_decompress_pipelined(mh_session* s, const mh_table* t, const uint8_t* payload, uint64_t payload_bytes, uint64_t n_bits,
+                                        uint8_t* out, uint64_t out_capacity, uint64_t* out_len) {
+	const uint64_t pay_half = (s->payload_cap / 2) & ~uint64_t(15), out_half = (s->max_input / 2) & ~uint64_t(63);
+	uint64_t chunk = env_bytes("MH_PIPE_CHUNK_BYTES", 16ull << 20) & ~uint64_t(3);   // measured best of 16, 32, 64, 128 MiB
+	if(chunk > pay_half) chunk = pay_half & ~uint64_t(3);
+	if(chunk < 4096 || out_half < 4096) return MH_ERR_WORKSPACE;
+	if(!s->h2d) {
+		MH_CUDA(cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking));
+		MH_CUDA(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking));
+		for(int i = 0; i < 2; ++i) {
+			MH_CUDA(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+			MH_CUDA(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+		}
+	}
+	int rc = upload_dectable(t, &s->dec, s->stream);
+	if(rc != MH_OK) return rc;
+	auto geometry = [&](uint64_t base_bit, uint64_t& b0, uint64_t& load, bool& last) {   // chunk that starts (nominally) at base_bit
+		b0 = (base_bit >> 3) & ~uint64_t(3);
+		load = payload_bytes - b0 < chunk ? payload_bytes - b0 : chunk;
+		last = b0 + load >= payload_bytes;
+	};
+	auto drain = [&]() { cudaStreamSynchronize(s->h2d); cudaStreamSynchronize(s->d2h); cudaStreamSynchronize(s->stream); };
+	uint64_t base = 0, rel = 0, produced = 0, b0, load;
+	uint8_t ctx = MH_PREV0;
+	bool last;
+	int corrupt = 0;
+	geometry(0, b0, load, last);
+	MH_CUDA(cudaMemcpyAsync(s->d_payload, payload + b0, load, cudaMemcpyHostToDevice, s->h2d));
+	MH_CUDA(cudaEventRecord(s->ev_in[0], s->h2d));
+	for(uint32_t k = 0;; ++k) {
+		const uint32_t cur = k & 1;
+		geometry(base, b0, load, last);
+		const uint64_t p = base + rel;                      // exact first bit: where the previous chunk's last codeword ended
+		const uint64_t first = p - 8 * b0;                  // ... relative to the bytes in the buffer
+		const uint64_t skip = (first >> 5) * 4;             // whole words before it
+		const uint64_t nb = last ? n_bits - p : (load - 64) * 8 - first;
+		const uint64_t next_base = 8 * (b0 + load - 64);    // the range ends 64 bytes before the loaded bytes do
+		if(!last) {                                         // the next chunk's bytes do not depend on this chunk's result
+			uint64_t nb0, nload;
+			bool nlast;
+			geometry(next_base, nb0, nload, nlast);
+			MH_CUDA(cudaMemcpyAsync(s->d_payload + (cur ^ 1) * pay_half, payload + nb0, nload, cudaMemcpyHostToDevice, s->h2d));
+			MH_CUDA(cudaEventRecord(s->ev_in[cur ^ 1], s->h2d));
+		}
+		MH_CUDA(cudaStreamWaitEvent(s->stream, s->ev_in[cur], 0));
+		if(k >= 2) MH_CUDA(cudaStreamWaitEvent(s->stream, s->ev_out[cur], 0));   // the bytes of chunk k - 2 have left this half
+		int iters = 2;
+		for(;;) {
+			rc = launch_decode_shard(s->d_payload + cur * pay_half + skip, uint32_t(first & 31), nb, load - skip, 1, ctx, 0, last ? 1 : 0, &s->dec,
+			                         s->d_raw + cur * out_half, out_half, reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
+			if(rc != MH_OK) { drain(); return rc; }
+			MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+			MH_CUDA(cudaStreamSynchronize(s->stream));
+			const int64_t dev_status = int64_t(s->h_result[1]);
+			if(dev_status == MH_ERR_NOT_CONVERGED && iters < (1 << 20)) { iters *= 4; continue; }
+			if(dev_status == MH_ERR_CAPACITY) { drain(); return MH_ERR_WORKSPACE; }   // a chunk outgrew its half: sequential path
+			if(dev_status != 0) { drain(); return int(dev_status); }
+			break;
+		}
+		const uint64_t count = s->h_result[0];
+		if(int64_t(s->h_result[2]) != 0) corrupt = int(int64_t(s->h_result[2]));
+		if(produced + count > out_capacity) { drain(); *out_len = produced + count; return MH_ERR_CAPACITY; }
+		if(count) MH_CUDA(cudaMemcpyAsync(out + produced, s->d_raw + cur * out_half, count, cudaMemcpyDeviceToHost, s->d2h));
+		MH_CUDA(cudaEventRecord(s->ev_out[cur], s->d2h));
+		produced += count;
+		if(last) break;
+		const uint32_t end = uint32_t(s->h_result[3] & 0xffffffffull);
+		rel = end >> 8;
+		ctx = uint8_t(end & 255u);
+		base = next_base;
+	}
+	drain();
+	*out_len = produced;
+	s->pending_out = 0;
+	return corrupt;
+}
+
 int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* stream, uint64_t stream_len, uint8_t* out,
                           uint64_t out_capacity, uint64_t* out_len) {
 	if(!s || !t || !stream || !out_len) return MH_ERR_INVALID_ARG;
@@ -739,6 +837,11 @@ int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* strea
 	// src/coding.cpp:115 in 64-bit; a negative length makes the reference's loop (:124) decode nothing
 	const uint64_t n_bits = payload_bytes * 8 < remainder ? 0 : payload_bytes * 8 - remainder;
 	MH_CUDA(cudaSetDevice(s->device));
+	if(out && payload_bytes >= env_bytes("MH_PIPE_MIN_BYTES", 32ull << 20)) {   // large and wanted on the host: overlap the copies
+		s->pending_out = 0;
+		const int prc = session_decompress_pipelined(s, t, stream + 1, payload_bytes, n_bits, out, out_capacity, out_len);
+		if(prc != MH_ERR_WORKSPACE) return prc;
+	}
 	if(payload_bytes > s->payload_cap) {   // larger than the device buffer: decode it in chunks
 		s->pending_out = 0;
 		return session_decompress_chunked(s, t, stream + 1, payload_bytes, n_bits, out, out_capacity, out_len);

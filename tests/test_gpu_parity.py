@@ -223,3 +223,23 @@ def test_session_streams_inputs_larger_than_its_buffer(ipsum_counts, order, kind
         assert s.decompress(provider, stream) == data
     finally:
         s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", ["4096", "20000", "65536", "1000000"])
+def test_pipelined_extract_into_a_host_buffer(ipsum_counts, chunk, monkeypatch):
+    """Extraction straight into a host buffer runs as a pipeline of bit-range chunks (H2D of chunk k + 1, decode of k and
+    D2H of k - 1 overlap): the bytes do not depend on where the chunks are cut."""
+    monkeypatch.setenv("MH_PIPE_MIN_BYTES", "1")
+    monkeypatch.setenv("MH_PIPE_CHUNK_BYTES", chunk)
+    s = mh.Session(3 << 20)
+    try:
+        for data in (o.synth_markov(ipsum_counts, 21, 4096, 0, (1 << 20) + 4321), o.synth_fibonacci(40, 48, 7, 0, 600_001)):
+            for order in (1, 0):
+                stream, provider = s.compress(data, order)
+                assert s.decompress_into(provider, stream, len(data) + 5) == data
+                with pytest.raises(mh.MhError) as e:
+                    s.decompress_into(provider, stream, len(data) - 1)
+                assert e.value.status == mh.MH_ERR_CAPACITY
+    finally:
+        s.close()
