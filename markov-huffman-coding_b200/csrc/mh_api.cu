@@ -762,8 +762,6 @@ static int session_decompress_pipelined(mh_session* s, const mh_table* t, const 
 			MH_CUDA(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
 		}
 	}
-	int rc = upload_dectable(t, &s->dec, s->stream);
-	if(rc != MH_OK) return rc;
 	auto geometry = [&](uint64_t base_bit, uint64_t& b0, uint64_t& load, bool& last) {   // chunk that starts (nominally) at base_bit
 		b0 = (base_bit >> 3) & ~uint64_t(3);
 		load = payload_bytes - b0 < chunk ? payload_bytes - b0 : chunk;
@@ -777,6 +775,8 @@ static int session_decompress_pipelined(mh_session* s, const mh_table* t, const 
 	geometry(0, b0, load, last);
 	MH_CUDA(cudaMemcpyAsync(s->d_payload, payload + b0, load, cudaMemcpyHostToDevice, s->h2d));
 	MH_CUDA(cudaEventRecord(s->ev_in[0], s->h2d));
+	int rc = upload_dectable(t, &s->dec, s->stream);   // flattened on the host while the first chunk is on its way
+	if(rc != MH_OK) { cudaStreamSynchronize(s->h2d); return rc; }
 	for(uint32_t k = 0;; ++k) {
 		const uint32_t cur = k & 1;
 		geometry(base, b0, load, last);
