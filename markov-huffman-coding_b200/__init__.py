@@ -122,6 +122,13 @@ def device_count():
     return _lib.mh_device_count()
 
 
+def device_memory(device=0):
+    """(free bytes, total bytes) of a device; a host driver sizes its session from it."""
+    free, total = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _check(_lib.mh_device_memory(int(device), ctypes.byref(free), ctypes.byref(total)), "mh_device_memory")
+    return free.value, total.value
+
+
 def kernel_launches():
     return _lib.mh_kernel_launches()
 

@@ -140,6 +140,9 @@ def test_no_device_fails_loudly():
     assert e.value.status in (mh.MH_ERR_NO_DEVICE, mh.MH_ERR_CUDA)
     with pytest.raises(mh.MhError):
         mh.compress(b"hello")
+    with pytest.raises(mh.MhError) as e:
+        mh.device_memory(0)
+    assert e.value.status in (mh.MH_ERR_NO_DEVICE, mh.MH_ERR_CUDA)
 
 
 def _pair_decode(pl, bits, n_bits, prev0, markov, n_symbols):
