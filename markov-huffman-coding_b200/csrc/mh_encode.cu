@@ -4,27 +4,28 @@
 // bitbuffer::push_encoding_descriptor / push_byte / flush (src/bitbuffer.cpp:21-73, :170-180): for every input
 // byte c with predecessor prev, append codeword[prev][c] MSB-first to one contiguous bit stream.
 //
-// Shape of the kernel. Persistent CTAs (a multiple of the SM count) pull tiles of 512 x SPT input
-// bytes (SPT = 32 or 16 symbols per thread) from an atomic ticket, so a tile only ever waits on tiles that are
-// already running.
-//   0. once per CTA the codebook is staged in shared memory: u32 entries (5-bit length | 27-bit code) for the
-//      RxR box of byte values the table actually uses (text: R ~ 113 -> 51 KiB), with a zero border that bytes
-//      outside the box are clamped onto. Tables whose box does not fit, or whose codewords exceed 27 bits, are
-//      gathered from global memory (L1/L2) instead;
-//   1. each thread takes SPT consecutive bytes with coalesced 128-bit loads (the byte before them comes from the
-//      neighbouring lane by shuffle), looks up its entries and sums their lengths;
+// Shape of the kernel. Persistent CTAs (two per SM) of 15 worker warps and one scanner warp pull
+// tiles of 480 x SPT input bytes (SPT = 32 or 16 symbols per thread) from an atomic ticket, so a tile only ever
+// waits on tiles that are already running.
+//   0. once per CTA the codebook is staged in shared memory: for text, context rows (one 256-entry u32 row per live
+//      context, entry = 5-bit length | next row | 16-bit code, the rare longer codeword escapes to the wide table);
+//      otherwise u32 entries (5-bit length | 27-bit code) for the RxR box of byte values the table uses, with a zero
+//      border that bytes outside the box are clamped onto; tables that fit neither are gathered from global memory;
+//   1. each worker thread takes SPT consecutive bytes with coalesced 128-bit loads (the byte before them comes from
+//      the neighbouring lane by shuffle), looks up its entries and sums their lengths;
 //   2. a block-wide exclusive scan of the per-thread bit counts gives every thread its bit offset in the tile; the
 //      tile's bit count is PUBLISHED RIGHT AWAY, so successors can resolve their offsets while this tile packs;
-//   3. codewords are merged pairwise, then by fours, in registers (a quad is one <= 64-bit unit; the rare longer
-//      quad goes out as two pairs) and funnelled through a 96-bit window; only completed 32-bit words are ORed
-//      into the zeroed shared-memory staging area (neighbouring threads share their boundary words, hence the OR);
-//   4. warp 0 publishes the tile's last 31 bits and resolves the tile's global bit offset by a warp-wide
-//      decoupled look-back (32 predecessors per poll, relaxed loads that bypass L1). The tile that ends a
-//      partially filled 32-bit output word writes it, using the predecessor's published tail bits — so every
-//      output word has exactly one writer: no pre-zeroed output, no global atomics, no second pass;
-//   5. the staged bits are funnel-shifted by the tile's global bit phase and written with coalesced 32-bit
-//      stores, byte-swapped so that stream bit p lands in byte p/8, bit 7 - p%8 (src/bitbuffer.cpp:12); the words
-//      just copied are re-zeroed for the next tile.
+//   3. codewords are merged pairwise, then by fours, in registers and funnelled through a bit window; only completed
+//      32-bit words are ORed into the zeroed shared-memory staging area (neighbouring threads share their boundary
+//      words, hence the OR); thread 0 publishes the tile's last 31 bits;
+//   4. the scanner warp resolves the tile's global bit offset by a warp-wide decoupled look-back (32 predecessors per
+//      poll, relaxed loads that bypass L1) as soon as the bit count is known — one iteration before the workers need
+//      it — and hands it over through a named barrier. It also writes the one output word the tile shares with its
+//      predecessor (the predecessor's tail bits, then this tile's first bits), so every output word has exactly one
+//      writer: no pre-zeroed output, no global atomics, no second pass;
+//   5. one iteration later the workers funnel-shift the staged bits by the tile's global bit phase and write them
+//      with coalesced 32-bit stores, byte-swapped so that stream bit p lands in byte p/8, bit 7 - p%8
+//      (src/bitbuffer.cpp:12); the words just copied are re-zeroed for the next tile.
 #include "mh_internal.hpp"
 
 namespace mh {
