@@ -17,10 +17,14 @@
 //   D2 seams    one thread per chunk boundary checks that the previous chunk's recorded end state equals what
 //               this chunk's warm-up produced; only on a mismatch does it re-decode from the recorded state until
 //               it merges. Repeats until no chunk end state changes (normally zero re-decodes).
-//   D3 offsets  per-chunk symbol totals, exclusive scan -> output offset of every chunk, total output size.
-//   D4 write    one thread per subsequence decodes from its verified start state and writes its symbols at its
-//               output offset (block scan of the per-subsequence counts inside the chunk).
-// D1 and D4 are persistent CTAs that stage the decode LUT (128 KiB in Markov mode) in shared memory once.
+//   D3 offsets  per-chunk symbol totals and, for every subsequence, the symbols of its chunk before it; exclusive
+//               scan of the totals -> output offset of every subsequence, total output size.
+//   D4 write    one thread per subsequence decodes from its verified start state; warps take 32 subsequences at a
+//               time from an atomic ticket. The symbols go through per-thread rings in shared memory and leave
+//               warp-wide as whole 64-byte units (pair-table path), or with per-thread 8-byte stores.
+// D1 and D4 are persistent CTAs that stage the decode table in shared memory once: the two-symbol pair table over the
+// live contexts (~50-75 KiB for text, see below) or, with more than 63 live contexts, the reference's 8-bit LUT
+// (128 KiB in Markov mode). The payload reaches every thread through a private cp.async ring in shared memory.
 #include "mh_internal.hpp"
 
 namespace mh {
