@@ -49,6 +49,15 @@ int mh_device_count(void);
  * session stream larger files through in chunks. */
 int mh_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes);
 int mh_version(void);
+/* Experiment / test overrides of the library's tunables ("enc_fmt", "dec_sub_bits_markov", "dec_sub_bits_huffman",
+ * "dec_pair", "dec_write_threads", "pipe_min_bytes", "pipe_chunk_bytes", "enc_pipe_chunk_bytes", "dec_fused"); -1 = the
+ * documented default. The matching environment variables (MH_ENC_FMT, ...) are read once, when the library is loaded. */
+int mh_tunable_set(const char* name, long long value);
+int mh_tunable_get(const char* name, long long* value);
+/* Page-locked host memory for the host-buffer calls below: copies from / to pageable memory cannot overlap with the
+ * kernels (a host driver reads its file straight into such a buffer). NULL when the allocation fails. */
+void* mh_pinned_alloc(size_t bytes);
+void mh_pinned_free(void* p);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Host side: the coding tables. Replaces huffman_table / markov_huffman_table (src/huffman.{h,cpp},
@@ -174,11 +183,16 @@ int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
 int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n,
                                    uint8_t* out, uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped);
 /* `markovhuffman in -o out -x -e table`: header checks (src/coding.cpp:100-116) then decode.
- * Call with out == NULL to decode on the device and get the size in *out_len; mh_session_fetch then delivers it. */
+ * Call with out == NULL to decode on the device and get the size in *out_len; mh_session_fetch then delivers it.
+ * The session's buffers are fixed at creation: a stream that is larger than the compressed-side buffer, or that
+ * decodes to more bytes than the uncompressed-side buffer holds, is decoded in bit-range chunks whose bytes leave for
+ * `out` chunk by chunk. Without `out` such a call only reports the size and nothing stays on the device:
+ * mh_session_fetch then returns MH_ERR_WORKSPACE, and the caller repeats mh_session_decompress with `out`. */
 int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* stream, uint64_t stream_len,
                           uint8_t* out, uint64_t out_capacity, uint64_t* out_len);
 /* Copies the bytes decoded by the last mh_session_decompress(out == NULL) call to the host: the size query and the
- * fetch then cost one decode, not two. */
+ * fetch then cost one decode, not two. MH_ERR_WORKSPACE (with *out_len = 0): that call decoded in chunks and only
+ * counted — nothing is resident; call mh_session_decompress again with the output buffer. */
 int mh_session_fetch(mh_session* s, uint8_t* out, uint64_t out_capacity, uint64_t* out_len);
 /* Histogram only (host buffer in, host counts out): construct_table on the device. */
 int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order, uint64_t* counts);

@@ -61,6 +61,10 @@ _SIGNATURES = {
     "mh_device_count": (_i, []),
     "mh_device_memory": (_i, [_i, _pu64, _pu64]),
     "mh_version": (_i, []),
+    "mh_tunable_set": (_i, [ctypes.c_char_p, ctypes.c_longlong]),
+    "mh_tunable_get": (_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_longlong)]),
+    "mh_pinned_alloc": (_vp, [_sz]),
+    "mh_pinned_free": (None, [_vp]),
     "mh_table_from_counts": (_i, [_vp, _i, _pp]),
     "mh_table_from_bytes": (_i, [_vp, _sz, _pp]),
     "mh_table_serialize": (_i, [_vp, _vp, _sz, _psz]),
@@ -127,6 +131,17 @@ def device_memory(device=0):
     free, total = ctypes.c_uint64(0), ctypes.c_uint64(0)
     _check(_lib.mh_device_memory(int(device), ctypes.byref(free), ctypes.byref(total)), "mh_device_memory")
     return free.value, total.value
+
+
+def tunable_set(name, value):
+    """Experiment / test override of a library tunable (-1 restores the default)."""
+    _check(_lib.mh_tunable_set(name.encode(), int(value)), "mh_tunable_set(%s)" % name)
+
+
+def tunable_get(name):
+    v = ctypes.c_longlong(0)
+    _check(_lib.mh_tunable_get(name.encode(), ctypes.byref(v)), "mh_tunable_get(%s)" % name)
+    return v.value
 
 
 def kernel_launches():
@@ -331,13 +346,15 @@ class Session:
             raise MhError(rc, "mh_session_decompress")
         need = out_len.value
         buf = np.empty(max(1, need), dtype=np.uint8)
-        _check(_lib.mh_session_fetch(self._h, buf.ctypes.data, buf.size, ctypes.byref(out_len)), "mh_session_fetch")
-        if out_len.value != need:
-            # a stream larger than the session's device buffer was decoded in chunks: the first call only counted,
-            # nothing stays resident to fetch — decode again, chunk by chunk, into the host buffer
+        frc = _lib.mh_session_fetch(self._h, buf.ctypes.data, buf.size, ctypes.byref(out_len))
+        if frc == MH_ERR_WORKSPACE:
+            # the stream did not fit the session's device buffers: it was decoded in chunks and only counted, nothing
+            # stays resident to fetch — decode again, chunk by chunk, into the host buffer
             rc = _lib.mh_session_decompress(self._h, provider._h, addr, n, buf.ctypes.data, buf.size, ctypes.byref(out_len))
             if rc not in (MH_OK, MH_ERR_CORRUPT_STREAM):
                 raise MhError(rc, "mh_session_decompress")
+        else:
+            _check(frc, "mh_session_fetch")
         if rc != MH_OK:
             raise MhError(rc, "mh_session_decompress")
         return buf[: out_len.value].tobytes()

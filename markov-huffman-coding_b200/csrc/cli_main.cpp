@@ -36,10 +36,55 @@ void probe_access(const char* path, bool write) {
 		eprintf("Error: Unable to open \"%s\" for %s; %s.", path, write ? "writing" : "reading", strerror(errno));
 }
 
-bool slurp(FILE* f, std::vector<uint8_t>& out) {
-	uint8_t buf[1 << 16];
+// A host buffer in page-locked memory (mh_pinned_alloc), so that the session's copies overlap with its kernels; plain
+// memory when pinning fails (the copies are then staged by the driver).
+struct HostBuf {
+	uint8_t* p = nullptr;
+	size_t n = 0, cap = 0;
+	bool pinned = false;
+	HostBuf() = default;
+	HostBuf(const HostBuf&) = delete;
+	HostBuf& operator=(const HostBuf&) = delete;
+	~HostBuf() { release(); }
+	void release() {
+		if(pinned) mh_pinned_free(p);
+		else free(p);
+		p = nullptr;
+		n = cap = 0;
+	}
+	bool reserve(size_t want) {   // contents are kept
+		if(want <= cap) return true;
+		uint8_t* q = static_cast<uint8_t*>(mh_pinned_alloc(want));
+		const bool pin = q != nullptr;
+		if(!q) q = static_cast<uint8_t*>(malloc(want));
+		if(!q) return false;
+		if(n) memcpy(q, p, n);
+		const size_t keep = n;
+		release();
+		p = q; n = keep; cap = want; pinned = pin;
+		return true;
+	}
+	bool resize(size_t want) {
+		if(!reserve(want ? want : 1)) return false;
+		n = want;
+		return true;
+	}
+};
+
+// the whole file, read straight into the pinned buffer (sized from the file when it is seekable)
+bool slurp(FILE* f, HostBuf& out) {
+	size_t hint = 1 << 16;
+	if(fseek(f, 0, SEEK_END) == 0) {
+		const long end = ftell(f);
+		if(end > 0) hint = size_t(end) + 1;
+		rewind(f);
+	}
+	if(!out.reserve(hint)) return false;
 	size_t got;
-	while((got = fread(buf, 1, sizeof buf, f)) > 0) out.insert(out.end(), buf, buf + got);
+	while((got = fread(out.p + out.n, 1, out.cap - out.n, f)) > 0) {
+		out.n += got;
+		if(out.n == out.cap && !out.reserve(out.cap * 2)) return false;
+	}
 	return !ferror(f);
 }
 
@@ -132,7 +177,7 @@ int main(int argc, char* argv[]) {
 		exit(1);
 	}
 
-	std::vector<uint8_t> in_bytes;
+	HostBuf in_bytes;
 	if(!slurp(input_fd, in_bytes)) {
 		eprintf("Error occurred while reading file.\n");   // src/utils.cpp:62-65
 		exit(1);
@@ -142,7 +187,7 @@ int main(int argc, char* argv[]) {
 	const int order = simple_huffman ? MH_ORDER_HUFFMAN : MH_ORDER_MARKOV;
 	mh_table* table = nullptr;
 	mh_session* session = nullptr;
-	std::vector<uint8_t> result;
+	HostBuf result;
 
 	if(encoding_input) {
 		eprintf("Loading encoding table from file...\n");
@@ -151,23 +196,23 @@ int main(int argc, char* argv[]) {
 			eprintf("Error while opening encoding input; %s.\n", strerror(errno));
 			exit(1);
 		}
-		std::vector<uint8_t> tbytes;
+		HostBuf tbytes;
 		if(!slurp(tf, tbytes)) {
 			eprintf("Error occurred while reading file.\n");
 			exit(1);
 		}
 		fclose(tf);
-		if(tbytes.empty()) {   // the reference peeks a bit of an empty buffer here (undefined); refuse instead
+		if(tbytes.n == 0) {   // the reference peeks a bit of an empty buffer here (undefined); refuse instead
 			eprintf("Error: Encoding table file is empty.\n");
 			exit(1);
 		}
-		const bool file_is_markov = (tbytes[0] & 0x80) != 0;   // src/main.cpp:147-154
+		const bool file_is_markov = (tbytes.p[0] & 0x80) != 0;   // src/main.cpp:147-154
 		if(file_is_markov != !simple_huffman) {
 			eprintf("Error: Incorrect encoding table provided for current operation; expected %s, found %s.\n",
 			        simple_huffman ? "simple Huffman" : "Markov-Huffman", file_is_markov ? "Markov-Huffman" : "simple Huffman");
 			exit(1);
 		}
-		int rc = mh_table_from_bytes(tbytes.data(), tbytes.size(), &table);
+		int rc = mh_table_from_bytes(tbytes.p, tbytes.n, &table);
 		if(rc != MH_OK) die_status("loading the encoding table", rc);
 	}
 
@@ -183,8 +228,8 @@ int main(int argc, char* argv[]) {
 		if(v >= 4096) cap = v;
 	}
 	auto capped = [&](uint64_t want) { return want < cap ? want : cap; };
-	int rc = extract ? mh_session_create_sized(0, capped(in_bytes.size() * 3 + 4096), capped(in_bytes.size() + 64), &session)
-	                 : mh_session_create(0, capped(in_bytes.size() + 64), &session);
+	int rc = extract ? mh_session_create_sized(0, capped(in_bytes.n * 3 + 4096), capped(in_bytes.n + 64), &session)
+	                 : mh_session_create(0, capped(in_bytes.n + 64), &session);
 	if(rc != MH_OK) die_status("creating the GPU session", rc);
 
 	bool built_here = false;
@@ -194,13 +239,14 @@ int main(int argc, char* argv[]) {
 		built_here = true;
 	}
 
+	auto alloc_fail = [&]() { eprintf("Error: out of host memory.\n"); exit(1); };
 	if(built_here) {
 		// histogram -> trees -> encode, all in one session call; the table comes back for -g / -d
-		result.resize(in_bytes.size() + in_bytes.size() / 8 + 4200);
+		if(!result.resize(in_bytes.n + in_bytes.n / 8 + 4200)) alloc_fail();
 		uint64_t out_len = 0;
-		rc = mh_session_compress(session, in_bytes.data(), in_bytes.size(), order, result.data(), result.size(), &out_len, &table);
+		rc = mh_session_compress(session, in_bytes.p, in_bytes.n, order, result.p, result.n, &out_len, &table);
 		if(rc != MH_OK) die_status("compressing", rc);
-		result.resize(out_len);
+		result.n = out_len;
 	}
 
 	if(debug) {   // src/main.cpp:187-190
@@ -230,41 +276,50 @@ int main(int argc, char* argv[]) {
 	if(extract) {
 		eprintf("Extracting %s ===> %s...\n", input, shown(output));
 		uint64_t n_out = 0;
-		rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), nullptr, 0, &n_out);   // decode, learn the size
+		rc = mh_session_decompress(session, table, in_bytes.p, in_bytes.n, nullptr, 0, &n_out);   // decode, learn the size
 		if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
-		const uint64_t need = n_out;
-		result.resize(n_out ? n_out : 1);
-		rc = mh_session_fetch(session, result.data(), result.size(), &n_out);
-		if(rc != MH_OK) die_status("extracting", rc);
-		if(n_out != need) {   // a stream larger than the device buffer: the first pass only counted; decode again into the host buffer
-			rc = mh_session_decompress(session, table, in_bytes.data(), in_bytes.size(), result.data(), result.size(), &n_out);
+		if(!result.resize(n_out)) alloc_fail();
+		rc = mh_session_fetch(session, result.p, result.cap, &n_out);
+		if(rc == MH_ERR_WORKSPACE) {   // the stream did not fit the device buffers: the first pass only counted; decode again, chunk by chunk, into the host buffer
+			rc = mh_session_decompress(session, table, in_bytes.p, in_bytes.n, result.p, result.cap, &n_out);
 			if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
+		} else if(rc != MH_OK) {
+			die_status("extracting", rc);
 		}
-		result.resize(n_out);
-		if(n_out && fwrite(result.data(), 1, n_out, output_fd) != n_out) {
+		result.n = n_out;
+		if(n_out && fwrite(result.p, 1, n_out, output_fd) != n_out) {
 			eprintf("Error occurred while writing file.\n");
 			exit(1);
 		}
 	} else {
 		eprintf("Compressing %s ===> %s...\n", input, shown(output));
 		if(!built_here) {
-			result.resize(in_bytes.size() + in_bytes.size() / 8 + 4200);
+			if(!result.resize(in_bytes.n + in_bytes.n / 8 + 4200)) alloc_fail();
 			uint64_t out_len = 0, dropped = 0;
-			rc = mh_session_compress_with_table(session, table, in_bytes.data(), in_bytes.size(), result.data(), result.size(), &out_len, &dropped);
+			rc = mh_session_compress_with_table(session, table, in_bytes.p, in_bytes.n, result.p, result.n, &out_len, &dropped);
+			if(rc == MH_ERR_CAPACITY && out_len > result.n) {   // a foreign table that expands this input: the call reported the size it needs
+				if(!result.resize(out_len)) alloc_fail();
+				rc = mh_session_compress_with_table(session, table, in_bytes.p, in_bytes.n, result.p, result.n, &out_len, &dropped);
+			}
 			if(rc != MH_OK) die_status("compressing", rc);
-			result.resize(out_len);
+			result.n = out_len;
+			// The reference drops a symbol that has no codeword in the given table without a word (its assert is compiled out,
+			// src/coding.cpp:72, Makefile:20); the bytes written are the same, but say so.
+			if(dropped)
+				eprintf("Warning: %llu input byte%s no codeword in the provided encoding table and %s dropped; the output will not extract to the input.\n",
+				        (unsigned long long) dropped, dropped == 1 ? " has" : "s have", dropped == 1 ? "was" : "were");
 		}
 		// The reference writes a 0x80 placeholder first and seeks back to patch the header (src/coding.cpp:66, :85-89).
 		// On a non-seekable sink the seek fails and the header byte lands after the payload; keep that behaviour.
 		const bool seekable = fseek(output_fd, 0, SEEK_CUR) == 0;
 		bool ok;
 		if(seekable) {
-			ok = fwrite(result.data(), 1, result.size(), output_fd) == result.size();
+			ok = fwrite(result.p, 1, result.n, output_fd) == result.n;
 		} else {
 			const uint8_t placeholder = 0x80;
 			ok = fwrite(&placeholder, 1, 1, output_fd) == 1 &&
-			     (result.size() == 1 || fwrite(result.data() + 1, 1, result.size() - 1, output_fd) == result.size() - 1) &&
-			     fwrite(result.data(), 1, 1, output_fd) == 1;
+			     (result.n == 1 || fwrite(result.p + 1, 1, result.n - 1, output_fd) == result.n - 1) &&
+			     fwrite(result.p, 1, 1, output_fd) == 1;
 		}
 		if(!ok) {
 			eprintf("Error occurred while writing file.\n");

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -28,41 +29,87 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 namespace {
 struct ProfRecord { const char* name; cudaEvent_t a, b; };
-bool g_prof_on = false;
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;   // guards g_prof: launches may come from one host thread per GPU
 std::vector<ProfRecord> g_prof;
 }  // namespace
 
 ProfScope::ProfScope(const char* name, cudaStream_t s) : slot(-1), st(s) {
-	if(!g_prof_on) return;
+	if(!g_prof_on.load(std::memory_order_relaxed)) return;
 	ProfRecord r{name, nullptr, nullptr};
 	if(cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
 	cudaEventRecord(r.a, st);
+	std::lock_guard<std::mutex> lock(g_prof_mu);
 	g_prof.push_back(r);
 	slot = int(g_prof.size()) - 1;
+	end = r.b;
 }
 ProfScope::~ProfScope() {
-	if(slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+	if(slot >= 0) cudaEventRecord(end, st);
 }
 
+namespace {
+constexpr int kMaxDevices = 64;
+int current_device_slot() {
+	int dev = 0;
+	if(cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+	return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+std::atomic<int> g_sm_count[kMaxDevices];
+std::atomic<int> g_smem_optin[kMaxDevices];
+}  // namespace
+
 int sm_count() {
-	static int cached = 0;
-	if(!cached) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		if(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cached <= 0) cached = 148;
+	const int dev = current_device_slot();
+	int v = g_sm_count[dev].load(std::memory_order_relaxed);
+	if(!v) {
+		if(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+		g_sm_count[dev].store(v, std::memory_order_relaxed);
 	}
-	return cached;
+	return v;
 }
 
 int max_smem_optin() {
-	static int cached = 0;
-	if(!cached) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		if(cudaDeviceGetAttribute(&cached, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) cached = 48 * 1024;
+	const int dev = current_device_slot();
+	int v = g_smem_optin[dev].load(std::memory_order_relaxed);
+	if(!v) {
+		if(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 48 * 1024; }
+		g_smem_optin[dev].store(v, std::memory_order_relaxed);
 	}
-	return cached;
+	return v;
 }
+
+bool first_use_on_device(std::atomic<uint64_t>& done_mask) {
+	const uint64_t bit = 1ull << current_device_slot();
+	return (done_mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
+
+// ---- tunables -------------------------------------------------------------------------------------------
+namespace {
+struct TunableDef { const char* name; const char* env; };
+const TunableDef kTunables[kTunCount] = {
+    {"enc_fmt", "MH_ENC_FMT"},
+    {"dec_sub_bits_markov", "MH_DEC_SUB_BITS_MARKOV"},
+    {"dec_sub_bits_huffman", "MH_DEC_SUB_BITS_HUFFMAN"},
+    {"dec_pair", "MH_DEC_PAIR"},
+    {"dec_write_threads", "MH_DEC_WRITE_THREADS"},
+    {"pipe_min_bytes", "MH_PIPE_MIN_BYTES"},
+    {"pipe_chunk_bytes", "MH_PIPE_CHUNK_BYTES"},
+    {"enc_pipe_chunk_bytes", "MH_ENC_PIPE_CHUNK_BYTES"},
+    {"dec_fused", "MH_DEC_FUSED"},
+};
+std::atomic<long long> g_tunables[kTunCount];
+struct TunableInit {
+	TunableInit() {
+		for(int i = 0; i < kTunCount; ++i) {
+			const char* e = getenv(kTunables[i].env);   // the only getenv calls of the library: once, at load time
+			g_tunables[i].store(e && *e ? strtoll(e, nullptr, 10) : -1, std::memory_order_relaxed);
+		}
+	}
+} g_tunable_init;
+}  // namespace
+
+long long tunable(Tunable t) { return g_tunables[t].load(std::memory_order_relaxed); }
 
 }  // namespace mh
 
@@ -115,6 +162,7 @@ int mh_version(void) { return 100; }
 uint64_t mh_kernel_launches(void) { return g_kernel_launches.load(); }
 
 int mh_profile_enable(int on) {
+	std::lock_guard<std::mutex> lock(g_prof_mu);
 	for(auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
 	g_prof.clear();
 	g_prof_on = on != 0;
@@ -125,9 +173,17 @@ int mh_profile_report(char* out, size_t cap, size_t* n_out) {
 	if(!n_out) return MH_ERR_INVALID_ARG;
 	struct Agg { const char* name; uint64_t launches; double ms; };
 	std::vector<Agg> agg;
-	for(auto& r : g_prof) {
+	std::vector<ProfRecord> recs;
+	{
+		std::lock_guard<std::mutex> lock(g_prof_mu);
+		recs.swap(g_prof);
+	}
+	for(auto& r : recs) {
 		float ms = 0.f;
-		if(cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+		const bool ok = cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess;
+		cudaEventDestroy(r.a);
+		cudaEventDestroy(r.b);
+		if(!ok) { cudaGetLastError(); continue; }
 		size_t k = 0;
 		while(k < agg.size() && strcmp(agg[k].name, r.name) != 0) ++k;
 		if(k == agg.size()) agg.push_back({r.name, 0, 0.0});
@@ -145,9 +201,21 @@ int mh_profile_report(char* out, size_t cap, size_t* n_out) {
 	*n_out = js.size() + 1;
 	if(js.size() + 1 > cap) return MH_ERR_CAPACITY;
 	memcpy(out, js.c_str(), js.size() + 1);
-	const bool keep = g_prof_on;
-	mh_profile_enable(keep ? 1 : 0);
 	return MH_OK;
+}
+
+int mh_tunable_set(const char* name, long long value) {
+	if(!name) return MH_ERR_INVALID_ARG;
+	for(int i = 0; i < kTunCount; ++i)
+		if(strcmp(name, kTunables[i].name) == 0) { g_tunables[i].store(value, std::memory_order_relaxed); return MH_OK; }
+	return MH_ERR_INVALID_ARG;
+}
+
+int mh_tunable_get(const char* name, long long* value) {
+	if(!name || !value) return MH_ERR_INVALID_ARG;
+	for(int i = 0; i < kTunCount; ++i)
+		if(strcmp(name, kTunables[i].name) == 0) { *value = g_tunables[i].load(std::memory_order_relaxed); return MH_OK; }
+	return MH_ERR_INVALID_ARG;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -264,7 +332,7 @@ static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st) 
 		if(cb->ctx_rows) MH_CUDA(cudaMemcpyAsync(cb->d_ctx, cb->h_ctx, size_t(cb->ctx_rows) * 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 	}
 	// the box table is only needed when the context rows are not available (or a test forces another format)
-	cb->has_box = cb->max_bits <= kEncBoxMaxBits && (cb->ctx_rows == 0 || getenv("MH_ENC_FMT") != nullptr);
+	cb->has_box = cb->max_bits <= kEncBoxMaxBits && (cb->ctx_rows == 0 || tunable(kTunEncFmt) >= 0);
 	if(cb->has_box) {
 		if(!cb->d_box) MH_CUDA(cudaMalloc(&cb->d_box, 257 * 257 * sizeof(uint32_t)));
 		if(!cb->h_box) MH_CUDA(cudaMallocHost(&cb->h_box, 257 * 257 * sizeof(uint32_t)));
@@ -441,32 +509,75 @@ uint32_t mh_decode_subsequence_bits(int order, uint64_t n_bits) { return decode_
 // ---------------------------------------------------------------------------------------------------------
 // host-buffer session
 // ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxPipeChunks = 4096;   // seam bytes kept per pipelined compress
+
 struct mh_session {
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	uint64_t max_input = 0;      // capacity of d_raw (grows on demand when extracting)
+	uint64_t max_input = 0;      // capacity of d_raw: fixed at creation, never reallocated
 	uint64_t enc_chunk = 0;      // bytes one histogram / encode launch may take (what the workspace was sized for)
 	uint64_t payload_cap = 0;
 	uint64_t pending_out = 0;    // decoded bytes waiting in d_raw for mh_session_fetch
+	uint64_t last_count = 0;     // bytes the last mh_session_decompress produced (resident or not)
 	uint8_t* d_raw = nullptr;       // uncompressed side
 	uint8_t* d_payload = nullptr;   // compressed side (no header byte)
 	uint64_t* d_counts = nullptr;   // [65536]
 	uint64_t* d_result = nullptr;   // [4]
 	uint64_t* h_counts = nullptr;   // pinned [65536]
 	uint64_t* h_result = nullptr;   // pinned [4]
+	uint8_t* h_seam = nullptr;      // pinned [kMaxPipeChunks]: the first payload byte of every pipelined encode chunk
 	mh_workspace* ws = nullptr;
 	mh_codebook book;
 	mh_dectable dec;
-	// pipelined extract: copy streams and their events (created on first use)
+	// pipelined paths: copy streams and their events (created on first use)
 	cudaStream_t h2d = nullptr, d2h = nullptr;
 	cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
+static int ensure_pipe_streams(mh_session* s) {
+	if(s->h2d) return MH_OK;
+	MH_CUDA(cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking));
+	MH_CUDA(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking));
+	for(int i = 0; i < 2; ++i) {
+		MH_CUDA(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
+		MH_CUDA(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
+	}
+	MH_CUDA(cudaMallocHost(&s->h_seam, kMaxPipeChunks));
+	return MH_OK;
+}
+
+static void drain_session(mh_session* s) {
+	if(s->h2d) cudaStreamSynchronize(s->h2d);
+	if(s->d2h) cudaStreamSynchronize(s->d2h);
+	cudaStreamSynchronize(s->stream);
+}
+// CUDA call inside a pipelined loop: every error exit waits for the copies that are still reading / writing the caller's buffers
+#define MH_CUDA_DRAIN(s, call)                                                      \
+	do {                                                                            \
+		cudaError_t e_ = (call);                                                    \
+		if(e_ != cudaSuccess) { drain_session(s); return ::mh::cuda_fail(e_, #call); } \
+	} while(0)
+
+static uint64_t tunable_bytes(Tunable t, uint64_t fallback) {
+	const long long v = tunable(t);
+	return v > 0 ? uint64_t(v) : fallback;
+}
+
 extern "C" {
+
+void* mh_pinned_alloc(size_t bytes) {
+	void* p = nullptr;
+	if(cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+void mh_pinned_free(void* p) {
+	if(p) cudaFreeHost(p);
+}
 
 int mh_session_create(int device, uint64_t max_input_bytes, mh_session** out) {
 	// An optimal prefix code built from the data's own counts never averages more than 8 bits per byte; a foreign
-	// -e table can expand, which is reported as MH_ERR_CAPACITY rather than silently truncated.
+	// -e table can expand: such an input is then encoded in chunks that fit (mh_session_compress_with_table).
 	return mh_session_create_sized(device, max_input_bytes, max_input_bytes + (max_input_bytes >> 3) + 4096, out);
 }
 
@@ -502,13 +613,14 @@ int mh_session_create_sized(int device, uint64_t max_input_bytes, uint64_t max_s
 void mh_session_destroy(mh_session* s) {
 	if(!s) return;
 	cudaSetDevice(s->device);
-	if(s->stream) cudaStreamSynchronize(s->stream);
+	drain_session(s);
 	if(s->d_raw) cudaFree(s->d_raw);
 	if(s->d_payload) cudaFree(s->d_payload);
 	if(s->d_counts) cudaFree(s->d_counts);
 	if(s->d_result) cudaFree(s->d_result);
 	if(s->h_counts) cudaFreeHost(s->h_counts);
 	if(s->h_result) cudaFreeHost(s->h_result);
+	if(s->h_seam) cudaFreeHost(s->h_seam);
 	release_book(&s->book);
 	release_dec(&s->dec);
 	mh_workspace_destroy(s->ws);
@@ -544,6 +656,9 @@ int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order
 	return MH_OK;
 }
 
+// header: 0 0 1 1 E R R R, E = inverse of the coder type, RRR = unused bits of the last byte (src/coding.cpp:88)
+static uint8_t stream_header(int order, uint64_t bits) { return uint8_t(0x30 | ((~order & 1) << 3) | ((8 - bits % 8) % 8)); }
+
 // encode d_raw[0..n) with `t`, fetch header + payload into out
 static int session_encode(mh_session* s, const mh_table* t, uint64_t n, uint8_t* out, uint64_t out_capacity,
                           uint64_t* out_len, uint64_t* dropped) {
@@ -561,8 +676,7 @@ static int session_encode(mh_session* s, const mh_table* t, uint64_t n, uint8_t*
 	if(dropped) *dropped = s->h_result[1];
 	*out_len = 1 + bytes;
 	if(1 + bytes > out_capacity) return MH_ERR_CAPACITY;
-	// header: 0 0 1 1 E R R R, E = inverse of the coder type, RRR = unused bits of the last byte (src/coding.cpp:88)
-	out[0] = uint8_t(0x30 | ((~t->impl.order & 1) << 3) | ((8 - bits % 8) % 8));
+	out[0] = stream_header(t->impl.order, bits);
 	if(bytes) {
 		MH_CUDA(cudaMemcpyAsync(out + 1, s->d_payload, bytes, cudaMemcpyDeviceToHost, s->stream));
 		MH_CUDA(cudaStreamSynchronize(s->stream));
@@ -591,27 +705,30 @@ static int session_histogram_chunked(mh_session* s, const uint8_t* in, uint64_t 
 	return MH_OK;
 }
 
-static int session_encode_chunked(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n, uint8_t* out, uint64_t out_capacity,
-                                  uint64_t* out_len, uint64_t* dropped) {
-	if(out_capacity < 1 || s->enc_chunk == 0) return MH_ERR_CAPACITY;
+// `chunk`: input bytes per launch (<= enc_chunk). A table whose codewords expand the input (a foreign -e table) gets
+// chunks small enough that chunk x longest codeword fits the compressed-side buffer.
+static int session_encode_chunked(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n, uint64_t chunk, uint8_t* out,
+                                  uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped) {
+	if(out_capacity < 1 || chunk == 0) return MH_ERR_CAPACITY;
 	int rc = upload_codebook(t, &s->book, s->stream);
 	if(rc != MH_OK) return rc;
 	uint64_t bit_base = 0, drop = 0;
-	for(uint64_t off = 0; off < n; off += s->enc_chunk) {
-		const uint64_t len = n - off < s->enc_chunk ? n - off : s->enc_chunk;
+	bool fits = true;
+	for(uint64_t off = 0; off < n; off += chunk) {
+		const uint64_t len = n - off < chunk ? n - off : chunk;
 		MH_CUDA(cudaMemcpyAsync(s->d_raw, in + off, len, cudaMemcpyHostToDevice, s->stream));
 		rc = launch_encode(s->d_raw, len, off ? in[off - 1] : uint8_t(MH_PREV0), &s->book, bit_base, s->d_payload, s->payload_cap,
 		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
 		if(rc != MH_OK) return rc;
 		MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
 		MH_CUDA(cudaStreamSynchronize(s->stream));
-		if(s->h_result[2]) return MH_ERR_CAPACITY;
+		if(s->h_result[2]) return MH_ERR_WORKSPACE;   // the device-side buffer: the chunk was sized wrongly
 		const uint64_t bits = s->h_result[0];
 		drop += s->h_result[1];
 		const uint32_t phase = uint32_t(bit_base & 7);
 		const uint64_t nbytes = (phase + bits + 7) / 8, first = 1 + (bit_base >> 3);
-		if(first + nbytes > out_capacity) return MH_ERR_CAPACITY;
-		if(nbytes) {
+		if(first + nbytes > out_capacity) fits = false;   // keep counting: the caller learns the size it needs
+		if(nbytes && fits) {
 			uint8_t seam = 0;
 			if(phase) {   // the chunk's first byte is the previous chunk's last: keep that one's bits, add ours
 				MH_CUDA(cudaMemcpyAsync(&seam, s->d_payload, 1, cudaMemcpyDeviceToHost, s->stream));
@@ -626,15 +743,119 @@ static int session_encode_chunked(mh_session* s, const mh_table* t, const uint8_
 	}
 	if(dropped) *dropped = drop;
 	*out_len = 1 + (bit_base + 7) / 8;
-	// header: 0 0 1 1 E R R R, E = inverse of the coder type, RRR = unused bits of the last byte (src/coding.cpp:88)
-	out[0] = uint8_t(0x30 | ((~t->impl.order & 1) << 3) | ((8 - bit_base % 8) % 8));
+	if(!fits) return MH_ERR_CAPACITY;
+	out[0] = stream_header(t->impl.order, bit_base);
+	return MH_OK;
+}
+
+// ---- pipelined compress (overlapping PCIe with the kernels) -----------------------------------
+// Phase 1 (needs the table, so only when `t` is null): the input travels to the device in chunks on the copy stream
+// while the histogram of the chunk before it runs — the counts accumulate in one device table, every chunk seeded
+// with the byte before it. Phase 2: the resident input is encoded in chunks at their global bit offsets into the two
+// halves of the compressed-side buffer; while chunk k is encoded, the payload of chunk k - 1 travels to the host
+// (a byte that two chunks share is OR-merged at the end from the chunks' first bytes). With a given table (`t`)
+// there is no phase 1: chunk k + 1 travels to the device while chunk k is encoded and chunk k - 1 travels back.
+// Returns MH_ERR_WORKSPACE when the buffers are too small for it (the caller takes the sequential path).
+static int session_compress_pipelined(mh_session* s, const mh_table* given, const uint8_t* in, uint64_t n, int order, uint8_t* out,
+                                      uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped, mh_table** table_out) {
+	const uint64_t half = (s->payload_cap / 2) & ~uint64_t(15);
+	uint64_t chunk = tunable_bytes(kTunEncPipeChunkBytes, 64ull << 20);
+	const int maxb = given ? (given->impl.max_code_bits() > 8 ? given->impl.max_code_bits() : 9) : 9;
+	while(chunk > 4096 && (chunk * uint64_t(maxb) + 7) / 8 + 4096 > half) chunk >>= 1;
+	chunk &= ~uint64_t(15);
+	if(chunk < 4096 || n > s->max_input || n > s->enc_chunk || (n + chunk - 1) / chunk > kMaxPipeChunks || out_capacity < 1) return MH_ERR_WORKSPACE;
+	int rc = ensure_pipe_streams(s);
+	if(rc != MH_OK) return rc;
+	mh_table* built = nullptr;
+	const mh_table* t = given;
+	if(!given) {
+		const size_t bins = order ? 65536 : 256;
+		MH_CUDA(cudaMemsetAsync(s->d_counts, 0, bins * sizeof(uint64_t), s->stream));
+		for(uint64_t off = 0; off < n; off += chunk) {
+			const uint64_t len = n - off < chunk ? n - off : chunk;
+			MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->d_raw + off, in + off, len, cudaMemcpyHostToDevice, s->h2d));
+			MH_CUDA_DRAIN(s, cudaEventRecord(s->ev_in[0], s->h2d));
+			MH_CUDA_DRAIN(s, cudaStreamWaitEvent(s->stream, s->ev_in[0], 0));
+			rc = launch_histogram(s->d_raw + off, len, off ? in[off - 1] : uint8_t(MH_PREV0), order,
+			                      reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream, /*accumulate=*/true);
+			if(rc != MH_OK) { drain_session(s); return rc; }
+		}
+		MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+		MH_CUDA_DRAIN(s, cudaStreamSynchronize(s->stream));
+		rc = mh_table_from_counts(s->h_counts, order, &built);
+		if(rc != MH_OK) return rc;
+		t = built;
+	}
+	auto fail = [&](int code) { drain_session(s); if(built) mh_table_destroy(built); return code; };
+	rc = upload_codebook(t, &s->book, s->stream);
+	if(rc != MH_OK) return fail(rc);
+	if(given && n) {   // the first chunk starts its trip now
+		const uint64_t len = n < chunk ? n : chunk;
+		if(cudaMemcpyAsync(s->d_raw, in, len, cudaMemcpyHostToDevice, s->h2d) != cudaSuccess || cudaEventRecord(s->ev_in[0], s->h2d) != cudaSuccess)
+			return fail(cuda_fail(cudaGetLastError(), "pipelined compress: H2D"));
+	}
+	struct Seam { uint64_t at; uint32_t k, phase; };
+	std::vector<Seam> seams;
+	uint64_t bit_base = 0, drop = 0;
+	uint32_t k = 0;
+	for(uint64_t off = 0; off < n; off += chunk, ++k) {
+		const uint32_t cur = k & 1;
+		const uint64_t len = n - off < chunk ? n - off : chunk;
+		if(given) {
+			const uint64_t noff = off + chunk;
+			if(noff < n) {   // chunk k + 1 travels while chunk k is encoded
+				const uint64_t nlen = n - noff < chunk ? n - noff : chunk;
+				if(cudaMemcpyAsync(s->d_raw + noff, in + noff, nlen, cudaMemcpyHostToDevice, s->h2d) != cudaSuccess ||
+				   cudaEventRecord(s->ev_in[cur ^ 1], s->h2d) != cudaSuccess)
+					return fail(cuda_fail(cudaGetLastError(), "pipelined compress: H2D"));
+			}
+			if(cudaStreamWaitEvent(s->stream, s->ev_in[cur], 0) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "pipelined compress: wait"));
+		}
+		if(k >= 2 && cudaStreamWaitEvent(s->stream, s->ev_out[cur], 0) != cudaSuccess)   // the payload of chunk k - 2 has left this half
+			return fail(cuda_fail(cudaGetLastError(), "pipelined compress: wait"));
+		uint8_t* d_half = s->d_payload + cur * half;
+		rc = launch_encode(s->d_raw + off, len, off ? in[off - 1] : uint8_t(MH_PREV0), &s->book, bit_base, d_half, half,
+		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
+		if(rc != MH_OK) return fail(rc);
+		if(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+		   cudaStreamSynchronize(s->stream) != cudaSuccess)
+			return fail(cuda_fail(cudaGetLastError(), "pipelined compress: result"));
+		if(s->h_result[2]) return fail(MH_ERR_WORKSPACE);
+		const uint64_t bits = s->h_result[0];
+		drop += s->h_result[1];
+		const uint32_t phase = uint32_t(bit_base & 7);
+		const uint64_t nbytes = (phase + bits + 7) / 8, first = 1 + (bit_base >> 3);
+		if(first + nbytes > out_capacity) return fail(MH_ERR_WORKSPACE);   // the sequential path reports the size needed
+		cudaError_t ce = cudaSuccess;
+		if(nbytes) {
+			if(phase) {   // the chunk's first byte is the previous chunk's last one: merged on the host when everything has arrived
+				ce = cudaMemcpyAsync(s->h_seam + k, d_half, 1, cudaMemcpyDeviceToHost, s->d2h);
+				if(ce == cudaSuccess && nbytes > 1) ce = cudaMemcpyAsync(out + first + 1, d_half + 1, nbytes - 1, cudaMemcpyDeviceToHost, s->d2h);
+				seams.push_back({first, k, phase});
+			} else {
+				ce = cudaMemcpyAsync(out + first, d_half, nbytes, cudaMemcpyDeviceToHost, s->d2h);
+			}
+		}
+		if(ce == cudaSuccess) ce = cudaEventRecord(s->ev_out[cur], s->d2h);
+		if(ce != cudaSuccess) return fail(cuda_fail(ce, "pipelined compress: D2H"));
+		bit_base += bits;
+	}
+	drain_session(s);
+	for(const Seam& sm : seams) out[sm.at] = uint8_t(out[sm.at] | (s->h_seam[sm.k] & (0xFFu >> sm.phase)));
+	if(dropped) *dropped = drop;
+	*out_len = 1 + (bit_base + 7) / 8;
+	out[0] = stream_header(t->impl.order, bit_base);
+	if(built) {
+		if(table_out) *table_out = built;
+		else mh_table_destroy(built);
+	}
 	return MH_OK;
 }
 
 int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order, uint8_t* out, uint64_t out_capacity,
                         uint64_t* out_len, mh_table** table_out) {
 	if(!s || !out || !out_len || (!in && n) || (order != 0 && order != 1)) return MH_ERR_INVALID_ARG;
-	s->pending_out = 0;
+	s->pending_out = s->last_count = 0;
 	MH_CUDA(cudaSetDevice(s->device));
 	if(n > s->enc_chunk || n > s->max_input) {   // larger than the device buffer: stream it through in chunks
 		std::vector<uint64_t> total;
@@ -643,10 +864,14 @@ int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
 		mh_table* t = nullptr;
 		rc = mh_table_from_counts(total.data(), order, &t);
 		if(rc != MH_OK) return rc;
-		rc = session_encode_chunked(s, t, in, n, out, out_capacity, out_len, nullptr);
+		rc = session_encode_chunked(s, t, in, n, s->enc_chunk, out, out_capacity, out_len, nullptr);
 		if(rc == MH_OK && table_out) *table_out = t;
 		else mh_table_destroy(t);
 		return rc;
+	}
+	if(n >= tunable_bytes(kTunPipeMinBytes, 32ull << 20)) {   // large: overlap the copies with the kernels
+		const int prc = session_compress_pipelined(s, nullptr, in, n, order, out, out_capacity, out_len, nullptr, table_out);
+		if(prc != MH_ERR_WORKSPACE) return prc;
 	}
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
@@ -666,24 +891,37 @@ int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
 int mh_session_compress_with_table(mh_session* s, const mh_table* t, const uint8_t* in, uint64_t n, uint8_t* out,
                                    uint64_t out_capacity, uint64_t* out_len, uint64_t* dropped) {
 	if(!s || !t || !out || !out_len || (!in && n)) return MH_ERR_INVALID_ARG;
-	s->pending_out = 0;
+	s->pending_out = s->last_count = 0;
 	MH_CUDA(cudaSetDevice(s->device));
-	if(n > s->enc_chunk || n > s->max_input) return session_encode_chunked(s, t, in, n, out, out_capacity, out_len, dropped);
+	// A foreign table may expand the input (the reference just writes the larger file): the chunk is bounded so that
+	// chunk x longest codeword fits the compressed-side buffer, and the chunks are coded at their global bit offsets.
+	const uint64_t maxb = uint64_t(t->impl.max_code_bits() > 0 ? t->impl.max_code_bits() : 1);
+	uint64_t chunk = s->enc_chunk < s->max_input ? s->enc_chunk : s->max_input;
+	const uint64_t fit = (s->payload_cap - 64) * 8 / maxb;
+	if(chunk > fit) chunk = fit & ~uint64_t(15);
+	if(n > chunk) return session_encode_chunked(s, t, in, n, chunk, out, out_capacity, out_len, dropped);
+	if(n >= tunable_bytes(kTunPipeMinBytes, 32ull << 20)) {
+		const int prc = session_compress_pipelined(s, t, in, n, t->impl.order, out, out_capacity, out_len, dropped, nullptr);
+		if(prc != MH_ERR_WORKSPACE) return prc;
+	}
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
 	return session_encode(s, t, n, out, out_capacity, out_len, dropped);
 }
 
-// A payload larger than the session's device buffer is decoded in chunks of bit ranges: every chunk starts from the
-// exact state (bit position, previous symbol) its predecessor ended in — the decoder's shard interface with a known
-// start — and keeps 64 bytes of the stream behind its range for the codeword that straddles the end. The decoded
-// bytes leave for the host chunk by chunk; without `out` the pass only counts (nothing stays resident to fetch).
+// A payload larger than the session's device buffer — or one that decodes to more bytes than the uncompressed-side
+// buffer holds — is decoded in chunks of bit ranges: every chunk starts from the exact state (bit position, previous
+// symbol) its predecessor ended in — the decoder's shard interface with a known start — and keeps 64 bytes of the
+// stream behind its range for the codeword that straddles the end. A chunk whose symbols do not fit the buffer is
+// halved and decoded again (the session never allocates after creation). The decoded bytes leave for the host chunk
+// by chunk; without `out` the pass only counts (nothing stays resident to fetch).
 static int session_decompress_chunked(mh_session* s, const mh_table* t, const uint8_t* payload, uint64_t payload_bytes, uint64_t n_bits,
                                       uint8_t* out, uint64_t out_capacity, uint64_t* out_len) {
 	const uint64_t cap = s->payload_cap & ~uint64_t(3);
-	if(cap < 4096) return MH_ERR_CAPACITY;
+	if(cap < 4096 || s->max_input < 64) return MH_ERR_CAPACITY;
 	int rc = upload_dectable(t, &s->dec, s->stream);
 	if(rc != MH_OK) return rc;
 	uint64_t p = 0, produced = 0;
+	uint64_t limit_bits = ~uint64_t(0);   // shrinks when a chunk's symbols outgrow the uncompressed-side buffer
 	uint8_t ctx = MH_PREV0;
 	int corrupt = 0;
 	bool fits = true;
@@ -691,11 +929,12 @@ static int session_decompress_chunked(mh_session* s, const mh_table* t, const ui
 		const uint64_t b0 = (p >> 3) & ~uint64_t(3);
 		const uint32_t start_bit = uint32_t(p - 8 * b0);
 		const uint64_t load = payload_bytes - b0 < cap ? payload_bytes - b0 : cap;
-		const bool last = b0 + load >= payload_bytes;
-		const uint64_t nb = last ? n_bits - p : (load - 64) * 8 - start_bit;
+		bool last = b0 + load >= payload_bytes;
+		uint64_t nb = last ? n_bits - p : (load - 64) * 8 - start_bit;
 		MH_CUDA(cudaMemcpyAsync(s->d_payload, payload + b0, load, cudaMemcpyHostToDevice, s->stream));
 		int iters = 2;
 		for(;;) {
+			if(nb > limit_bits) { nb = limit_bits; last = false; }
 			rc = launch_decode_shard(s->d_payload, start_bit, nb, load, 1, ctx, 0, last ? 1 : 0, &s->dec, s->d_raw, s->max_input,
 			                         reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
 			if(rc != MH_OK) return rc;
@@ -703,13 +942,13 @@ static int session_decompress_chunked(mh_session* s, const mh_table* t, const ui
 			MH_CUDA(cudaStreamSynchronize(s->stream));
 			const int64_t dev_status = int64_t(s->h_result[1]);
 			if(dev_status == MH_ERR_NOT_CONVERGED && iters < (1 << 20)) { iters *= 4; continue; }
-			if(dev_status == MH_ERR_CAPACITY) {   // this chunk decodes to more than the uncompressed-side buffer holds: grow it
+			if(dev_status == MH_ERR_CAPACITY) {   // more symbols than d_raw holds: a smaller bit range, decoded again
 				const uint64_t need = s->h_result[0];
-				cudaFree(s->d_raw);
-				s->d_raw = nullptr;
-				s->max_input = 0;
-				MH_CUDA(cudaMalloc(&s->d_raw, need + 64));
-				s->max_input = need;
+				uint64_t shrunk = need ? nb / (need / s->max_input + 1) : nb / 2;   // aim below the buffer size, at least halve
+				if(shrunk > nb / 2) shrunk = nb / 2;
+				shrunk &= ~uint64_t(63);
+				if(shrunk < 512) return MH_ERR_CAPACITY;   // the buffer cannot even hold the symbols of 512 bits
+				limit_bits = shrunk;
 				continue;
 			}
 			if(dev_status != 0) return int(dev_status);
@@ -732,6 +971,7 @@ static int session_decompress_chunked(mh_session* s, const mh_table* t, const ui
 	}
 	*out_len = produced;
 	s->pending_out = 0;
+	s->last_count = produced;
 	if(out && !fits) return MH_ERR_CAPACITY;
 	return corrupt;
 }
@@ -741,42 +981,28 @@ static int session_decompress_chunked(mh_session* s, const mh_table* t, const ui
 // 2.4x larger D2H side hides both the H2D copies and the kernels. Two halves of the payload buffer and of the
 // uncompressed-side buffer alternate. Returns MH_ERR_WORKSPACE when the buffers are too small for it (the caller then
 // takes the sequential path); needs pinned host memory to actually overlap.
-static uint64_t env_bytes(const char* name, uint64_t fallback) {
-	const char* e = getenv(name);
-	if(!e) return fallback;
-	const unsigned long long v = strtoull(e, nullptr, 10);
-	return v ? uint64_t(v) : fallback;
-}
-
 static int session_decompress_pipelined(mh_session* s, const mh_table* t, const uint8_t* payload, uint64_t payload_bytes, uint64_t n_bits,
                                         uint8_t* out, uint64_t out_capacity, uint64_t* out_len) {
 	const uint64_t pay_half = (s->payload_cap / 2) & ~uint64_t(15), out_half = (s->max_input / 2) & ~uint64_t(63);
-	uint64_t chunk = env_bytes("MH_PIPE_CHUNK_BYTES", 16ull << 20) & ~uint64_t(3);   // measured best of 16, 32, 64, 128 MiB
+	uint64_t chunk = tunable_bytes(kTunPipeChunkBytes, 16ull << 20) & ~uint64_t(3);   // measured best of 16, 32, 64, 128 MiB
 	if(chunk > pay_half) chunk = pay_half & ~uint64_t(3);
 	if(chunk < 4096 || out_half < 4096) return MH_ERR_WORKSPACE;
-	if(!s->h2d) {
-		MH_CUDA(cudaStreamCreateWithFlags(&s->h2d, cudaStreamNonBlocking));
-		MH_CUDA(cudaStreamCreateWithFlags(&s->d2h, cudaStreamNonBlocking));
-		for(int i = 0; i < 2; ++i) {
-			MH_CUDA(cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming));
-			MH_CUDA(cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming));
-		}
-	}
+	int rc = ensure_pipe_streams(s);
+	if(rc != MH_OK) return rc;
 	auto geometry = [&](uint64_t base_bit, uint64_t& b0, uint64_t& load, bool& last) {   // chunk that starts (nominally) at base_bit
 		b0 = (base_bit >> 3) & ~uint64_t(3);
 		load = payload_bytes - b0 < chunk ? payload_bytes - b0 : chunk;
 		last = b0 + load >= payload_bytes;
 	};
-	auto drain = [&]() { cudaStreamSynchronize(s->h2d); cudaStreamSynchronize(s->d2h); cudaStreamSynchronize(s->stream); };
 	uint64_t base = 0, rel = 0, produced = 0, b0, load;
 	uint8_t ctx = MH_PREV0;
 	bool last;
 	int corrupt = 0;
 	geometry(0, b0, load, last);
-	MH_CUDA(cudaMemcpyAsync(s->d_payload, payload + b0, load, cudaMemcpyHostToDevice, s->h2d));
-	MH_CUDA(cudaEventRecord(s->ev_in[0], s->h2d));
-	int rc = upload_dectable(t, &s->dec, s->stream);   // flattened on the host while the first chunk is on its way
-	if(rc != MH_OK) { cudaStreamSynchronize(s->h2d); return rc; }
+	MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->d_payload, payload + b0, load, cudaMemcpyHostToDevice, s->h2d));
+	MH_CUDA_DRAIN(s, cudaEventRecord(s->ev_in[0], s->h2d));
+	rc = upload_dectable(t, &s->dec, s->stream);   // flattened on the host while the first chunk is on its way
+	if(rc != MH_OK) { drain_session(s); return rc; }
 	for(uint32_t k = 0;; ++k) {
 		const uint32_t cur = k & 1;
 		geometry(base, b0, load, last);
@@ -789,29 +1015,29 @@ static int session_decompress_pipelined(mh_session* s, const mh_table* t, const 
 			uint64_t nb0, nload;
 			bool nlast;
 			geometry(next_base, nb0, nload, nlast);
-			MH_CUDA(cudaMemcpyAsync(s->d_payload + (cur ^ 1) * pay_half, payload + nb0, nload, cudaMemcpyHostToDevice, s->h2d));
-			MH_CUDA(cudaEventRecord(s->ev_in[cur ^ 1], s->h2d));
+			MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->d_payload + (cur ^ 1) * pay_half, payload + nb0, nload, cudaMemcpyHostToDevice, s->h2d));
+			MH_CUDA_DRAIN(s, cudaEventRecord(s->ev_in[cur ^ 1], s->h2d));
 		}
-		MH_CUDA(cudaStreamWaitEvent(s->stream, s->ev_in[cur], 0));
-		if(k >= 2) MH_CUDA(cudaStreamWaitEvent(s->stream, s->ev_out[cur], 0));   // the bytes of chunk k - 2 have left this half
+		MH_CUDA_DRAIN(s, cudaStreamWaitEvent(s->stream, s->ev_in[cur], 0));
+		if(k >= 2) MH_CUDA_DRAIN(s, cudaStreamWaitEvent(s->stream, s->ev_out[cur], 0));   // the bytes of chunk k - 2 have left this half
 		int iters = 2;
 		for(;;) {
 			rc = launch_decode_shard(s->d_payload + cur * pay_half + skip, uint32_t(first & 31), nb, load - skip, 1, ctx, 0, last ? 1 : 0, &s->dec,
 			                         s->d_raw + cur * out_half, out_half, reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
-			if(rc != MH_OK) { drain(); return rc; }
-			MH_CUDA(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-			MH_CUDA(cudaStreamSynchronize(s->stream));
+			if(rc != MH_OK) { drain_session(s); return rc; }
+			MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+			MH_CUDA_DRAIN(s, cudaStreamSynchronize(s->stream));
 			const int64_t dev_status = int64_t(s->h_result[1]);
 			if(dev_status == MH_ERR_NOT_CONVERGED && iters < (1 << 20)) { iters *= 4; continue; }
-			if(dev_status == MH_ERR_CAPACITY) { drain(); return MH_ERR_WORKSPACE; }   // a chunk outgrew its half: sequential path
-			if(dev_status != 0) { drain(); return int(dev_status); }
+			if(dev_status == MH_ERR_CAPACITY) { drain_session(s); return MH_ERR_WORKSPACE; }   // a chunk outgrew its half: sequential path
+			if(dev_status != 0) { drain_session(s); return int(dev_status); }
 			break;
 		}
 		const uint64_t count = s->h_result[0];
 		if(int64_t(s->h_result[2]) != 0) corrupt = int(int64_t(s->h_result[2]));
-		if(produced + count > out_capacity) { drain(); *out_len = produced + count; return MH_ERR_CAPACITY; }
-		if(count) MH_CUDA(cudaMemcpyAsync(out + produced, s->d_raw + cur * out_half, count, cudaMemcpyDeviceToHost, s->d2h));
-		MH_CUDA(cudaEventRecord(s->ev_out[cur], s->d2h));
+		if(produced + count > out_capacity) { drain_session(s); return MH_ERR_WORKSPACE; }   // the sequential path reports the size needed
+		if(count) MH_CUDA_DRAIN(s, cudaMemcpyAsync(out + produced, s->d_raw + cur * out_half, count, cudaMemcpyDeviceToHost, s->d2h));
+		MH_CUDA_DRAIN(s, cudaEventRecord(s->ev_out[cur], s->d2h));
 		produced += count;
 		if(last) break;
 		const uint32_t end = uint32_t(s->h_result[3] & 0xffffffffull);
@@ -819,9 +1045,10 @@ static int session_decompress_pipelined(mh_session* s, const mh_table* t, const 
 		ctx = uint8_t(end & 255u);
 		base = next_base;
 	}
-	drain();
+	drain_session(s);
 	*out_len = produced;
 	s->pending_out = 0;
+	s->last_count = produced;
 	return corrupt;
 }
 
@@ -837,20 +1064,18 @@ int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* strea
 	// src/coding.cpp:115 in 64-bit; a negative length makes the reference's loop (:124) decode nothing
 	const uint64_t n_bits = payload_bytes * 8 < remainder ? 0 : payload_bytes * 8 - remainder;
 	MH_CUDA(cudaSetDevice(s->device));
-	if(out && payload_bytes >= env_bytes("MH_PIPE_MIN_BYTES", 32ull << 20)) {   // large and wanted on the host: overlap the copies
-		s->pending_out = 0;
+	s->pending_out = s->last_count = 0;
+	if(out && payload_bytes >= tunable_bytes(kTunPipeMinBytes, 32ull << 20)) {   // large and wanted on the host: overlap the copies
 		const int prc = session_decompress_pipelined(s, t, stream + 1, payload_bytes, n_bits, out, out_capacity, out_len);
 		if(prc != MH_ERR_WORKSPACE) return prc;
+		s->pending_out = s->last_count = 0;
 	}
-	if(payload_bytes > s->payload_cap) {   // larger than the device buffer: decode it in chunks
-		s->pending_out = 0;
+	if(payload_bytes > s->payload_cap)   // larger than the device buffer: decode it in chunks
 		return session_decompress_chunked(s, t, stream + 1, payload_bytes, n_bits, out, out_capacity, out_len);
-	}
 	int rc = upload_dectable(t, &s->dec, s->stream);
 	if(rc != MH_OK) return rc;
 	if(payload_bytes) MH_CUDA(cudaMemcpyAsync(s->d_payload, stream + 1, payload_bytes, cudaMemcpyHostToDevice, s->stream));
 	int iters = 2;
-	s->pending_out = 0;
 	for(;;) {
 		rc = launch_decode(s->d_payload, 0, n_bits, MH_PREV0, &s->dec, s->d_raw, s->max_input,
 		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream, iters);
@@ -859,19 +1084,19 @@ int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* strea
 		MH_CUDA(cudaStreamSynchronize(s->stream));
 		const int64_t dev_status = int64_t(s->h_result[1]);
 		if(dev_status == MH_ERR_NOT_CONVERGED && iters < (1 << 20)) { iters *= 4; continue; }   // pathological seams: keep fixing
-		if(dev_status == MH_ERR_CAPACITY) {
-			// the decoded size is only known after the count pass: grow the device buffer to fit and decode again
-			const uint64_t need = s->h_result[0];
-			cudaFree(s->d_raw);
-			s->d_raw = nullptr;
-			s->max_input = 0;
-			MH_CUDA(cudaMalloc(&s->d_raw, need + 64));
-			s->max_input = need;
-			continue;
-		}
 		break;
 	}
-	*out_len = s->h_result[0];
+	if(int64_t(s->h_result[1]) == MH_ERR_CAPACITY) {
+		// The decoded size is only known after the count pass, and it exceeds the uncompressed-side buffer. The session
+		// does not reallocate: the stream is decoded in bit-range chunks that fit, and the bytes leave chunk by chunk.
+		// Without `out` this only reports the size (mh_session_fetch then answers MH_ERR_WORKSPACE: call again with out).
+		if(!out) {
+			*out_len = s->last_count = s->h_result[0];
+			return MH_OK;
+		}
+		return session_decompress_chunked(s, t, stream + 1, payload_bytes, n_bits, out, out_capacity, out_len);
+	}
+	*out_len = s->last_count = s->h_result[0];
 	if(int64_t(s->h_result[1]) != 0) return int(int64_t(s->h_result[1]));
 	s->pending_out = s->h_result[0];
 	const int corrupt = int(int64_t(s->h_result[2]));   // bytes are delivered, like the reference, but flagged
@@ -881,7 +1106,12 @@ int mh_session_decompress(mh_session* s, const mh_table* t, const uint8_t* strea
 }
 
 int mh_session_fetch(mh_session* s, uint8_t* out, uint64_t out_capacity, uint64_t* out_len) {
-	if(!s || !out_len || (!out && s->pending_out)) return MH_ERR_INVALID_ARG;
+	if(!s || !out_len) return MH_ERR_INVALID_ARG;
+	if(s->pending_out == 0 && s->last_count != 0) {   // decoded in chunks: counted, but nothing stayed on the device
+		*out_len = 0;
+		return MH_ERR_WORKSPACE;
+	}
+	if(!out && s->pending_out) return MH_ERR_INVALID_ARG;
 	*out_len = s->pending_out;
 	if(s->pending_out > out_capacity) return MH_ERR_CAPACITY;
 	MH_CUDA(cudaSetDevice(s->device));

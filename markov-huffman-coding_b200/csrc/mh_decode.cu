@@ -929,8 +929,8 @@ __global__ void __launch_bounds__(PAIR ? kDecWriteMaxThreads : kDecThreads, 1) d
 }  // namespace
 
 static uint32_t decode_write_threads() {
-	const char* env = getenv("MH_DEC_WRITE_THREADS");   // experiments
-	const int v = env ? atoi(env) : kDecWriteMaxThreads;
+	const long long t = tunable(kTunDecWriteThreads);   // experiments
+	const int v = t > 0 ? int(t) : kDecWriteMaxThreads;
 	return (v >= 64 && v <= kDecWriteMaxThreads && v % 32 == 0) ? uint32_t(v) : uint32_t(kDecWriteMaxThreads);
 }
 
@@ -938,12 +938,9 @@ uint32_t decode_sub_bits(int order, uint64_t n_bits) {
 	// Subsequence size. Longer subsequences amortise the self-synchronisation overlap (Markov streams re-synchronise
 	// ~10x slower than plain Huffman streams) but there must be enough of them to fill the machine:
 	// the largest candidate that still yields kDecTargetSubs subsequences, else the smallest.
-	// The environment override exists for experiments and tests.
-	const char* env = getenv(order ? "MH_DEC_SUB_BITS_MARKOV" : "MH_DEC_SUB_BITS_HUFFMAN");
-	if(env) {
-		const int v = atoi(env);
-		if(v >= kDecMinSubBits && v % 256 == 0 && v <= (1 << 16)) return uint32_t(v);
-	}
+	// The tunable override exists for experiments and tests.
+	const long long v = tunable(order ? kTunDecSubBitsMarkov : kTunDecSubBitsHuffman);
+	if(v >= kDecMinSubBits && v % 256 == 0 && v <= (1 << 16)) return uint32_t(v);
 	const uint32_t largest = order ? kDecMaxSubBitsMarkov : kDecMaxSubBitsHuffman;
 	const uint32_t smallest = order ? 1024u : 512u;
 	uint32_t sub = largest;
@@ -977,13 +974,12 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	if(n_subs > ws->dec_subs_cap || chunks64 > ws->dec_chunks_cap) return MH_ERR_WORKSPACE;
 	const uint32_t n_chunks = uint32_t(chunks64);
 	const size_t lut_bytes = PAIR ? size_t(pair_table_bytes(dt->pair_rows, dt->pair_ctx_rows)) : (ORDER ? 65536 * 2 : 256 * 2);
-	static bool attr_done = false;
-	if(!attr_done) {
+	static std::atomic<uint64_t> attr_done{0};   // one per template instantiation, one bit per device
+	if(first_use_on_device(attr_done)) {
 		const int ring_bytes = kDecThreads * int(kRingBytesPerThread);
 		MH_CUDA(cudaFuncSetAttribute(dec_sync_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (PAIR ? kDecPairBytes : int(lut_bytes)) + ring_bytes));
 		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                             PAIR ? max_smem_optin() - 1024 : int(lut_bytes) + ring_bytes));   // pair path: the launcher fits the thread count
-		attr_done = true;
 	}
 	const int sms = sm_count();
 	const uint32_t grid = n_chunks < uint32_t(sms) ? n_chunks : uint32_t(sms);
@@ -1035,12 +1031,11 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	return MH_OK;
 }
 
-// The pair table is used whenever it exists (<= 63 live contexts); MH_DEC_PAIR=0 forces the u16 LUT (tests, experiments).
+// The pair table is used whenever it exists (<= 63 live contexts); the tunable dec_pair = 0 forces the u16 LUT (tests, experiments).
 int dispatch_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, uint32_t skip_subs, uint32_t stream_end,
                     const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws,
                     cudaStream_t st, int fix_iters, uint32_t sub_bits) {
-	const char* env = getenv("MH_DEC_PAIR");
-	const bool pair = dt->pair_rows != 0 && !(env && atoi(env) == 0);
+	const bool pair = dt->pair_rows != 0 && tunable(kTunDecPair) != 0;
 	if(dt->order) {
 		if(pair) return run_decode<1, true>(words, n_bits, buf_bytes, start0, skip_subs, stream_end, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);
 		return run_decode<1, false>(words, n_bits, buf_bytes, start0, skip_subs, stream_end, dt, d_out, out_capacity, d_result, ws, st, fix_iters, sub_bits);

@@ -651,8 +651,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 
 	// table format
 	const int maxb = cb->max_bits > 0 ? cb->max_bits : 1;
-	const char* fmt_env = getenv("MH_ENC_FMT");   // experiments / tests: force a table format (1: box in global, 2: wide)
-	const int force_fmt = fmt_env ? atoi(fmt_env) : -1;
+	const int force_fmt = int(tunable(kTunEncFmt));   // experiments / tests: force a table format (0: box in shared memory, 1: box in global, 2: wide)
 	int fmt = FMT_WIDE;
 	size_t table_bytes = 0;
 	if(cb->has_box && force_fmt != FMT_WIDE) {

@@ -150,6 +150,11 @@ __device__ __forceinline__ uint32_t lane_tally16(const uint4 v, uint32_t prev, u
 	return acc;
 }
 
+template <int THREADS>
+__device__ __forceinline__ void hist_box_body(const uint8_t* __restrict__ in, uint64_t n, uint32_t prev0,
+                                              unsigned long long* __restrict__ counts, const uint32_t* __restrict__ params,
+                                              uint32_t smem_words, uint32_t* sh);
+
 __global__ void __launch_bounds__(kLaneThreads, 1) hist_lane_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t prev0,
                                                                      unsigned long long* __restrict__ counts,
                                                                      const uint32_t* __restrict__ params) {
@@ -170,7 +175,10 @@ __global__ void __launch_bounds__(kLaneThreads, 1) hist_lane_kernel(const uint8_
 	}
 	__syncthreads();
 	const LanePlan P = s_plan;
-	if(P.mode == 0) return;   // hist_kernel<1> counts this input
+	if(P.mode == 0) {   // alphabet too large for lane-private bins: the R x R box path, in this same launch
+		hist_box_body<kLaneThreads>(in, n, prev0, counts, params, kLaneSmemBytes / 4, sh);
+		return;
+	}
 	const bool pack16 = P.mode == 1;
 	const uint32_t K = P.K, K1 = K + 1;
 	const uint32_t row_bytes = pack16 ? (P.pitch / 2) * 128u : K1 * P.S * 4u;
@@ -337,21 +345,21 @@ __global__ void __launch_bounds__(kLaneThreads, 2) hist0_lane_kernel(const uint8
 	}
 }
 
-template <int ORDER>
-__global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint8_t* __restrict__ in, uint64_t n, uint32_t prev0,
-                                                             unsigned long long* __restrict__ counts,
-                                                             const uint32_t* __restrict__ params, uint32_t smem_words) {
-	extern __shared__ uint32_t sh[];
+// The general box path, called by hist_lane_kernel when the alphabet is too large for lane-private bins (all
+// threads of the CTA enter; `sh` is the CTA's dynamic shared memory of smem_words words).
+template <int THREADS>
+__device__ __forceinline__ void hist_box_body(const uint8_t* __restrict__ in, uint64_t n, uint32_t prev0,
+                                              unsigned long long* __restrict__ counts, const uint32_t* __restrict__ params,
+                                              uint32_t smem_words, uint32_t* sh) {
+	constexpr int ORDER = 1;
+	constexpr int kHistThreads = THREADS;
 	__shared__ uint32_t s_plan[3];
-	if(ORDER) {
-		if(lane_plan(params).mode != 0) return;   // hist_lane_kernel counted this input
-		if(threadIdx.x == 0) hist_plan(params, smem_words, s_plan[0], s_plan[1], s_plan[2]);
-		__syncthreads();
-	}
-	const uint32_t lo = ORDER ? s_plan[0] : 0u;
-	const uint32_t R = ORDER ? s_plan[1] : 256u;
-	const uint32_t reps = ORDER ? s_plan[2] : uint32_t(kHistWarps);
-	const uint32_t box = ORDER ? R * R : 256u;
+	if(threadIdx.x == 0) hist_plan(params, smem_words, s_plan[0], s_plan[1], s_plan[2]);
+	__syncthreads();
+	const uint32_t lo = s_plan[0];
+	const uint32_t R = s_plan[1];
+	const uint32_t reps = s_plan[2];
+	const uint32_t box = R * R;
 	for(uint32_t i = threadIdx.x; i < reps * box; i += kHistThreads) sh[i] = 0;
 	__syncthreads();
 	uint32_t* mine = sh + ((threadIdx.x >> 5) % reps) * box;
@@ -415,12 +423,14 @@ __global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint8_t* __res
 
 }  // namespace
 
+static std::atomic<uint64_t> g_hist_attr_done{0};
+
 int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, unsigned long long* d_counts,
-                     mh_workspace* ws, cudaStream_t st) {
+                     mh_workspace* ws, cudaStream_t st, bool accumulate) {
 	if(order != 0 && order != 1) return MH_ERR_INVALID_ARG;
 	if(!d_counts || (!d_in && n)) return MH_ERR_INVALID_ARG;
 	if(!ws || !ws->hist_params) return MH_ERR_WORKSPACE;
-	MH_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (order ? 65536 : 256), st));
+	if(!accumulate) MH_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * (order ? 65536 : 256), st));
 	if(n == 0) return MH_OK;
 	// each CTA counts in u32: keep a CTA's share below 2^32 samples
 	const int sms = sm_count();
@@ -433,28 +443,20 @@ int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, 
 		return unsigned(grid);
 	};
 	if(order) {
-		const uint32_t smem_bytes = 100 * 1024;
-		static bool attr_done = false;
-		if(!attr_done) {
-			MH_CUDA(cudaFuncSetAttribute(hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
+		if(first_use_on_device(g_hist_attr_done))
 			MH_CUDA(cudaFuncSetAttribute(hist_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLaneSmemBytes)));
-			attr_done = true;
-		}
 		{
 			MH_CUDA(cudaMemsetAsync(ws->hist_params, 0, 8 * sizeof(uint32_t), st));
 			ProfScope p("hist_probe_kernel", st);
 			hist_probe_kernel<<<kProbeWindows, kProbeThreads, 0, st>>>(d_in, n, ws->hist_params);
 		}
-		// Both counting kernels derive the same plan from the probe's bitmap; exactly one of them does the work.
+		// One counting kernel: it derives its plan (lane-private bins, or the R x R box for large alphabets) from the
+		// probe's bitmap on the device, so no host round trip sits between the probe and the count.
 		{
 			ProfScope p("hist_lane_kernel", st);
 			hist_lane_kernel<<<grid_for(kLaneThreads, 1), kLaneThreads, kLaneSmemBytes, st>>>(d_in, n, prev0, d_counts, ws->hist_params);
 		}
-		{
-			ProfScope p("hist_kernel<1>", st);
-			hist_kernel<1><<<grid_for(kHistThreads, 2), kHistThreads, smem_bytes, st>>>(d_in, n, prev0, d_counts, ws->hist_params, smem_bytes / 4);
-		}
-		count_launch(3);
+		count_launch(2);
 	} else {
 		ProfScope p("hist0_lane_kernel", st);
 		hist0_lane_kernel<<<grid_for(kLaneThreads, 2), kLaneThreads, 0, st>>>(d_in, n, d_counts);

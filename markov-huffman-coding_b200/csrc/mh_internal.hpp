@@ -20,6 +20,7 @@ struct ProfScope {
 	~ProfScope();
 	int slot;
 	cudaStream_t st;
+	cudaEvent_t end = nullptr;
 };
 
 int cuda_fail(cudaError_t e, const char* what);   // records mh_last_error(), returns MH_ERR_CUDA
@@ -29,8 +30,17 @@ int cuda_fail(cudaError_t e, const char* what);   // records mh_last_error(), re
 		if(e_ != cudaSuccess) return ::mh::cuda_fail(e_, #call);   \
 	} while(0)
 
-int sm_count();          // multiprocessors of the current device (cached)
-int max_smem_optin();    // bytes of opt-in dynamic shared memory per block (cached)
+int sm_count();          // multiprocessors of the CURRENT device (cached per device)
+int max_smem_optin();    // bytes of opt-in dynamic shared memory per block on the current device (cached per device)
+// Function attributes (opt-in shared memory) are per device: true exactly once per (mask, current device).
+bool first_use_on_device(std::atomic<uint64_t>& done_mask);
+
+// Tunables: experiment / test overrides. Read from the environment ONCE when the library is loaded (MH_ENC_FMT,
+// MH_DEC_SUB_BITS_MARKOV, MH_DEC_SUB_BITS_HUFFMAN, MH_DEC_PAIR, MH_DEC_WRITE_THREADS, MH_PIPE_MIN_BYTES,
+// MH_PIPE_CHUNK_BYTES); afterwards only mh_tunable_set changes them. -1 = the documented default.
+enum Tunable { kTunEncFmt = 0, kTunDecSubBitsMarkov, kTunDecSubBitsHuffman, kTunDecPair, kTunDecWriteThreads, kTunPipeMinBytes,
+               kTunPipeChunkBytes, kTunEncPipeChunkBytes, kTunDecFused, kTunCount };
+long long tunable(Tunable t);
 
 // ---- tunables (env overrides exist for experiments; defaults are what DESIGN.md documents) ------------
 constexpr int kEncThreads = 480;                      // worker threads per CTA: a tile is kEncThreads x SPT input bytes
@@ -110,8 +120,9 @@ struct mh_dectable {
 
 namespace mh {
 
+// accumulate: add to d_counts instead of overwriting it (chunked inputs: the counts of the chunks add up)
 int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, unsigned long long* d_counts,
-                     mh_workspace* ws, cudaStream_t st);
+                     mh_workspace* ws, cudaStream_t st, bool accumulate = false);
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
                   uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st);
 int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,

@@ -33,6 +33,20 @@ def sha(b):
     return hashlib.sha256(b).hexdigest()
 
 
+@pytest.fixture
+def tunables():
+    """Set library tunables for one test (mh_tunable_set); everything goes back to its default afterwards."""
+    touched = []
+
+    def set_(name, value):
+        touched.append(name)
+        mh.tunable_set(name, int(value))
+
+    yield set_
+    for name in touched:
+        mh.tunable_set(name, -1)
+
+
 # ---- config 1: the reference's own corpus, -d then -x, both modes ---------------------------------------
 @pytest.mark.parametrize("case", CASES, ids=IDS)
 def test_corpus_compress_matches_reference_bytes(session, case):
@@ -170,24 +184,24 @@ def test_single_symbol_contexts(session):
 
 
 @pytest.mark.parametrize("fmt", ["1", "2"])
-def test_encoder_table_formats_agree(session, ipsum_counts, fmt, monkeypatch):
+def test_encoder_table_formats_agree(session, ipsum_counts, fmt, tunables):
     """The encoder picks a table format from the codebook (u32 box in shared memory / u32 box in global memory /
     u64 wide entries). Force the two fallbacks on data that would normally take the first."""
     data = o.synth_markov(ipsum_counts, 5, 65536, 0, (3 << 20) + 77)
     want = {order: o.compress_from_input(data, bool(order))[0] for order in (0, 1)}
-    monkeypatch.setenv("MH_ENC_FMT", fmt)
+    tunables("enc_fmt", fmt)
     for order in (0, 1):
         assert session.compress(data, order)[0] == want[order]
 
 
 @pytest.mark.parametrize("pair", ["1", "0"], ids=["pair-table", "lut8"])
 @pytest.mark.parametrize("sub_bits", ["256", "1024", "8192"])
-def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, pair, monkeypatch):
+def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, pair, tunables):
     """The subsequence size only changes how the work is cut, never the bytes — through the two-symbol pair table
     (text has few live contexts) and, forced, through the reference's 8-bit LUT + tree walk."""
-    monkeypatch.setenv("MH_DEC_SUB_BITS_MARKOV", sub_bits)
-    monkeypatch.setenv("MH_DEC_SUB_BITS_HUFFMAN", sub_bits)
-    monkeypatch.setenv("MH_DEC_PAIR", pair)
+    tunables("dec_sub_bits_markov", sub_bits)
+    tunables("dec_sub_bits_huffman", sub_bits)
+    tunables("dec_pair", pair)
     s = mh.Session(8 << 20)
     try:
         text = o.synth_markov(ipsum_counts, 9, 4096, 0, (2 << 20) + 123)
@@ -227,11 +241,11 @@ def test_session_streams_inputs_larger_than_its_buffer(ipsum_counts, order, kind
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("chunk", ["4096", "20000", "65536", "1000000"])
-def test_pipelined_extract_into_a_host_buffer(ipsum_counts, chunk, monkeypatch):
+def test_pipelined_extract_into_a_host_buffer(ipsum_counts, chunk, tunables):
     """Extraction straight into a host buffer runs as a pipeline of bit-range chunks (H2D of chunk k + 1, decode of k and
     D2H of k - 1 overlap): the bytes do not depend on where the chunks are cut."""
-    monkeypatch.setenv("MH_PIPE_MIN_BYTES", "1")
-    monkeypatch.setenv("MH_PIPE_CHUNK_BYTES", chunk)
+    tunables("pipe_min_bytes", 1)
+    tunables("pipe_chunk_bytes", chunk)
     s = mh.Session(3 << 20)
     try:
         for data in (o.synth_markov(ipsum_counts, 21, 4096, 0, (1 << 20) + 4321), o.synth_fibonacci(40, 48, 7, 0, 600_001)):
@@ -243,3 +257,53 @@ def test_pipelined_extract_into_a_host_buffer(ipsum_counts, chunk, monkeypatch):
                 assert e.value.status == mh.MH_ERR_CAPACITY
     finally:
         s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", ["4096", "50000", "262144", "1048576"])
+def test_pipelined_compress_from_a_host_buffer(ipsum_counts, chunk, tunables):
+    """Compression of a large host buffer runs as a pipeline: the input travels in chunks while the histogram of the chunk
+    before it runs (counts accumulate on the device), then the chunks are encoded at their global bit offsets while the
+    payload of the chunk before travels back; bytes shared by two chunks are OR-merged. Same bytes as one pass, wherever
+    the chunks are cut, with a built table and with a given one (-e)."""
+    tunables("pipe_min_bytes", 1)
+    tunables("enc_pipe_chunk_bytes", chunk)
+    s = mh.Session(3 << 20)
+    try:
+        for data in (o.synth_markov(ipsum_counts, 23, 4096, 0, (1 << 20) + 4321), o.synth_fibonacci(40, 48, 8, 0, 600_001), b"", b"x"):
+            for order in (1, 0):
+                want_stream, want_table = o.compress_from_input(data, bool(order))
+                stream, provider = s.compress(data, order)
+                assert stream == want_stream
+                assert provider.write_coding_tree() == want_table
+                again, dropped = s.compress_with_table(provider, data)
+                assert again == want_stream and dropped == 0
+    finally:
+        s.close()
+
+
+@pytest.mark.gpu
+def test_extract_larger_than_the_uncompressed_side_buffer(ipsum_counts):
+    """The session never reallocates: a stream that decodes to more bytes than its uncompressed-side buffer holds is
+    decoded in bit-range chunks that fit (halved until they do). The size query reports the size, mh_session_fetch
+    answers MH_ERR_WORKSPACE (nothing resident), the call with a host buffer delivers the bytes."""
+    import ctypes
+    data = b"a" * 3_000_000 + o.synth_markov(ipsum_counts, 31, 4096, 0, 500_000)   # ~1 bit per symbol, then text
+    big = mh.Session(4 << 20)
+    stream, provider = big.compress(data, 1)
+    big.close()
+    assert len(stream) < 700_000
+    h = ctypes.c_void_p()
+    assert mh._lib.mh_session_create_sized(0, 300_000, len(stream) + 64, ctypes.byref(h)) == 0
+    try:
+        src = np.frombuffer(stream, dtype=np.uint8)
+        n = ctypes.c_uint64(0)
+        assert mh._lib.mh_session_decompress(h, provider._h, src.ctypes.data, src.size, None, 0, ctypes.byref(n)) == 0
+        assert n.value == len(data)
+        out = np.zeros(len(data), dtype=np.uint8)
+        got = ctypes.c_uint64(1)
+        assert mh._lib.mh_session_fetch(h, out.ctypes.data, out.size, ctypes.byref(got)) == mh.MH_ERR_WORKSPACE and got.value == 0
+        assert mh._lib.mh_session_decompress(h, provider._h, src.ctypes.data, src.size, out.ctypes.data, out.size, ctypes.byref(n)) == 0
+        assert n.value == len(data) and out.tobytes() == data
+    finally:
+        mh._lib.mh_session_destroy(h)
