@@ -198,6 +198,71 @@ int mh_session_fetch(mh_session* s, uint8_t* out, uint64_t out_capacity, uint64_
 int mh_session_histogram(mh_session* s, const uint8_t* in, uint64_t n, int order, uint64_t* counts);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * ONE logical stream over several GPUs: what a multi-GPU host driver binds in place of the callers of
+ * compress / decompress (src/main.cpp:204-212). One host thread or process per GPU, each with its own mh_comm; every
+ * rank makes the same mh_sharded_* calls (they are collective). The transport is NCCL over NVLink / NVSwitch
+ * (libnccl.so.2, loaded at run time) or, for ranks inside one process, an in-process transport.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct mh_comm mh_comm;
+#define MH_COMM_ID_BYTES 128
+#define MH_MAX_SHARDS 64
+int mh_comm_available(void);                        /* 1 when NCCL could be loaded */
+/* One process per GPU: rank 0 makes an id, the caller hands it to every rank (its own bootstrap: MPI, a file, torch). */
+int mh_comm_unique_id(uint8_t id[MH_COMM_ID_BYTES]);
+int mh_comm_create(int device, int rank, int world, const uint8_t id[MH_COMM_ID_BYTES], mh_comm** out);
+/* One process, `world` ranks on devices[r] (NULL: rank r on device r mod device count); out[world]. use_nccl: 0 the
+ * in-process transport (several ranks may then share a device), 1 NCCL when every rank has its own device and NCCL
+ * loads, else in-process, 2 NCCL or fail. Every rank's calls must then come from its own host thread. */
+int mh_comm_create_local(int world, const int* devices, int use_nccl, mh_comm** out);
+int mh_comm_rank(const mh_comm* c);
+int mh_comm_world(const mh_comm* c);
+int mh_comm_device(const mh_comm* c);
+int mh_comm_transport(const mh_comm* c);            /* 0 none (world 1), 1 NCCL, 2 in-process */
+void mh_comm_destroy(mh_comm* c);
+/* Size the rank's scratch for shards up to max_shard_bytes / payloads up to max_payload_bytes ahead of time; the
+ * mh_sharded_* calls do this themselves on first use and allocate nothing afterwards. */
+int mh_comm_reserve(mh_comm* c, uint64_t max_shard_bytes, uint64_t max_payload_bytes);
+/* Accumulated per-rank timings in microseconds: [0] histogram all-gather, [1] halo all-gather, [2] seam all-gather
+ * (device time on the stream, waiting for the slowest rank included), [3] host tree build, [4] host codebook flatten +
+ * upload, [5] host decode-table flatten + upload, [6] extra seam rounds, [7] calls. reset != 0 clears them. */
+int mh_comm_stats(mh_comm* c, double* out, int n, int reset);
+
+typedef struct mh_shard_layout {            /* how one stream is cut into `world` shards */
+	int world, order;
+	int exact;                              /* cuts are codeword boundaries and prev0[] is known (what compress produces) */
+	uint64_t total_bits;                    /* payload bits of the whole stream */
+	uint64_t dropped;                       /* this rank's symbols without a codeword (src/coding.cpp:72) */
+	uint64_t bit_base[MH_MAX_SHARDS];       /* global bit offset of each shard's first bit */
+	uint64_t n_bits[MH_MAX_SHARDS];
+	uint8_t prev0[MH_MAX_SHARDS];           /* the byte before each shard's first symbol */
+} mh_shard_layout;
+
+/* A rank's local buffer holds its payload at d_local + mh_shard_payload_offset(), first bit at bit (bit_base & 7) of
+ * that byte, with room in front and behind for the neighbours' halos; it needs mh_shard_local_bytes(payload bytes),
+ * 16-byte aligned. The whole stream is the shards' payloads concatenated at their bit offsets (seam bytes OR-merged),
+ * after the header byte 0 0 1 1 E R R R. */
+uint64_t mh_shard_local_bytes(uint64_t max_payload_bytes);
+uint32_t mh_shard_payload_offset(void);
+
+/* Collective. Rank r holds bytes d_in[0..n) of the logical input (device memory; byte ranges in rank order). Builds the
+ * global table (identical on every rank; *table_out optional, the caller destroys it), encodes the shard at its global
+ * bit offset into d_local and fills *layout. One all-gather (the histograms) and one host round trip (the tree build)
+ * sit between the histogram and the encoder. prepare_decode != 0 also flattens the decoder's tables for this table
+ * while the encoder runs. */
+int mh_sharded_compress(mh_comm* c, const uint8_t* d_in, uint64_t n, int order, uint8_t* d_local, uint64_t local_cap,
+                        mh_shard_layout* layout, mh_table** table_out, int prepare_decode, mh_stream_t stream);
+/* Collective. Decodes this rank's bit range [bit_base[r], bit_base[r] + n_bits[r]) of the logical stream to d_out.
+ * speculative == 0: the layout is exact (codeword boundaries, known contexts): every rank decodes from its known state.
+ * speculative != 0: the cuts are treated as arbitrary, as for a stream without an index: neighbours exchange a halo
+ * (one all-gather), every rank but the first starts MH_DECODE_WARM_UNIT bits before its range from a guessed state, and
+ * the ranks all-gather their seam states; a rank whose warm-up did not reach its predecessor's end state decodes again
+ * from exactly that state. The codeword that straddles a cut belongs to the earlier shard. *n_out = symbols this rank
+ * wrote, *out_offset (optional) = symbols of the ranks before it. d_local is modified (the halos are spliced in). */
+int mh_sharded_decompress(mh_comm* c, const mh_table* t, uint8_t* d_local, uint64_t local_cap, const mh_shard_layout* layout,
+                          int speculative, uint8_t* d_out, uint64_t out_capacity, uint64_t* n_out, uint64_t* out_offset,
+                          mh_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Synthetic workloads of the benchmark configs; not part of the reference. Byte-identical to
  * the oracle's generators (oracle/mh_oracle.c) so the CPU baseline can be fed the same data.
  * ------------------------------------------------------------------------------------------------------- */

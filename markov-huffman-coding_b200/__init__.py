@@ -100,6 +100,21 @@ _SIGNATURES = {
     "mh_session_histogram": (_i, [_vp, _vp, _u64, _i, _vp]),
     "mh_synth_markov": (_i, [_vp, _u64, _u64, _u64, _vp, _u64, _vp]),
     "mh_synth_fibonacci": (_i, [_i, _u8, _u64, _u64, _vp, _u64, _vp]),
+    "mh_comm_available": (_i, []),
+    "mh_comm_unique_id": (_i, [_vp]),
+    "mh_comm_create": (_i, [_i, _i, _i, _vp, _pp]),
+    "mh_comm_create_local": (_i, [_i, _vp, _i, _pp]),
+    "mh_comm_rank": (_i, [_vp]),
+    "mh_comm_world": (_i, [_vp]),
+    "mh_comm_device": (_i, [_vp]),
+    "mh_comm_transport": (_i, [_vp]),
+    "mh_comm_destroy": (None, [_vp]),
+    "mh_comm_reserve": (_i, [_vp, _u64, _u64]),
+    "mh_comm_stats": (_i, [_vp, _vp, _i, _i]),
+    "mh_shard_local_bytes": (_u64, [_u64]),
+    "mh_shard_payload_offset": (ctypes.c_uint32, []),
+    "mh_sharded_compress": (_i, [_vp, _vp, _u64, _i, _vp, _u64, _vp, _pp, _i, _vp]),
+    "mh_sharded_decompress": (_i, [_vp, _vp, _vp, _u64, _vp, _i, _vp, _u64, _pu64, _pu64, _vp]),
     "mh_kernel_launches": (_u64, []),
     "mh_profile_enable": (_i, [_i]),
     "mh_profile_report": (_i, [_vp, _sz, _psz]),
@@ -467,3 +482,92 @@ def gpu_decode_shard(d_bits, start_bit, n_bits, buf_bytes, exact_start, prev0, w
 
 def decode_subsequence_bits(order, n_bits):
     return _lib.mh_decode_subsequence_bits(int(order), int(n_bits))
+
+
+# ---- one logical stream over several GPUs (mh_comm_* / mh_sharded_*) ------------------------------------------
+MAX_SHARDS = 64
+COMM_ID_BYTES = 128
+STAT_NAMES = ("gather_us", "halo_us", "seam_us", "trees_us", "codebook_us", "dectable_us", "seam_rounds", "calls")
+
+
+class ShardLayout(ctypes.Structure):
+    """mh_shard_layout: how one stream is cut into `world` shards."""
+    _fields_ = [("world", ctypes.c_int), ("order", ctypes.c_int), ("exact", ctypes.c_int), ("total_bits", ctypes.c_uint64),
+                ("dropped", ctypes.c_uint64), ("bit_base", ctypes.c_uint64 * MAX_SHARDS), ("n_bits", ctypes.c_uint64 * MAX_SHARDS),
+                ("prev0", ctypes.c_uint8 * MAX_SHARDS)]
+
+
+def comm_available():
+    return bool(_lib.mh_comm_available())
+
+
+def comm_unique_id():
+    buf = (ctypes.c_uint8 * COMM_ID_BYTES)()
+    _check(_lib.mh_comm_unique_id(buf), "mh_comm_unique_id")
+    return bytes(buf)
+
+
+def shard_local_bytes(max_payload_bytes):
+    return _lib.mh_shard_local_bytes(int(max_payload_bytes))
+
+
+def shard_payload_offset():
+    return _lib.mh_shard_payload_offset()
+
+
+class Comm:
+    """One rank of a multi-GPU group (mh_comm). Every rank makes the same compress / decompress calls."""
+
+    def __init__(self, handle):
+        self._h = ctypes.c_void_p(handle)
+
+    @classmethod
+    def create(cls, device, rank, world, unique_id):
+        """One process per GPU: `unique_id` comes from rank 0's comm_unique_id(), handed round by the caller."""
+        out = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * COMM_ID_BYTES).from_buffer_copy(unique_id) if unique_id else None
+        _check(_lib.mh_comm_create(int(device), int(rank), int(world), buf, ctypes.byref(out)), "mh_comm_create")
+        return cls(out.value)
+
+    @classmethod
+    def create_local(cls, world, devices=None, use_nccl=1):
+        """`world` ranks inside this process (each must then be driven by its own thread)."""
+        out = (ctypes.c_void_p * world)()
+        devs = (ctypes.c_int * world)(*devices) if devices is not None else None
+        _check(_lib.mh_comm_create_local(int(world), devs, int(use_nccl), out), "mh_comm_create_local")
+        return [cls(h) for h in out]
+
+    rank = property(lambda self: _lib.mh_comm_rank(self._h))
+    world = property(lambda self: _lib.mh_comm_world(self._h))
+    device = property(lambda self: _lib.mh_comm_device(self._h))
+    transport = property(lambda self: ("none", "nccl", "in-process")[_lib.mh_comm_transport(self._h)])
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.mh_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reserve(self, max_shard_bytes, max_payload_bytes):
+        _check(_lib.mh_comm_reserve(self._h, int(max_shard_bytes), int(max_payload_bytes)), "mh_comm_reserve")
+
+    def stats(self, reset=False):
+        buf = (ctypes.c_double * len(STAT_NAMES))()
+        _check(_lib.mh_comm_stats(self._h, buf, len(STAT_NAMES), 1 if reset else 0), "mh_comm_stats")
+        return dict(zip(STAT_NAMES, buf))
+
+    def compress(self, d_in, n, order, d_local, local_cap, prepare_decode=False, stream=0):
+        """Collective: (ShardLayout, CodingProvider). d_in / d_local are device addresses."""
+        layout = ShardLayout()
+        table = ctypes.c_void_p()
+        _check(_lib.mh_sharded_compress(self._h, d_in, int(n), int(order), d_local, int(local_cap), ctypes.byref(layout), ctypes.byref(table),
+                                        1 if prepare_decode else 0, stream or None), "mh_sharded_compress")
+        return layout, CodingProvider(table.value)
+
+    def decompress(self, provider, d_local, local_cap, layout, d_out, out_capacity, speculative=True, stream=0):
+        """Collective: (symbols this rank wrote, symbols of the ranks before it)."""
+        n_out, off = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        _check(_lib.mh_sharded_decompress(self._h, provider._h, d_local, int(local_cap), ctypes.byref(layout), 1 if speculative else 0,
+                                          d_out, int(out_capacity), ctypes.byref(n_out), ctypes.byref(off), stream or None), "mh_sharded_decompress")
+        return n_out.value, off.value

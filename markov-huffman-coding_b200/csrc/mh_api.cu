@@ -12,14 +12,21 @@
 #include "mh_host.hpp"
 #include "mh_internal.hpp"
 
+static std::atomic<uint64_t> g_table_serial{0};
+
 struct mh_table {
 	mh::CodingTable impl;
+	const uint64_t serial = ++g_table_serial;   // never reused: identifies the table the device images were flattened from
 };
 
 namespace mh {
 
 std::atomic<uint64_t> g_kernel_launches{0};
 static thread_local std::string t_last_error;
+
+void set_last_error(const char* msg) { t_last_error = msg ? msg : ""; }
+int table_order(const mh_table* t) { return t->impl.order; }
+uint64_t table_serial(const mh_table* t) { return t->serial; }
 
 int cuda_fail(cudaError_t e, const char* what) {
 	t_last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -397,6 +404,15 @@ static void release_dec(mh_dectable* dt) {
 	if(dt->h_pair) cudaFreeHost(dt->h_pair);
 	*dt = mh_dectable();
 }
+
+}  // extern "C"
+namespace mh {
+int upload_codebook_for(const mh_table* t, mh_codebook* cb, cudaStream_t st) { return upload_codebook(t, cb, st); }
+int upload_dectable_for(const mh_table* t, mh_dectable* dt, cudaStream_t st) { return upload_dectable(t, dt, st); }
+void release_codebook(mh_codebook* cb) { release_book(cb); }
+void release_dectable(mh_dectable* dt) { release_dec(dt); }
+}  // namespace mh
+extern "C" {
 
 int mh_codebook_create(const mh_table* t, mh_codebook** out) {
 	if(!t || !out) return MH_ERR_INVALID_ARG;

@@ -98,6 +98,7 @@ struct EncArgs {
 	const uint32_t* ctx;              // FMT_CTX table: ctx_rows x 256 entries, the last row is the null row
 	uint32_t ctx_rows;
 	uint32_t bit0;
+	const unsigned long long* bit_base_dev;   // optional: the global bit offset lives in device memory (its low 3 bits replace bit0)
 	uint32_t stage_words;
 	uint32_t* out_words;
 	uint64_t out_capacity_words;
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	__shared__ volatile uint32_t s_head[2];                       // workers -> scanner: the first staged word of that tile
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t bit0 = A.bit_base_dev ? uint32_t(__ldg(A.bit_base_dev) & 7ull) : A.bit0;
 	uint32_t table_entries = 0;
 	if(FMT == FMT_BOX_SMEM) {
 		table_entries = A.order ? (A.box_r + 1) * (A.box_r + 1) : 256u;
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 		uint32_t q_tile = 0, q_bits = 0, q_near = 0;
 		unsigned long long q_excl = 0;
 		auto boundary_word = [&](uint32_t head) {   // lane 0: the first output word of tile q_tile, if it shares it
-			const unsigned long long g0 = A.bit0 + q_excl, g1 = g0 + q_bits;
+			const unsigned long long g0 = bit0 + q_excl, g1 = g0 + q_bits;
 			const uint32_t s = uint32_t(g0 & 31);
 			const unsigned long long w0 = g0 >> 5;
 			unsigned long long w1 = g1 >> 5;
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 			bar_wait(4 + ((it - 1) & 1));   // normally passed at once: the scanner had a whole iteration
 			const unsigned long long prefix_bits = s_prefix_bits[(it - 1) & 1];
 			// funnel-shift copy-out
-			const unsigned long long g0 = A.bit0 + prefix_bits;     // global bit index of the tile's first bit
+			const unsigned long long g0 = bit0 + prefix_bits;     // global bit index of the tile's first bit
 			const unsigned long long g1 = g0 + p_bits;
 			const uint32_t s = uint32_t(g0 & 31);
 			const unsigned long long w0 = g0 >> 5;
@@ -642,7 +644,8 @@ int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStr
 uint64_t encode_tiles_for(uint64_t n) { return (n + kEncThreads * 16 - 1) / (kEncThreads * 16); }
 
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
-                  uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st) {
+                  uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st,
+                  const unsigned long long* d_bit_base) {
 	if(!cb || !cb->d_enc || !d_result || (!d_in && n) || (!d_out && n)) return MH_ERR_INVALID_ARG;
 	if(reinterpret_cast<uint64_t>(d_out) & 3) return MH_ERR_INVALID_ARG;
 	if(!ws || !ws->enc_desc) return MH_ERR_WORKSPACE;
@@ -682,6 +685,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.box = cb->d_box; a.box_lo = cb->box_lo; a.box_r = cb->box_r;
 	a.ctx = cb->d_ctx; a.ctx_rows = cb->ctx_rows;
 	a.bit0 = uint32_t(bit_base & 7);
+	a.bit_base_dev = d_bit_base;
 	a.stage_words = stage_words;
 	a.out_words = reinterpret_cast<uint32_t*>(d_out);
 	a.out_capacity_words = out_capacity / 4;

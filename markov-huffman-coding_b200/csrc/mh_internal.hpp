@@ -123,8 +123,11 @@ namespace mh {
 // accumulate: add to d_counts instead of overwriting it (chunked inputs: the counts of the chunks add up)
 int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, unsigned long long* d_counts,
                      mh_workspace* ws, cudaStream_t st, bool accumulate = false);
+// d_bit_base (optional): the shard's global bit offset in DEVICE memory — its low three bits are the bit phase of the
+// first codeword and replace `bit_base` (a sharded compress computes the offsets on the device and never waits for them)
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
-                  uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st);
+                  uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st,
+                  const unsigned long long* d_bit_base = nullptr);
 int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
                   uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
 int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start, uint8_t prev0,

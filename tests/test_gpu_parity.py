@@ -307,3 +307,74 @@ def test_extract_larger_than_the_uncompressed_side_buffer(ipsum_counts):
         assert n.value == len(data) and out.tobytes() == data
     finally:
         mh._lib.mh_session_destroy(h)
+
+
+@pytest.mark.gpu
+def test_payload_longer_than_2_pow_32_bits():
+    """The reference's own decoder breaks at 2^31 payload bits (int length / int bi, src/coding.cpp:115,120).
+    600 MB of K = 256 data code to ~4.8 Gbit: the stream must equal the oracle's (64-bit restatement) byte for byte
+    and extract to the input — through the device API (one launch each) and through a session that has to chunk it."""
+    import torch
+    n = 600_000_000
+    rng = np.random.default_rng(2026)
+    data = rng.integers(0, 256, n, dtype=np.uint8)
+    data[::3] &= 0x3F                      # skew the statistics a little: codewords of 6..10 bits, the LUT8 fallback included
+    want_stream, want_table = o.compress_from_input(data, True)
+    assert (len(want_stream) - 1) * 8 > (1 << 32)
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(data).to(dev)
+    cap = n + n // 8 + 4096
+    d_pay = torch.zeros(cap + 256, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(n, dtype=torch.uint8, device=dev)
+    d_counts = torch.zeros(65536, dtype=torch.int64, device=dev)
+    d_res = torch.zeros(8, dtype=torch.int64, device=dev)
+    ws = mh.Workspace(n, cap)
+    mh.gpu_histogram(d_in.data_ptr(), n, 0x20, 1, d_counts.data_ptr(), ws)
+    provider = mh.CodingProvider.from_counts_array(d_counts.cpu().numpy().view(np.uint64), 1)
+    assert provider.write_coding_tree() == want_table
+    book, dectab = mh.Codebook(provider), mh.DecodeTable(provider)
+    mh.gpu_encode(d_in.data_ptr(), n, 0x20, book, 0, d_pay.data_ptr(), cap, d_res.data_ptr(), ws)
+    bits = int(d_res[0].item())
+    assert bits > (1 << 32) and int(d_res[2].item()) == 0
+    nbytes = (bits + 7) // 8
+    assert 1 + nbytes == len(want_stream)
+    got = hashlib.sha256(bytes([0x30 | ((8 - bits % 8) % 8)]))
+    got.update(memoryview(d_pay[:nbytes].cpu().numpy()))
+    assert got.hexdigest() == sha(want_stream)
+    mh.gpu_decode(d_pay.data_ptr(), 0, bits, 0x20, dectab, d_out.data_ptr(), n, d_res[4:].data_ptr(), ws)
+    assert d_res[4:7].tolist() == [n, 0, 0]
+    assert torch.equal(d_out, d_in)
+    del d_pay, d_out, ws, book, dectab
+    torch.cuda.empty_cache()
+    # the host-buffer path with device buffers a quarter of the size: chunked encode at bit offsets beyond 2^32,
+    # chunked extract from exact states at bit positions beyond 2^32
+    s = mh.Session(160_000_000)
+    try:
+        stream, _ = s.compress(data, 1)
+        assert sha(stream) == sha(want_stream)
+        assert np.array_equal(np.frombuffer(s.decompress_into(provider, stream, n), dtype=np.uint8), data)
+    finally:
+        s.close()
+
+
+@pytest.mark.gpu
+def test_large_text_takes_the_8192_bit_subsequences_and_equals_the_oracle(ipsum_counts):
+    """200 MB of Markov text is long enough for the decoder to pick its largest subsequences (8192 bits, what the 1 GiB
+    bench runs) without any override; stream == oracle, extract == input, both coder types."""
+    import torch
+    n = 200_000_000
+    dev = torch.device("cuda", 0)
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    mh.synth_markov(ipsum_counts, 4242, 65536, 0, d_in.data_ptr(), n)
+    torch.cuda.synchronize()
+    data = d_in.cpu().numpy()
+    s = mh.Session(n)
+    try:
+        for order in (1, 0):
+            want_stream, want_table = o.compress_from_input(data, bool(order))
+            assert mh.decode_subsequence_bits(order, (len(want_stream) - 1) * 8) == 8192
+            stream, provider = s.compress(data, order)
+            assert sha(stream) == sha(want_stream) and provider.write_coding_tree() == want_table
+            assert np.array_equal(np.frombuffer(s.decompress_into(provider, stream, n), dtype=np.uint8), data)
+    finally:
+        s.close()
