@@ -747,11 +747,20 @@ def main():
         run_reference_arm(args, rank, world)
         return
     args.warmup = max(3, args.warmup)
+    # stdout carries exactly ONE line (the JSON record): whatever libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(rec):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(rec) + "\n").encode())
+
     mh = importlib.import_module("markov-huffman-coding_b200")   # raises if libmh_gpu.so is missing: no fallback
     if world > 1:
         rec = run_multi(args, rank, world, local_rank, mh)
         if rec is not None:
-            print(json.dumps(rec), flush=True)
+            emit(rec)
         return
     import torch
     numa = pin_to_gpu_numa_node(local_rank)
@@ -766,7 +775,7 @@ def main():
         for name in ("huffman", "fib", "fib-h"):
             torch.cuda.empty_cache()
             line["configs"][name] = run_single(args, name, max(3, min(args.steps, 10)), dev, mh, not args.no_e2e, not args.no_cpu_baseline)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":

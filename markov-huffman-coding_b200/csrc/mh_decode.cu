@@ -67,25 +67,40 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 struct Cursor {
 	const uint32_t* words;   // payload (4-byte aligned)
 	uint64_t n_bytes;        // payload bytes; reads past them return zero (pop_rest pads, src/bitbuffer.cpp:129-140)
+	uint64_t base16;         // the 16-byte boundary at or before `words`
 	uint32_t ring;           // shared-space address of this thread's piece 0 (set once by the kernel)
-	uint32_t cw;             // next chunk to request, counted from the 16-byte boundary at or before `words`
+	uint32_t cw;             // next chunk to request, counted from base16
 	uint32_t rw;             // next word to pop, counted from the same boundary
-	uint32_t ticks;          // top_up() calls since the last seek
 	uint32_t hi, lo, nextw;  // nextw is kept in memory (little-endian) order and byte-swapped only when consumed
 	uint32_t pos, loaded;
+	bool interior;           // every chunk this thread can request lies inside the payload: no bounds arithmetic
 
 	__device__ __forceinline__ void attach(uint32_t ring_base_shared) {
 		ring = ring_base_shared + ((threadIdx.x >> 5) * (kRingPieces * 32u) + (threadIdx.x & 31u)) * 16u;
+		base16 = reinterpret_cast<uint64_t>(words) & ~uint64_t(15);
+		interior = false;
+	}
+	// `last_bit`: no bit at or beyond it (relative to words[0]) is popped by this thread before the next set_reach()
+	__device__ __forceinline__ void set_reach(uint64_t last_bit) {
+		// chunks are requested up to kRingPieces ahead of the one being read
+		interior = ((reinterpret_cast<uint64_t>(words) & 15) + (last_bit >> 3) + 16u * (kRingPieces + 2)) <= (reinterpret_cast<uint64_t>(words) & 15) + n_bytes;
 	}
 	// chunk c -> slot c % kRingPieces (if `go`); bytes outside the payload are zero-filled by the copy itself
 	__device__ __forceinline__ void request_if(uint32_t c, bool go) {
+		const uint32_t dst = ring + ((c << 9) & ((kRingPieces - 1) << 9));
+		if(interior) {
+			cp_async_16_if(dst, reinterpret_cast<const void*>(base16 + (uint64_t(c) << 4)), 16u, go);
+			return;
+		}
 		const uint64_t addr = reinterpret_cast<uint64_t>(words);
-		const uint64_t base = addr & ~uint64_t(15);
 		const int64_t left = int64_t((addr & 15) + n_bytes) - (int64_t(c) << 4);   // payload bytes from the chunk's start on
 		const uint32_t n = left >= 16 ? 16u : (left > 0 ? uint32_t(left) : 0u);
-		cp_async_16_if(ring + (c & (kRingPieces - 1)) * 512u, reinterpret_cast<const void*>(n ? base + (uint64_t(c) << 4) : base), n, go);
+		cp_async_16_if(dst, reinterpret_cast<const void*>(n ? base16 + (uint64_t(c) << 4) : base16), n, go);
 	}
-	// keep kRingPieces chunks requested from the one being read on: at most one is missing per round (<= 4 pops)
+	// keep kRingPieces chunks requested from the one being read on: at most one is missing per round (<= 4 pops).
+	// The decode loops call this on a WARP-UNIFORM cadence (every kRefillEvery-th trip of the loop, all lanes in the same
+	// trip, plus once when a loop is entered): a cadence that each lane keeps for itself drifts apart between the lanes
+	// (slow paths, checkpoint records), and then almost every trip of the warp steps through this code for a few lanes.
 	__device__ __forceinline__ void refill_round() {
 		const bool go = int32_t((rw >> 2) + kRingPieces - cw) > 0;
 		request_if(cw, go);
@@ -106,7 +121,6 @@ struct Cursor {
 		cp_async_wait<0>();   // nothing of a previous subsequence may still land in the ring
 		rw = uint32_t(w);
 		cw = rw >> 2;
-		ticks = 0;
 #pragma unroll
 		for(uint32_t j = 0; j < kRingPieces; ++j) request_if(cw++, true);
 		cp_async_commit();
@@ -131,7 +145,7 @@ struct Cursor {
 		asm("shl.b32 %0, %0, %1;" : "+r"(lo) : "r"(nbits));   // PTX shl clamps: 32 -> 0
 		pos += nbits;
 	}
-	// Called at least once per 32 bits consumed.
+	// Called at least once per 32 bits consumed: keeps more than 32 valid bits in the window.
 	__device__ __forceinline__ void top_up() {
 		const uint32_t avail = loaded - pos;
 		if(avail <= 32) {   // all valid bits sit in hi
@@ -141,7 +155,12 @@ struct Cursor {
 			loaded += 32;
 			nextw = pop();
 		}
-		if((++ticks & (kRefillEvery - 1)) == 0) refill_round();
+	}
+	// The slow paths (codewords longer than 8 bits walked bit by bit) consume more than 32 bits per trip of their loop:
+	// they top the ring up themselves, one round per 32 bits.
+	__device__ __forceinline__ void top_up_slow() {
+		top_up();
+		refill_round();
 	}
 };
 
