@@ -43,11 +43,11 @@ constexpr uint32_t kDeep = 0x10u, kNull = 0x20u, kExt = 0x40u;
 // The payload reaches the window through a small ring in shared memory that every thread owns privately:
 // kRingPieces aligned 16-byte chunks, filled by cp.async (global -> shared, no registers, L1 bypassed). With plain
 // loads, one word ahead, almost every iteration of a warp had one lane of 32 whose next word missed, and the warp
-// waited for it. The ring is topped up on a fixed cadence — every kRefillEvery-th top_up(), i.e. at the same
-// iteration for all lanes of a warp, with predicated copies — because a refill that each lane triggers when IT
+// waited for it. The ring is topped up on a fixed cadence — every kRefillEvery-th trip of the decode loop, at the same
+// trip for all lanes of a warp, with predicated copies — because a refill that each lane triggers when IT
 // crosses a chunk boundary is rare per lane but happens in most iterations of the warp, and then the whole warp
 // steps through the refill code for a handful of lanes (measured: 78 % of D1's iterations, 6 lanes active).
-// Between two top_up() calls at most 32 bits are consumed, so a round sees at most one chunk (four words) used up;
+// A trip consumes at most 32 bits (the slow paths add rounds of their own), so a round sees at most one chunk (four words) used up;
 // a chunk is requested two rounds (>= 256 stream bits) before its first word can be popped, and each round waits
 // for the copies of the round before it.
 // The pieces of the 32 lanes of a warp are interleaved (piece j of lane l at (j * 32 + l) * 16) to spread the banks.
@@ -59,6 +59,9 @@ __device__ __forceinline__ void cp_async_16_if(uint32_t dst_shared, const void* 
 	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t}" ::"r"(dst_shared), "l"(src), "r"(src_bytes),
 	             "r"(uint32_t(go))
 	             : "memory");
+}
+__device__ __forceinline__ void cp_async_16_full_if(uint32_t dst_shared, uint64_t src, bool go) {   // the whole 16 bytes, no size operand
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst_shared), "l"(src), "r"(uint32_t(go)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -89,7 +92,7 @@ struct Cursor {
 	__device__ __forceinline__ void request_if(uint32_t c, bool go) {
 		const uint32_t dst = ring + ((c << 9) & ((kRingPieces - 1) << 9));
 		if(interior) {
-			cp_async_16_if(dst, reinterpret_cast<const void*>(base16 + (uint64_t(c) << 4)), 16u, go);
+			cp_async_16_full_if(dst, base16 + (uint64_t(c) << 4), go);
 			return;
 		}
 		const uint64_t addr = reinterpret_cast<uint64_t>(words);
@@ -156,12 +159,6 @@ struct Cursor {
 			nextw = pop();
 		}
 	}
-	// The slow paths (codewords longer than 8 bits walked bit by bit) consume more than 32 bits per trip of their loop:
-	// they top the ring up themselves, one round per 32 bits.
-	__device__ __forceinline__ void top_up_slow() {
-		top_up();
-		refill_round();
-	}
 };
 
 // One symbol: look the top 8 window bits up in the context's row; leaves take the fast path. Returns the symbol and
@@ -206,6 +203,7 @@ __device__ __forceinline__ uint32_t decode_one(Cursor& cur, uint32_t lut_s, cons
 			const uint32_t* nodes = walk + row_off;   // row_off = ctx * 512 is also the context's offset in the walk table
 			for(int guard = 0; guard < 256; ++guard) {
 				cur.top_up();
+				if((guard & 15) == 0) cur.refill_round();   // the walk may consume more than a trip's 32 bits: it tops the ring up itself
 				const uint32_t bit = cur.hi >> 31;
 				cur.take(1);
 				const uint32_t w = __ldg(nodes + node);
@@ -256,7 +254,10 @@ __device__ __forceinline__ bool decode_until(Cursor& cur, uint32_t lut_s, const 
 	bool clean = true;
 	uint32_t sym = ctx;
 	uint32_t row_off = ORDER ? ctx << 9 : 0u;
+	uint32_t trip = 0;
+	cur.refill_round();
 	while(cur.pos < limit) {
+		if((++trip & 1) == 0) cur.refill_round();   // four symbols of up to 16 bits per trip (longer ones walk, and top up themselves)
 #pragma unroll
 		for(int j = 0; j < 4; ++j) {
 			if(cur.pos < limit) {
@@ -286,10 +287,12 @@ template <int ORDER>
 __device__ __forceinline__ bool walk_subsequence(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
                                                  const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t seg_bits, uint32_t span,
                                                  uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
-	uint32_t cp_end = sub_begin, cnt = 0;
+	uint32_t cp_end = sub_begin, cnt = 0, trip = 0;
 	int j = -1;   // segment being decoded; the first pass through the record branch only sets up segment 0
 	bool clean = true;
+	cur.refill_round();
 	for(;;) {
+		if((++trip & (kRefillEvery - 1)) == 0) cur.refill_round();   // every lane of the warp in the same trip
 		if(j < 0 || cur.pos >= cp_end) {
 			if(j >= 0) {
 				const uint16_t st = uint16_t(pack_cp(cur.pos - cp_end, ORDER ? (row - lut_s) >> 9 : 0u));
@@ -348,12 +351,15 @@ __device__ __forceinline__ bool walk_subsequence(Cursor& cur, uint32_t lut_s, co
 constexpr uint32_t kPairFlags = kDeep | kNull;
 constexpr uint32_t kPairCount = 0xc0u;   // symbols produced by one entry: 0x40 one, 0x80 two, 0 = prefix entry
 
+// Rows are named by their byte offset inside the table (row r = r * 1024): the entry's next-row field [15:10] already
+// is that offset, so a lookup address is (entry & 0xfc00) | (window byte * 4) — one LOP3 — plus the table's base,
+// which rides in the load's uniform-register operand.
 struct PairTab {
 	uint32_t tab;    // shared-space address of the table (row r at tab + r * 1024)
 	uint32_t rank;   // shared-space address of rank[256]: row of a byte as context
 	uint32_t live;   // shared-space address of live[64]: context byte of a context row
 	uint32_t len1;   // shared-space address of len1[ctx_rows * 256]: length of an entry's first codeword
-	uint32_t null_row;
+	uint32_t null_row;   // offset of the null row
 };
 
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
@@ -380,12 +386,12 @@ __device__ __forceinline__ PairTab stage_pair_table(uint32_t* smem, const uint32
 	T.rank = T.tab + rows * 1024u;
 	T.live = T.rank + 256u;
 	T.len1 = T.live + 64u;
-	T.null_row = T.tab + ctx_rows * 1024u;
+	T.null_row = ctx_rows * 1024u;
 	return T;
 }
 
 template <int ORDER>
-__device__ __forceinline__ uint32_t pair_row_of(const PairTab& T, uint32_t ctx) { return ORDER ? T.tab + (lds_u8(T.rank + ctx) << 10) : T.tab; }
+__device__ __forceinline__ uint32_t pair_row_of(const PairTab& T, uint32_t ctx) { return ORDER ? lds_u8(T.rank + ctx) << 10 : 0u; }
 
 // Four speculative lookups; the window is left untouched. a[i] = sum of the first i entries, r[i] = row after them.
 template <int ORDER>
@@ -395,9 +401,9 @@ __device__ __forceinline__ void pair_lookups(const Cursor& cur, const PairTab& T
 #pragma unroll
 	for(int i = 0; i < 4; ++i) {
 		const uint32_t t = __funnelshift_l(cur.lo, cur.hi, a[i]);
-		e[i] = lds_u32(r[i] + ((t >> 24) << 2));
+		e[i] = lds_u32(T.tab + (r[i] | ((t >> 22) & 0x3fcu)));
 		a[i + 1] = a[i] + e[i];
-		r[i + 1] = T.tab + (e[i] & 0xfc00u);   // order 0: context row 0, or a prefix row
+		r[i + 1] = e[i] & 0xfc00u;   // order 0: context row 0, or a prefix row
 	}
 }
 
@@ -406,9 +412,9 @@ __device__ __forceinline__ void pair_lookups(const Cursor& cur, const PairTab& T
 template <int ORDER>
 __device__ __forceinline__ uint32_t pair_slow_one(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
                                                   const uint32_t* __restrict__ walk, uint32_t& row, bool& clean) {
-	uint32_t row_off = ORDER ? lds_u8(T.live + ((row - T.tab) >> 10)) << 9 : 0u;
+	uint32_t row_off = ORDER ? lds_u8(T.live + (row >> 10)) << 9 : 0u;
 	const uint32_t sym = decode_one<ORDER, false>(cur, 0u, lut_g, walk, row_off, clean);
-	if(ORDER) row = T.tab + (lds_u8(T.rank + sym) << 10);
+	if(ORDER) row = lds_u8(T.rank + sym) << 10;
 	return sym;
 }
 
@@ -421,11 +427,11 @@ __device__ __forceinline__ uint32_t pair_step_one(Cursor& cur, const PairTab& T,
 	if((e0 & kPairFlags) || !(e0 & kPairCount)) return pair_slow_one<ORDER>(cur, T, lut_g, walk, row, clean);
 	const uint32_t sym = (e0 >> 16) & 255u;
 	if(e0 & 0x80u) {
-		cur.take(lds_u8(T.len1 + ((row - T.tab) >> 2) + (cur.hi >> 24)));
+		cur.take(lds_u8(T.len1 + (row >> 2) + (cur.hi >> 24)));
 		row = pair_row_of<ORDER>(T, sym);
 	} else {
 		cur.take(e0 & 15u);
-		row = T.tab + (e0 & 0xfc00u);
+		row = e0 & 0xfc00u;
 	}
 	return sym;
 }
@@ -438,13 +444,15 @@ template <int ORDER>
 __device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
                                                       const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t seg_bits, uint32_t span,
                                                       uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
-	uint32_t cp_end = sub_begin, cnt = 0;
+	uint32_t cp_end = sub_begin, cnt = 0, trip = 0;
 	int j = -1;
 	bool clean = true;
+	cur.refill_round();
 	for(;;) {
+		if((++trip & (kRefillEvery - 1)) == 0) cur.refill_round();   // every lane of the warp in the same trip
 		if(j < 0 || cur.pos >= cp_end) {
 			if(j >= 0) {
-				const uint16_t st = uint16_t(pack_cp(cur.pos - cp_end, (row - T.tab) >> 10));
+				const uint16_t st = uint16_t(pack_cp(cur.pos - cp_end, row >> 10));
 				cp_cn[j * kDecThreads] = uint16_t(cnt);
 				if(compare && cp_st[j * kDecThreads] == st) return true;
 				cp_st[j * kDecThreads] = st;
@@ -587,8 +595,10 @@ __device__ __forceinline__ bool decode_emit_pair(Cursor& cur, const PairTab& T, 
 	uint32_t row = pair_row_of<ORDER>(T, ctx);
 	uint32_t rem = count;
 	os.begin(out);
+	if(rem) cur.refill_round();
 	for(uint32_t it = 0; __any_sync(0xffffffffu, rem != 0); ++it) {
 		if(rem) {
+			if((it & (kRefillEvery - 1)) == kRefillEvery - 1) cur.refill_round();   // every lane of the warp in the same trip
 			uint32_t e[4], a[5], r[5];
 			pair_lookups<ORDER>(cur, T, row, e, a, r);
 			const uint32_t f4 = e[0] | e[1] | e[2] | e[3];
@@ -632,9 +642,12 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 	uint32_t row_off = ORDER ? ctx << 9 : 0u;
 	uint32_t head = uint32_t((8 - (reinterpret_cast<uint64_t>(out) & 7)) & 7);
 	if(head > count) head = count;
+	uint32_t trip = 0;
+	cur.refill_round();
 	for(uint32_t i = 0; i < head; ++i) {
 		*out++ = uint8_t(decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean));
 		cur.top_up();
+		if((++trip & (kRefillEvery - 1)) == 0) cur.refill_round();
 	}
 	const uint32_t groups = (count - head) >> 3;
 	uint32_t row = lut_s + row_off;
@@ -650,6 +663,7 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 				row = lut_s + row_off;
 			}
 			cur.top_up();
+			if((++trip & 1) == 0) cur.refill_round();   // a half is four LUT hits (<= 32 bits) or four symbols of up to 16 bits
 		}
 		__stcg(reinterpret_cast<uint2*>(out), make_uint2(w[0], w[1]));   // L2 only: the output must not push payload lines out of L1
 		out += 8;
@@ -659,6 +673,7 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 	for(uint32_t i = 0; i < tail; ++i) {
 		*out++ = uint8_t(decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean));
 		cur.top_up();
+		if((++trip & (kRefillEvery - 1)) == 0) cur.refill_round();
 	}
 	return clean;
 }
@@ -699,7 +714,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 	uint32_t guess_row = lut_sa + (ORDER ? uint32_t(' ') << 9 : 0u);
 	if(PAIR) {
 		guess_row = pair_row_of<ORDER>(T, ' ');
-		if(ORDER && guess_row == T.null_row) guess_row = T.tab;
+		if(ORDER && guess_row == T.null_row) guess_row = 0u;   // row 0: the first live context
 	}
 	Cursor cur;
 	cur.words = words;
@@ -926,6 +941,7 @@ __global__ void __launch_bounds__(PAIR ? kDecWriteMaxThreads : kDecThreads, 1) d
 		const uint32_t lim = uint32_t(e - origin);
 		uint8_t* dst = out;
 		if(c) {
+			cur.set_reach(origin + sub_bits + 64);   // the last codeword may run a few bits past the subsequence
 			cur.seek(origin + pos, pos);
 			dst = out + (chunk_base[k / chunk_subs] + prefix[k]);
 		}
