@@ -107,6 +107,18 @@ int mh_codebook_create(const mh_table* t, mh_codebook** out);
 /* Re-upload another table into an existing handle, stream-ordered, without allocating or blocking the host. */
 int mh_codebook_update(mh_codebook* cb, const mh_table* t, mh_stream_t stream);
 void mh_codebook_destroy(mh_codebook* cb);
+/* The encoder's tables built ON THE DEVICE from the device-resident histogram (d_counts as mh_gpu_histogram writes it):
+ * the same heap, tie-breaking and int32 weight arithmetic as the host's (src/huffman.cpp:131-164, src/min_pq.tpp), one
+ * warp per context, stream-ordered, no copy to the host and no host wait between the histogram and the encoder. The
+ * host's mh_table (table file, decoder tables) can be built from a copy of the counts meanwhile. mh_gpu_encode checks
+ * that its launch fits the tables that were built; when it does not (more than ~59 live contexts, a codeword longer
+ * than 28 bits, a count that wrapped to 0) it writes nothing and sets d_result[3] != 0: encode again with a codebook
+ * made from the host table (mh_codebook_update). mh_codebook_create_empty makes a handle without a table. */
+int mh_codebook_create_empty(mh_codebook** out);
+int mh_codebook_build_device(mh_codebook* cb, const uint64_t* d_counts, int order, mh_stream_t stream);
+/* Test introspection: copies the handle's device tables to the host (synchronises the device). enc: 65536 x u64 (256 for
+ * order 0), ctx: up to 96 x 256 x u32, meta: 8 x u32 (rows incl. the null row, status, longest codeword, live contexts). */
+int mh_codebook_download(mh_codebook* cb, uint64_t* enc, uint32_t* ctx, uint32_t* meta);
 int mh_dectable_create(const mh_table* t, mh_dectable** out);
 int mh_dectable_update(mh_dectable* dt, const mh_table* t, mh_stream_t stream);
 void mh_dectable_destroy(mh_dectable* dt);
@@ -127,7 +139,8 @@ int mh_gpu_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, 
  * out_capacity >= ceil(((bit_base & 7) + total_bits) / 32) * 4 bytes; bytes past the payload end inside the last
  * 32-bit word are written as zero. d_result is 4 x uint64: [0] = payload bits produced, [1] = symbols that had no
  * codeword and were dropped like the reference does (assert compiled out, src/coding.cpp:72), [2] = 1 if
- * out_capacity was too small (nothing useful was written), [3] reserved. */
+ * out_capacity was too small (nothing useful was written), [3] != 0: the codebook's device-built tables do not fit this
+ * encoder launch (see mh_codebook_build_device); nothing was written. */
 int mh_gpu_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
                   uint8_t* d_out, uint64_t out_capacity, uint64_t* d_result, mh_workspace* ws, mh_stream_t stream);
 
@@ -261,6 +274,19 @@ int mh_sharded_compress(mh_comm* c, const uint8_t* d_in, uint64_t n, int order, 
 int mh_sharded_decompress(mh_comm* c, const mh_table* t, uint8_t* d_local, uint64_t local_cap, const mh_shard_layout* layout,
                           int speculative, uint8_t* d_out, uint64_t out_capacity, uint64_t* n_out, uint64_t* out_offset,
                           mh_stream_t stream);
+
+/* Ranks of ONE process on shared HOST buffers — what a command-line driver with several GPUs calls in place of
+ * compress(FILE*, FILE*) / decompress(FILE*, FILE*) (src/main.cpp:204-212). Only for comms made by mh_comm_create_local:
+ * every rank (its own host thread) passes the SAME pointers and sizes; rank r copies its byte range of `in` (compress) or
+ * its bit range of the payload plus the warm-up in front of it (decompress) to its GPU, the ranks run the collective calls
+ * above (decompress: cuts at arbitrary bits, speculative start, seam handshake), and every rank copies its part of the
+ * result to its place in `out` (seam bytes OR-merged). The calls return on every rank when `out` is complete;
+ * *out_len = size of the whole result; *table_out (optional) is handed to rank 0 only.
+ * mh_sharded_decompress_host answers MH_ERR_INVALID_ARG for a stream too short to cut (use a session on one GPU). */
+int mh_sharded_compress_host(mh_comm* c, const uint8_t* in, uint64_t n, int order, uint8_t* out, uint64_t out_capacity,
+                             uint64_t* out_len, mh_table** table_out);
+int mh_sharded_decompress_host(mh_comm* c, const mh_table* t, const uint8_t* stream, uint64_t stream_len, uint8_t* out,
+                               uint64_t out_capacity, uint64_t* out_len);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Synthetic workloads of the benchmark configs; not part of the reference. Byte-identical to

@@ -80,6 +80,9 @@ _SIGNATURES = {
     "mh_codebook_create": (_i, [_vp, _pp]),
     "mh_codebook_update": (_i, [_vp, _vp, _vp]),
     "mh_codebook_destroy": (None, [_vp]),
+    "mh_codebook_create_empty": (_i, [_pp]),
+    "mh_codebook_build_device": (_i, [_vp, _vp, _i, _vp]),
+    "mh_codebook_download": (_i, [_vp, _vp, _vp, _vp]),
     "mh_dectable_create": (_i, [_vp, _pp]),
     "mh_dectable_update": (_i, [_vp, _vp, _vp]),
     "mh_dectable_destroy": (None, [_vp]),
@@ -115,6 +118,8 @@ _SIGNATURES = {
     "mh_shard_payload_offset": (ctypes.c_uint32, []),
     "mh_sharded_compress": (_i, [_vp, _vp, _u64, _i, _vp, _u64, _vp, _pp, _i, _vp]),
     "mh_sharded_decompress": (_i, [_vp, _vp, _vp, _u64, _vp, _i, _vp, _u64, _pu64, _pu64, _vp]),
+    "mh_sharded_compress_host": (_i, [_vp, _vp, _u64, _i, _vp, _u64, _pu64, _pp]),
+    "mh_sharded_decompress_host": (_i, [_vp, _vp, _vp, _u64, _vp, _u64, _pu64]),
     "mh_kernel_launches": (_u64, []),
     "mh_profile_enable": (_i, [_i]),
     "mh_profile_report": (_i, [_vp, _sz, _psz]),
@@ -417,10 +422,26 @@ class Workspace:
 
 
 class Codebook:
-    def __init__(self, provider):
+    def __init__(self, provider=None):
         out = ctypes.c_void_p()
-        _check(_lib.mh_codebook_create(provider._h, ctypes.byref(out)), "mh_codebook_create")
+        if provider is None:
+            _check(_lib.mh_codebook_create_empty(ctypes.byref(out)), "mh_codebook_create_empty")
+        else:
+            _check(_lib.mh_codebook_create(provider._h, ctypes.byref(out)), "mh_codebook_create")
         self._h = out
+
+    def build_device(self, d_counts, order, stream=0):
+        """The encoder's tables straight from the device-resident histogram (no host round trip)."""
+        _check(_lib.mh_codebook_build_device(self._h, d_counts, int(order), stream or None), "mh_codebook_build_device")
+
+    def download(self):
+        """(wide u64[65536], ctx u32[rows*256], meta u32[8]) as numpy arrays (synchronises the device)."""
+        import numpy as np
+        enc = np.zeros(65536, dtype=np.uint64)
+        ctx = np.zeros(96 * 256, dtype=np.uint32)
+        meta = np.zeros(8, dtype=np.uint32)
+        _check(_lib.mh_codebook_download(self._h, enc.ctypes.data, ctx.ctypes.data, meta.ctypes.data), "mh_codebook_download")
+        return enc, (ctx[: int(meta[0]) * 256] if meta[0] <= 96 else ctx[:0]), meta
 
     def update(self, provider, stream=0):
         _check(_lib.mh_codebook_update(self._h, provider._h, stream or None), "mh_codebook_update")
@@ -564,6 +585,20 @@ class Comm:
         _check(_lib.mh_sharded_compress(self._h, d_in, int(n), int(order), d_local, int(local_cap), ctypes.byref(layout), ctypes.byref(table),
                                         1 if prepare_decode else 0, stream or None), "mh_sharded_compress")
         return layout, CodingProvider(table.value)
+
+    def compress_host(self, data_np, order, out_np):
+        """Ranks of one process on shared host buffers (numpy uint8 arrays): returns (stream length, CodingProvider or None)."""
+        out_len = ctypes.c_uint64(0)
+        table = ctypes.c_void_p()
+        _check(_lib.mh_sharded_compress_host(self._h, data_np.ctypes.data, data_np.size, int(order), out_np.ctypes.data, out_np.size,
+                                             ctypes.byref(out_len), ctypes.byref(table)), "mh_sharded_compress_host")
+        return out_len.value, (CodingProvider(table.value) if table.value else None)
+
+    def decompress_host(self, provider, stream_np, out_np):
+        out_len = ctypes.c_uint64(0)
+        _check(_lib.mh_sharded_decompress_host(self._h, provider._h, stream_np.ctypes.data, stream_np.size, out_np.ctypes.data, out_np.size,
+                                               ctypes.byref(out_len)), "mh_sharded_decompress_host")
+        return out_len.value
 
     def decompress(self, provider, d_local, local_cap, layout, d_out, out_capacity, speculative=True, stream=0):
         """Collective: (symbols this rank wrote, symbols of the ranks before it)."""

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <unistd.h>
@@ -97,6 +98,37 @@ bool slurp(FILE* f, HostBuf& out) {
 }
 
 const char* shown(const char* s) { return s ? s : "(null)"; }   // what glibc prints for a null %s
+
+// How many GPUs the file is cut over: MH_CLI_GPUS when set, else every device of the box for inputs of at
+// least 256 MiB, else one. The shards have to fit their devices; otherwise the single-GPU session streams the file.
+int gpus_for(uint64_t file_bytes, uint64_t per_byte_footprint) {
+	int ndev = mh_device_count();
+	if(ndev > MH_MAX_SHARDS) ndev = MH_MAX_SHARDS;
+	int want = file_bytes >= (256ull << 20) ? ndev : 1;
+	if(const char* env = getenv("MH_CLI_GPUS")) want = atoi(env);
+	if(want < 2) return 1;
+	uint64_t free_b = 0, total_b = 0;
+	if(mh_device_memory(0, &free_b, &total_b) != MH_OK) return 1;
+	if(file_bytes / uint64_t(want) * per_byte_footprint + (64ull << 20) > free_b / 2) return 1;
+	return want;
+}
+
+// fn(rank, comm) on one host thread per GPU (or per rank: MH_CLI_GPUS may exceed the device count, the ranks then share
+// devices through the library's in-process transport); returns the first failure, MH_OK otherwise
+template <typename F>
+int on_every_rank(int world, F fn) {
+	std::vector<mh_comm*> comms(size_t(world), nullptr);
+	int rc = mh_comm_create_local(world, nullptr, 1, comms.data());
+	if(rc != MH_OK) return rc;
+	std::vector<int> rcs(size_t(world), MH_OK);
+	std::vector<std::thread> threads;
+	for(int r = 0; r < world; ++r) threads.emplace_back([&, r] { rcs[size_t(r)] = fn(r, comms[size_t(r)]); });
+	for(auto& t : threads) t.join();
+	for(mh_comm* c : comms) mh_comm_destroy(c);
+	for(int v : rcs)
+		if(v != MH_OK) return v;
+	return MH_OK;
+}
 
 }  // namespace
 
@@ -228,9 +260,14 @@ int main(int argc, char* argv[]) {
 		if(v >= 4096) cap = v;
 	}
 	auto capped = [&](uint64_t want) { return want < cap ? want : cap; };
-	int rc = extract ? mh_session_create_sized(0, capped(in_bytes.n * 3 + 4096), capped(in_bytes.n + 64), &session)
-	                 : mh_session_create(0, capped(in_bytes.n + 64), &session);
-	if(rc != MH_OK) die_status("creating the GPU session", rc);
+	int rc = MH_OK;
+	auto open_session = [&]() {
+		if(session) return;
+		rc = extract ? mh_session_create_sized(0, capped(in_bytes.n * 3 + 4096), capped(in_bytes.n + 64), &session)
+		             : mh_session_create(0, capped(in_bytes.n + 64), &session);
+		if(rc != MH_OK) die_status("creating the GPU session", rc);
+	};
+	auto alloc_fail = [&]() { eprintf("Error: out of host memory.\n"); exit(1); };
 
 	bool built_here = false;
 	if(!encoding_input) {
@@ -239,13 +276,25 @@ int main(int argc, char* argv[]) {
 		built_here = true;
 	}
 
-	auto alloc_fail = [&]() { eprintf("Error: out of host memory.\n"); exit(1); };
 	if(built_here) {
-		// histogram -> trees -> encode, all in one session call; the table comes back for -g / -d
+		// histogram -> trees -> encode; the table comes back for -g / -d
 		if(!result.resize(in_bytes.n + in_bytes.n / 8 + 4200)) alloc_fail();
 		uint64_t out_len = 0;
-		rc = mh_session_compress(session, in_bytes.p, in_bytes.n, order, result.p, result.n, &out_len, &table);
-		if(rc != MH_OK) die_status("compressing", rc);
+		const int gpus = gpus_for(in_bytes.n, 3);
+		bool done = false;
+		if(gpus > 1) {   // one stream over several GPUs: byte-range shards, one host thread per GPU
+			std::vector<uint64_t> lens(size_t(gpus), 0);
+			rc = on_every_rank(gpus, [&](int r, mh_comm* c) {
+				return mh_sharded_compress_host(c, in_bytes.p, in_bytes.n, order, result.p, result.n, &lens[size_t(r)], r == 0 ? &table : nullptr);
+			});
+			if(rc == MH_OK) { out_len = lens[0]; done = true; }
+			else if(table) { mh_table_destroy(table); table = nullptr; }
+		}
+		if(!done) {
+			open_session();
+			rc = mh_session_compress(session, in_bytes.p, in_bytes.n, order, result.p, result.n, &out_len, &table);
+			if(rc != MH_OK) die_status("compressing", rc);
+		}
 		result.n = out_len;
 	}
 
@@ -276,15 +325,34 @@ int main(int argc, char* argv[]) {
 	if(extract) {
 		eprintf("Extracting %s ===> %s...\n", input, shown(output));
 		uint64_t n_out = 0;
-		rc = mh_session_decompress(session, table, in_bytes.p, in_bytes.n, nullptr, 0, &n_out);   // decode, learn the size
-		if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
-		if(!result.resize(n_out)) alloc_fail();
-		rc = mh_session_fetch(session, result.p, result.cap, &n_out);
-		if(rc == MH_ERR_WORKSPACE) {   // the stream did not fit the device buffers: the first pass only counted; decode again, chunk by chunk, into the host buffer
-			rc = mh_session_decompress(session, table, in_bytes.p, in_bytes.n, result.p, result.cap, &n_out);
+		const int gpus = gpus_for(in_bytes.n, 5);
+		bool done = false;
+		if(gpus > 1) {   // the payload is cut at arbitrary bits: speculative start per GPU, seam handshake
+			if(!result.resize(in_bytes.n * 4 + 4096)) alloc_fail();
+			for(int attempt = 0; attempt < 2 && !done; ++attempt) {
+				std::vector<uint64_t> lens(size_t(gpus), 0);
+				rc = on_every_rank(gpus, [&](int r, mh_comm* c) {
+					return mh_sharded_decompress_host(c, table, in_bytes.p, in_bytes.n, result.p, result.cap, &lens[size_t(r)]);
+				});
+				n_out = lens[0];
+				if(rc == MH_OK || rc == MH_ERR_CORRUPT_STREAM) done = true;
+				else if(rc == MH_ERR_CAPACITY && n_out > result.cap) { if(!result.resize(n_out)) alloc_fail(); }   // now the size is known
+				else if(rc == MH_ERR_BAD_HEADER || rc == MH_ERR_TYPE_MISMATCH) die_status("extracting", rc);
+				else break;   // too short to cut, or no second device after all: one GPU
+			}
+		}
+		if(!done) {
+			open_session();
+			rc = mh_session_decompress(session, table, in_bytes.p, in_bytes.n, nullptr, 0, &n_out);   // decode, learn the size
 			if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
-		} else if(rc != MH_OK) {
-			die_status("extracting", rc);
+			if(!result.resize(n_out)) alloc_fail();
+			rc = mh_session_fetch(session, result.p, result.cap, &n_out);
+			if(rc == MH_ERR_WORKSPACE) {   // the stream did not fit the device buffers: the first pass only counted; decode again, chunk by chunk, into the host buffer
+				rc = mh_session_decompress(session, table, in_bytes.p, in_bytes.n, result.p, result.cap, &n_out);
+				if(rc != MH_OK && rc != MH_ERR_CORRUPT_STREAM) die_status("extracting", rc);
+			} else if(rc != MH_OK) {
+				die_status("extracting", rc);
+			}
 		}
 		result.n = n_out;
 		if(n_out && fwrite(result.p, 1, n_out, output_fd) != n_out) {
@@ -294,6 +362,7 @@ int main(int argc, char* argv[]) {
 	} else {
 		eprintf("Compressing %s ===> %s...\n", input, shown(output));
 		if(!built_here) {
+			open_session();
 			if(!result.resize(in_bytes.n + in_bytes.n / 8 + 4200)) alloc_fail();
 			uint64_t out_len = 0, dropped = 0;
 			rc = mh_session_compress_with_table(session, table, in_bytes.p, in_bytes.n, result.p, result.n, &out_len, &dropped);

@@ -330,6 +330,7 @@ static int upload_codebook(const mh_table* t, mh_codebook* cb, cudaStream_t st) 
 	MH_CUDA(cudaMemcpyAsync(cb->d_enc, cb->h_stage, t->impl.trees.size() * 256 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
 	cb->order = t->impl.order;
 	cb->max_bits = t->impl.max_code_bits();
+	cb->device_built = false;
 	// preferred encoder table: rows for the live contexts only (text: a few dozen), next row carried by the entry
 	cb->ctx_rows = 0;
 	if(cb->max_bits <= kEncCtxMaxBits) {
@@ -391,6 +392,7 @@ static void release_book(mh_codebook* cb) {
 	if(cb->h_box) cudaFreeHost(cb->h_box);
 	if(cb->d_ctx) cudaFree(cb->d_ctx);
 	if(cb->h_ctx) cudaFreeHost(cb->h_ctx);
+	if(cb->d_meta) cudaFree(cb->d_meta);
 	*cb = mh_codebook();
 }
 
@@ -433,6 +435,30 @@ void mh_codebook_destroy(mh_codebook* cb) {
 	if(!cb) return;
 	release_book(cb);
 	delete cb;
+}
+
+int mh_codebook_create_empty(mh_codebook** out) {
+	if(!out) return MH_ERR_INVALID_ARG;
+	mh_codebook* cb = new(std::nothrow) mh_codebook;
+	if(!cb) return MH_ERR_INVALID_ARG;
+	*out = cb;
+	return MH_OK;
+}
+
+int mh_codebook_build_device(mh_codebook* cb, const uint64_t* d_counts, int order, mh_stream_t stream) {
+	return launch_build_codebook(reinterpret_cast<const unsigned long long*>(d_counts), order, cb, static_cast<cudaStream_t>(stream));
+}
+
+int mh_codebook_download(mh_codebook* cb, uint64_t* enc, uint32_t* ctx, uint32_t* meta) {
+	if(!cb || !cb->d_enc) return MH_ERR_INVALID_ARG;
+	MH_CUDA(cudaDeviceSynchronize());
+	const size_t ntab = cb->order ? 256 : 1;
+	if(enc) MH_CUDA(cudaMemcpy(enc, cb->d_enc, ntab * 256 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+	uint32_t m[8] = {cb->ctx_rows, 0, uint32_t(cb->max_bits), 0, 0, 0, 0, 0};
+	if(cb->device_built) MH_CUDA(cudaMemcpy(m, cb->d_meta, sizeof m, cudaMemcpyDeviceToHost));
+	if(meta) memcpy(meta, m, sizeof m);
+	if(ctx && cb->d_ctx && m[0] && m[0] <= uint32_t(kEncCtxMaxRows)) MH_CUDA(cudaMemcpy(ctx, cb->d_ctx, size_t(m[0]) * 256 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	return MH_OK;
 }
 
 int mh_dectable_create(const mh_table* t, mh_dectable** out) {

@@ -99,6 +99,9 @@ struct EncArgs {
 	uint32_t ctx_rows;
 	uint32_t bit0;
 	const unsigned long long* bit_base_dev;   // optional: the global bit offset lives in device memory (its low 3 bits replace bit0)
+	const unsigned long long* prev0_dev;      // optional: the byte before in[0] lives in device memory
+	const uint32_t* meta;                     // optional: tables built on the device: rows / status / longest codeword live there
+	uint32_t launched_bits;                   // ... and this launch was sized for at most ctx_rows rows and launched_bits-bit codewords
 	uint32_t stage_words;
 	uint32_t* out_words;
 	uint64_t out_capacity_words;
@@ -272,13 +275,23 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t bit0 = A.bit_base_dev ? uint32_t(__ldg(A.bit_base_dev) & 7ull) : A.bit0;
+	const uint32_t first_prev = A.prev0_dev ? uint32_t(__ldg(A.prev0_dev) & 255ull) : A.prev0;
+	uint32_t ctx_rows = A.ctx_rows;
+	if(FMT == FMT_CTX && A.meta) {   // device-built tables: check that this launch's shared memory and tile size fit them
+		ctx_rows = __ldg(A.meta);
+		const uint32_t status = __ldg(A.meta + 1), longest = __ldg(A.meta + 2);
+		if(status != 0 || ctx_rows > A.ctx_rows || longest > A.launched_bits) {
+			if(blockIdx.x == 0 && tid == 0) A.result[3] = status ? (unsigned long long) (long long) (int) status : 1ull;   // the caller takes the host-built path
+			return;
+		}
+	}
 	uint32_t table_entries = 0;
 	if(FMT == FMT_BOX_SMEM) {
 		table_entries = A.order ? (A.box_r + 1) * (A.box_r + 1) : 256u;
 		for(uint32_t i = tid; i < table_entries; i += kEncCtaThreads) table[i] = __ldg(A.box + i);
 	}
 	if(FMT == FMT_CTX) {
-		table_entries = A.ctx_rows * 256u;
+		table_entries = ctx_rows * 256u;
 		for(uint32_t i = tid; i < table_entries / 4; i += kEncCtaThreads) reinterpret_cast<uint4*>(table)[i] = __ldg(reinterpret_cast<const uint4*>(A.ctx) + i);
 	}
 	uint32_t* stage = smem + ((table_entries + 3) & ~3u) + 4;   // [stage_words + 4], after four zero words: stage[-1] reads as "no bits"
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				}
 			}
 			uint32_t prev = __shfl_up_sync(0xffffffffu, w[NWORDS - 1] >> 24, 1);
-			if(lane == 0 && my < A.n) prev = my == 0 ? A.prev0 : uint32_t(A.in[my - 1]);
+			if(lane == 0 && my < A.n) prev = my == 0 ? first_prev : uint32_t(A.in[my - 1]);
 			uint32_t my_bits = 0;
 			if constexpr(FMT == FMT_CTX) {
 				// One shared-memory lookup per symbol; the entry names the next context's row, so inside a quad the
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				// the byte before it (its row comes from the null row), so the eight quads of a thread are independent.
 				// Codewords are merged on the fly: pairs (<= 32 bits), then quads kept as (hi:lo, length) — a quad
 				// longer than 32 bits goes out in two steps.
-				const uint32_t null_row = table_sa + (A.ctx_rows - 1) * 1024u;
+				const uint32_t null_row = table_sa + (ctx_rows - 1) * 1024u;
 				uint32_t row = table_sa;
 				if(ORDER) row = table_sa + __byte_perm(lds32(null_row + prev * 4), 0, 0x4442) * 1024u;
 				uint32_t floor = 0xffffffffu, ceil = 0;
@@ -645,7 +658,7 @@ uint64_t encode_tiles_for(uint64_t n) { return (n + kEncThreads * 16 - 1) / (kEn
 
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
                   uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st,
-                  const unsigned long long* d_bit_base) {
+                  const unsigned long long* d_bit_base, const unsigned long long* d_prev0) {
 	if(!cb || !cb->d_enc || !d_result || (!d_in && n) || (!d_out && n)) return MH_ERR_INVALID_ARG;
 	if(reinterpret_cast<uint64_t>(d_out) & 3) return MH_ERR_INVALID_ARG;
 	if(!ws || !ws->enc_desc) return MH_ERR_WORKSPACE;
@@ -653,7 +666,12 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	if(n == 0) return MH_OK;
 
 	// table format
-	const int maxb = cb->max_bits > 0 ? cb->max_bits : 1;
+	// Device-built tables: the host knows neither the rows nor the longest codeword. The launch is sized for the largest
+	// context-row table that still leaves two CTAs per SM with kEncCtxMaxBits-bit codewords; the kernel checks the real
+	// values (d_meta) and reports through d_result[3] when they do not fit — the caller then takes the host-built path.
+	const bool dev = cb->device_built;
+	const uint32_t dev_rows = uint32_t((size_t(kEncCtxSmemLimit) - (size_t(kEncThreads) * kEncCtxMaxBits + 64) * 4) / 1024);
+	const int maxb = dev ? kEncCtxMaxBits : (cb->max_bits > 0 ? cb->max_bits : 1);
 	const int force_fmt = int(tunable(kTunEncFmt));   // experiments / tests: force a table format (0: box in shared memory, 1: box in global, 2: wide)
 	int fmt = FMT_WIDE;
 	size_t table_bytes = 0;
@@ -666,6 +684,10 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	if(cb->ctx_rows && force_fmt < 0 && size_t(cb->ctx_rows) * 1024 + (size_t(kEncThreads) * maxb + 64) * 4 <= size_t(kEncCtxSmemLimit)) {
 		fmt = FMT_CTX;
 		table_bytes = size_t(cb->ctx_rows) * 1024;
+	}
+	if(dev) {
+		fmt = FMT_CTX;
+		table_bytes = size_t(dev_rows) * 1024;
 	}
 	// Tile size: the staged bits of one tile must fit the staging area whatever the input, so symbols per tile x
 	// longest codeword bounds it: 32 symbols per thread while that bound stays within kEncStageMaxWords.
@@ -683,7 +705,10 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.in = d_in; a.n = n; a.prev0 = prev0; a.order = cb->order;
 	a.wide = reinterpret_cast<const unsigned long long*>(cb->d_enc);
 	a.box = cb->d_box; a.box_lo = cb->box_lo; a.box_r = cb->box_r;
-	a.ctx = cb->d_ctx; a.ctx_rows = cb->ctx_rows;
+	a.ctx = cb->d_ctx; a.ctx_rows = dev ? dev_rows : cb->ctx_rows;
+	a.meta = dev ? cb->d_meta : nullptr;
+	a.launched_bits = uint32_t(maxb);
+	a.prev0_dev = d_prev0;
 	a.bit0 = uint32_t(bit_base & 7);
 	a.bit_base_dev = d_bit_base;
 	a.stage_words = stage_words;

@@ -102,6 +102,10 @@ struct mh_codebook {
 	cudaEvent_t uploaded = nullptr;
 	int order = 1;
 	int max_bits = 0;
+	// tables built on the device from the device-resident histogram (mh_tables.cu): the host knows neither the number of
+	// context rows nor the longest codeword; the encoder reads them from d_meta and reports when its launch did not fit
+	uint32_t* d_meta = nullptr;    // [8] rows, status, longest codeword, live contexts; then rank[256] bytes
+	bool device_built = false;
 };
 
 struct mh_dectable {
@@ -123,16 +127,18 @@ namespace mh {
 // accumulate: add to d_counts instead of overwriting it (chunked inputs: the counts of the chunks add up)
 int launch_histogram(const uint8_t* d_in, uint64_t n, uint8_t prev0, int order, unsigned long long* d_counts,
                      mh_workspace* ws, cudaStream_t st, bool accumulate = false);
+// d_prev0 (optional): the byte before d_in[0] in DEVICE memory (replaces prev0).
 // d_bit_base (optional): the shard's global bit offset in DEVICE memory — its low three bits are the bit phase of the
 // first codeword and replace `bit_base` (a sharded compress computes the offsets on the device and never waits for them)
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
                   uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st,
-                  const unsigned long long* d_bit_base = nullptr);
+                  const unsigned long long* d_bit_base = nullptr, const unsigned long long* d_prev0 = nullptr);
 int launch_decode(const uint8_t* d_bits, uint64_t bit_base, uint64_t n_bits, uint8_t prev0, const mh_dectable* dt, uint8_t* d_out,
                   uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
 int launch_decode_shard(const uint8_t* d_bits, uint32_t start_bit, uint64_t n_bits, uint64_t buf_bytes, int exact_start, uint8_t prev0,
                         uint32_t warm_bits, int stream_end, const mh_dectable* dt, uint8_t* d_out, uint64_t out_capacity,
                         unsigned long long* d_result, mh_workspace* ws, cudaStream_t st, int fix_iters);
+int launch_build_codebook(const unsigned long long* d_counts, int order, mh_codebook* cb, cudaStream_t st);   // mh_tables.cu
 uint32_t decode_sub_bits(int order, uint64_t n_bits);   // subsequence size in bits for a stream of n_bits of this coder type
 uint64_t decode_max_subs(uint64_t max_payload_bytes);   // workspace bound on the number of subsequences
 uint64_t encode_tiles_for(uint64_t n);               // worst-case tile count for n input bytes

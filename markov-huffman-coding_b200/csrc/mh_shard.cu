@@ -102,6 +102,10 @@ struct LocalGroup {
 	int arrived = 0;
 	uint64_t generation = 0;
 	std::vector<const void*> send;
+	// ranks of one process working on shared host buffers (mh_sharded_*_host): seam bytes, per-rank values
+	std::vector<uint8_t> seam = std::vector<uint8_t>(MH_MAX_SHARDS, 0);
+	std::vector<uint64_t> value = std::vector<uint64_t>(MH_MAX_SHARDS, 0);
+	std::vector<int> status = std::vector<int>(MH_MAX_SHARDS, 0);
 	void barrier() {
 		std::unique_lock<std::mutex> lock(mu);
 		const uint64_t gen = generation;
@@ -234,6 +238,8 @@ __global__ void halo_splice_kernel(uint8_t* __restrict__ local, const uint8_t* _
 	}
 }
 
+int cuda_fail_if(cudaError_t e, const char* what) { return e == cudaSuccess ? MH_OK : cuda_fail(e, what); }
+
 double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 }  // namespace
@@ -247,7 +253,12 @@ enum { kStatGather = 0, kStatHalo, kStatSeam, kStatTrees, kStatCodebook, kStatDe
 struct mh_comm {
 	int device = 0, rank = 0, world = 1;
 	ncclComm_t nccl = nullptr;
-	std::shared_ptr<LocalGroup> local;
+	std::shared_ptr<LocalGroup> local;   // in-process transport (null with NCCL or a single rank)
+	std::shared_ptr<LocalGroup> host;    // ranks created together in one process share this (host barrier, seam bytes)
+	// device buffers of the host-buffer calls (mh_sharded_*_host), grown on demand outside the hot path
+	cudaStream_t stream = nullptr;
+	uint8_t *d_hin = nullptr, *d_hlocal = nullptr, *d_hout = nullptr;
+	uint64_t hin_cap = 0, hlocal_cap = 0, hout_cap = 0;
 	// per-rank state, sized on first use (mh_comm_reserve) — nothing is allocated on the hot path afterwards
 	mh_workspace* ws = nullptr;
 	uint64_t ws_input = 0, ws_payload = 0;
@@ -317,6 +328,86 @@ void add_elapsed(mh_comm* c, int stat, int ev_slot) {
 	else cudaGetLastError();
 }
 
+// Decode the bits [own_bit, own_bit + bits) of this rank's local buffer (bit coordinates of d_local; buf_end readable
+// bytes) and agree with the neighbours. spec == false: the start is exact (own_bit is a codeword boundary, prev0 the byte
+// before it, and the range ends on a codeword boundary). spec == true: every rank but the first starts kWarmBits before
+// own_bit from a guessed state; ONE all-gather of 32 bytes per rank carries symbol counts and seam states; a rank whose
+// warm-up did not reach the state its predecessor ended in decodes again from exactly that state. All ranks track what
+// every rank started from, so the handshake needs no second message. counts[g] = symbols rank g owns.
+int decode_with_handshake(mh_comm* c, uint8_t* d_local, uint64_t own_bit, uint64_t bits, uint64_t buf_end, bool spec, uint8_t first_prev0,
+                          uint8_t* d_out, uint64_t out_capacity, cudaStream_t st, bool time_halo, uint64_t* counts) {
+	const uint32_t world = uint32_t(c->world), r = uint32_t(c->rank);
+	unsigned long long* h_seams = c->h_small + 2 * world + 4;
+	bool exact = !spec || r == 0;
+	uint8_t prev0 = first_prev0;
+	uint64_t start = own_bit;
+	uint32_t warm = exact ? 0u : kWarmBits;
+	std::vector<int64_t> started(world, -1);
+	std::vector<uint64_t> views(world), ends(world);
+	int rounds = 0, rc = MH_OK;
+	for(;;) {
+		const uint64_t origin = start - warm;
+		const uint64_t off = (origin / 32) * 4;
+		const uint64_t n_bits = own_bit + bits - origin;
+		if(bits == 0 || own_bit + bits <= start) {
+			MH_CUDA(cudaMemsetAsync(c->d_result, 0, 4 * sizeof(unsigned long long), st));
+		} else {
+			rc = launch_decode_shard(d_local + off, uint32_t(origin % 32), n_bits, buf_end - off, exact ? 1 : 0, prev0, warm,
+			                         (!spec || r == world - 1) ? 1 : 0, &c->dec, d_out, out_capacity, c->d_result, c->ws, st, 2);
+			if(rc != MH_OK) return rc;
+		}
+		rc = all_gather(c, c->d_result, c->d_seams, 4 * sizeof(unsigned long long), st, 4);
+		if(rc != MH_OK) return rc;
+		MH_CUDA(cudaMemcpyAsync(h_seams, c->d_seams, 4 * world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		MH_CUDA(cudaStreamSynchronize(st));
+		if(time_halo) { add_elapsed(c, kStatHalo, 2); time_halo = false; }
+		add_elapsed(c, kStatSeam, 4);
+		int worst = 0;
+		for(uint32_t g = 0; g < world; ++g) {
+			const int64_t s1 = int64_t(h_seams[4 * g + 1]), s2 = int64_t(h_seams[4 * g + 2]);
+			if(s1 != 0 && (worst == 0 || s1 == MH_ERR_NOT_CONVERGED)) worst = int(s1);
+			if(s1 == 0 && s2 != 0 && worst == 0) worst = int(s2);
+			counts[g] = h_seams[4 * g];
+			views[g] = h_seams[4 * g + 3] >> 32;
+			ends[g] = h_seams[4 * g + 3] & 0xffffffffull;
+		}
+		if(worst != 0) return worst;   // every rank sees the same words and leaves together
+		if(!spec) break;
+		bool all_ok = true, mine_ok = true;
+		std::vector<int64_t> next_started = started;
+		for(uint32_t g = 1; g < world; ++g) {
+			const bool ok = started[g] >= 0 ? uint64_t(started[g]) == ends[g - 1] : views[g] == ends[g - 1];
+			if(!ok) {
+				all_ok = false;
+				next_started[g] = int64_t(ends[g - 1]);
+				if(g == r) mine_ok = false;
+			}
+		}
+		if(all_ok) break;
+		if(++rounds > int(world) + 1) { set_last_error("sharded decompress: the seam handshake did not converge"); return MH_ERR_NOT_CONVERGED; }
+		started = next_started;
+		if(!mine_ok) {   // decode again, this time from the state my predecessor really ended in
+			const uint64_t e = ends[r - 1];
+			exact = true;
+			prev0 = uint8_t(e & 255u);
+			warm = 0;
+			start = own_bit + (e >> 8);
+		}
+	}
+	c->stats[kStatRounds] += rounds;
+	return MH_OK;
+}
+
+int ensure_device(uint8_t** p, uint64_t* cap, uint64_t want) {
+	if(*cap >= want) return MH_OK;
+	if(*p) cudaFree(*p);
+	*p = nullptr;
+	*cap = 0;
+	MH_CUDA(cudaMalloc(p, want));
+	*cap = want;
+	return MH_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -368,7 +459,8 @@ int mh_comm_create_local(int world, const int* devices, int use_nccl, mh_comm** 
 		for(int b = a + 1; b < world; ++b) distinct = distinct && dev[a] != dev[b];
 	const bool with_nccl = use_nccl && world > 1 && distinct && nccl_api().ok;   // NCCL wants one rank per device
 	if(use_nccl > 1 && world > 1 && !with_nccl) { set_last_error("NCCL requested but not usable (not loaded, or two ranks share a device)"); return MH_ERR_CUDA; }
-	std::shared_ptr<LocalGroup> group = (world > 1 && !with_nccl) ? std::make_shared<LocalGroup>(world) : nullptr;
+	std::shared_ptr<LocalGroup> host_group = std::make_shared<LocalGroup>(world);
+	std::shared_ptr<LocalGroup> group = (world > 1 && !with_nccl) ? host_group : nullptr;
 	std::vector<ncclComm_t> comms(world, nullptr);
 	if(with_nccl) MH_NCCL(nccl_api().CommInitAll(comms.data(), world, dev.data()));
 	for(int r = 0; r < world; ++r) out[r] = nullptr;
@@ -379,6 +471,7 @@ int mh_comm_create_local(int world, const int* devices, int use_nccl, mh_comm** 
 			c->device = dev[r]; c->rank = r; c->world = world;
 			c->nccl = comms[r];
 			c->local = group;
+			c->host = host_group;
 			rc = comm_alloc(c);
 			out[r] = c;
 		}
@@ -415,7 +508,8 @@ void mh_comm_destroy(mh_comm* c) {
 	release_codebook(&c->book);
 	release_dectable(&c->dec);
 	mh_workspace_destroy(c->ws);
-	void* dptrs[] = {c->d_msg, c->d_gather, c->d_total, c->d_bits, c->d_layout, c->d_result, c->d_seams, c->d_halo, c->d_halos};
+	if(c->stream) cudaStreamDestroy(c->stream);
+	void* dptrs[] = {c->d_msg, c->d_gather, c->d_total, c->d_bits, c->d_layout, c->d_result, c->d_seams, c->d_halo, c->d_halos, c->d_hin, c->d_hlocal, c->d_hout};
 	for(void* p : dptrs)
 		if(p) cudaFree(p);
 	if(c->h_total) cudaFreeHost(c->h_total);
@@ -546,7 +640,6 @@ int mh_sharded_decompress(mh_comm* c, const mh_table* t, uint8_t* d_local, uint6
 		if(rc != MH_OK) return rc;
 		c->dec_serial = table_serial(t);
 	}
-	unsigned long long* h_seams = c->h_small + 2 * world + 4;
 	uint8_t* pay = d_local + kShardPad;
 	const bool spec = speculative && world > 1;
 	if(spec) {
@@ -562,74 +655,131 @@ int mh_sharded_decompress(mh_comm* c, const mh_table* t, uint8_t* d_local, uint6
 		count_launch(1);
 		MH_CUDA(cudaGetLastError());
 	}
-	const uint64_t buf_end = uint64_t(kShardPad) + nbytes + (spec ? kHaloHead : 0);
-	const uint64_t own_bit = uint64_t(kShardPad) * 8 + phase;   // my first bit, in local-buffer bit coordinates
-	bool exact = !spec || r == 0;
-	uint8_t prev0 = layout->prev0[r];
-	uint64_t start = own_bit;
-	uint32_t warm = exact ? 0u : kWarmBits;
-	// what every rank started from in this round (all ranks track all ranks: the handshake needs no extra message)
-	std::vector<int64_t> started(world, -1);
-	std::vector<uint64_t> views(world), ends(world), counts(world);
-	int rounds = 0;
-	bool first_halo = spec;
-	for(;;) {
-		const uint64_t origin = start - warm;
-		const uint64_t off = (origin / 32) * 4;
-		const uint64_t n_bits = own_bit + bits - origin;
-		if(bits == 0) {
-			MH_CUDA(cudaMemsetAsync(c->d_result, 0, 4 * sizeof(unsigned long long), st));
-		} else if(!spec) {
-			rc = launch_decode(pay, base, bits, prev0, &c->dec, d_out, out_capacity, c->d_result, c->ws, st, 2);
-		} else {
-			rc = launch_decode_shard(d_local + off, uint32_t(origin % 32), n_bits, buf_end - off, exact ? 1 : 0, prev0, warm, r == world - 1 ? 1 : 0, &c->dec,
-			                         d_out, out_capacity, c->d_result, c->ws, st, 2);
-		}
-		if(rc != MH_OK) return rc;
-		rc = all_gather(c, c->d_result, c->d_seams, 4 * sizeof(unsigned long long), st, 4);
-		if(rc != MH_OK) return rc;
-		MH_CUDA(cudaMemcpyAsync(h_seams, c->d_seams, 4 * world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-		MH_CUDA(cudaStreamSynchronize(st));
-		if(first_halo) { add_elapsed(c, kStatHalo, 2); first_halo = false; }
-		add_elapsed(c, kStatSeam, 4);
-		int worst = 0;
-		for(uint32_t g = 0; g < world; ++g) {
-			const int64_t s1 = int64_t(h_seams[4 * g + 1]), s2 = int64_t(h_seams[4 * g + 2]);
-			if(s1 != 0 && (worst == 0 || s1 == MH_ERR_NOT_CONVERGED)) worst = int(s1);
-			if(s1 == 0 && s2 != 0 && worst == 0) worst = int(s2);
-			counts[g] = h_seams[4 * g];
-			views[g] = h_seams[4 * g + 3] >> 32;
-			ends[g] = h_seams[4 * g + 3] & 0xffffffffull;
-		}
-		if(worst != 0) return worst;   // every rank sees the same words and leaves together
-		if(!spec) break;
-		bool all_ok = true, mine_ok = true;
-		std::vector<int64_t> next_started = started;
-		for(uint32_t g = 1; g < world; ++g) {
-			const bool ok = started[g] >= 0 ? uint64_t(started[g]) == ends[g - 1] : views[g] == ends[g - 1];
-			if(!ok) {
-				all_ok = false;
-				next_started[g] = int64_t(ends[g - 1]);
-				if(g == r) mine_ok = false;
-			}
-		}
-		if(all_ok) break;
-		if(++rounds > int(world) + 1) { set_last_error("sharded decompress: the seam handshake did not converge"); return MH_ERR_NOT_CONVERGED; }
-		started = next_started;
-		if(!mine_ok) {   // decode again, this time from the state my predecessor really ended in
-			const uint64_t e = ends[r - 1];
-			exact = true;
-			prev0 = uint8_t(e & 255u);
-			warm = 0;
-			start = own_bit + (e >> 8);
-		}
-	}
-	c->stats[kStatRounds] += rounds;
+	std::vector<uint64_t> counts(world);
+	rc = decode_with_handshake(c, d_local, uint64_t(kShardPad) * 8 + phase, bits, uint64_t(kShardPad) + nbytes + (spec ? kHaloHead : 0), spec,
+	                           layout->prev0[r], d_out, out_capacity, st, spec, counts.data());
+	if(rc != MH_OK) return rc;
 	c->stats[kStatCalls] += 1;
 	uint64_t before = 0;
 	for(uint32_t g = 0; g < r; ++g) before += counts[g];
 	*n_out = counts[r];
 	if(out_offset) *out_offset = before;
+	return MH_OK;
+}
+
+// ---- ranks of ONE process on shared host buffers (the multi-GPU path of a command-line driver) ---------------------
+// Every rank (its own host thread) passes the SAME host pointers; rank r takes its share. The calls return on every
+// rank when the whole result is in `out`.
+int mh_sharded_compress_host(mh_comm* c, const uint8_t* in, uint64_t n, int order, uint8_t* out, uint64_t out_capacity, uint64_t* out_len,
+                             mh_table** table_out) {
+	if(!c || !c->host || !out || !out_len || (!in && n) || (order != 0 && order != 1) || out_capacity < 1) return MH_ERR_INVALID_ARG;
+	MH_CUDA(cudaSetDevice(c->device));
+	LocalGroup& g = *c->host;
+	const uint64_t W = uint64_t(c->world), r = uint64_t(c->rank);
+	const uint64_t lo = n / W * r + (r < n % W ? r : n % W), len = n / W + (r < n % W ? 1 : 0);   // contiguous byte ranges in rank order
+	if(!c->stream) MH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	const uint64_t local_cap = mh_shard_local_bytes(len + len / 8 + 4096);
+	int rc = ensure_device(&c->d_hin, &c->hin_cap, len + 64);
+	if(rc == MH_OK) rc = ensure_device(&c->d_hlocal, &c->hlocal_cap, local_cap);
+	mh_shard_layout layout;
+	mh_table* t = nullptr;
+	if(rc == MH_OK && len) rc = cuda_fail_if(cudaMemcpyAsync(c->d_hin, in + lo, len, cudaMemcpyHostToDevice, c->stream), "H2D of the shard");
+	g.status[r] = rc;
+	g.barrier();   // nobody enters the collective unless everybody can
+	for(uint64_t q = 0; q < W; ++q)
+		if(g.status[q] != MH_OK) return g.status[q];
+	rc = mh_sharded_compress(c, c->d_hin, len, order, c->d_hlocal, c->hlocal_cap, &layout, &t, 0, c->stream);
+	if(rc != MH_OK) return rc;
+	const uint64_t total = 1 + (layout.total_bits + 7) / 8;
+	*out_len = total;
+	if(total > out_capacity) { mh_table_destroy(t); return MH_ERR_CAPACITY; }   // the same decision on every rank
+	const uint64_t base = layout.bit_base[r], bits = layout.n_bits[r];
+	const uint32_t phase = uint32_t(base & 7);
+	const uint64_t nbytes = (phase + bits + 7) / 8, first = 1 + (base >> 3);
+	const uint8_t* pay = c->d_hlocal + kShardPad;
+	cudaError_t ce = cudaSuccess;
+	g.seam[r] = 0;
+	g.value[r] = 0;
+	if(nbytes) {
+		if(phase) {   // my first byte is my predecessor's last: it keeps that one's bits; mine are merged below
+			ce = cudaMemcpyAsync(&g.seam[r], pay, 1, cudaMemcpyDeviceToHost, c->stream);
+			if(ce == cudaSuccess && nbytes > 1) ce = cudaMemcpyAsync(out + first + 1, pay + 1, nbytes - 1, cudaMemcpyDeviceToHost, c->stream);
+			g.value[r] = (first << 8) | phase;
+		} else {
+			ce = cudaMemcpyAsync(out + first, pay, nbytes, cudaMemcpyDeviceToHost, c->stream);
+		}
+	}
+	if(ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+	g.status[r] = ce == cudaSuccess ? MH_OK : cuda_fail(ce, "D2H of the payload shard");
+	g.barrier();
+	rc = MH_OK;
+	for(uint64_t q = 0; q < W; ++q)
+		if(g.status[q] != MH_OK) rc = g.status[q];
+	if(r == 0 && rc == MH_OK) {
+		for(uint64_t q = 0; q < W; ++q)
+			if(g.value[q]) out[g.value[q] >> 8] = uint8_t(out[g.value[q] >> 8] | (g.seam[q] & (0xFFu >> (g.value[q] & 7))));
+		out[0] = uint8_t(0x30 | ((~order & 1) << 3) | ((8 - layout.total_bits % 8) % 8));   // src/coding.cpp:88
+	}
+	g.barrier();   // the stream is complete when anybody returns
+	if(rc == MH_OK && table_out && r == 0) *table_out = t;
+	else mh_table_destroy(t);
+	return rc;
+}
+
+int mh_sharded_decompress_host(mh_comm* c, const mh_table* t, const uint8_t* stream, uint64_t stream_len, uint8_t* out, uint64_t out_capacity,
+                               uint64_t* out_len) {
+	if(!c || !c->host || !t || !stream || !out_len) return MH_ERR_INVALID_ARG;
+	if(stream_len < 1) return MH_ERR_BAD_HEADER;
+	const uint8_t header = stream[0];
+	if((header & 0xF0) != 0x30) return MH_ERR_BAD_HEADER;                       // src/coding.cpp:103-106
+	if(((~header >> 3) & 1) != table_order(t)) return MH_ERR_TYPE_MISMATCH;     // src/coding.cpp:107-110
+	const uint8_t* payload = stream + 1;
+	const uint64_t payload_bytes = stream_len - 1, remainder = header & 7;
+	const uint64_t B = payload_bytes * 8 < remainder ? 0 : payload_bytes * 8 - remainder;
+	const uint64_t W = uint64_t(c->world), r = uint64_t(c->rank);
+	if(W > 1 && B / W < 4ull * kHaloTail * 8) { set_last_error("sharded decompress: the stream is too short to cut; use one GPU"); return MH_ERR_INVALID_ARG; }
+	MH_CUDA(cudaSetDevice(c->device));
+	LocalGroup& g = *c->host;
+	if(!c->stream) MH_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	// bit ranges: cuts at multiples of 32 bits, wherever they fall inside codewords
+	auto cut = [&](uint64_t q) { return q >= W ? B : (B / W * q) & ~uint64_t(31); };
+	const uint64_t b0 = cut(r), b1 = cut(r + 1);
+	const uint64_t s0 = r == 0 ? 0 : (((b0 - kWarmBits) >> 3) - 8) & ~uint64_t(15);          // my slice of the payload: warm-up in front ...
+	const uint64_t e0 = (b1 >> 3) + kHaloHead + 8 < payload_bytes ? (b1 >> 3) + kHaloHead + 8 : payload_bytes;   // ... room for the last codeword behind
+	int rc = ensure_device(&c->d_hlocal, &c->hlocal_cap, e0 - s0 + 64);
+	if(rc == MH_OK) rc = ensure_device(&c->d_hout, &c->hout_cap, (e0 - s0) * 3 + 4096);
+	if(rc == MH_OK) rc = mh_comm_reserve(c, 0, e0 - s0 + 64);
+	if(rc == MH_OK && table_serial(t) != c->dec_serial) {
+		rc = upload_dectable_for(t, &c->dec, c->stream);
+		if(rc == MH_OK) c->dec_serial = table_serial(t);
+	}
+	if(rc == MH_OK) rc = cuda_fail_if(cudaMemsetAsync(c->d_hlocal + (e0 - s0), 0, 64, c->stream), "clearing the slack behind the slice");
+	if(rc == MH_OK && e0 > s0) rc = cuda_fail_if(cudaMemcpyAsync(c->d_hlocal, payload + s0, e0 - s0, cudaMemcpyHostToDevice, c->stream), "H2D of the slice");
+	std::vector<uint64_t> counts(W);
+	for(int attempt = 0;; ++attempt) {
+		g.status[r] = rc;
+		g.barrier();   // nobody enters the collective unless everybody can
+		for(uint64_t q = 0; q < W; ++q)
+			if(g.status[q] != MH_OK) return g.status[q];
+		rc = decode_with_handshake(c, c->d_hlocal, b0 - 8 * s0, b1 - b0, e0 - s0, W > 1, MH_PREV0, c->d_hout, c->hout_cap, c->stream, false, counts.data());
+		if(rc != MH_ERR_CAPACITY || attempt >= 2) break;
+		// some rank's symbols outgrew its buffer (the count pass told every rank how many each has): grow mine if it was me
+		rc = counts[r] > c->hout_cap ? ensure_device(&c->d_hout, &c->hout_cap, counts[r] + 64) : MH_OK;
+	}
+	if(rc != MH_OK) return rc;
+	uint64_t before = 0, total = 0;
+	for(uint64_t q = 0; q < W; ++q) {
+		if(q < r) before += counts[q];
+		total += counts[q];
+	}
+	*out_len = total;
+	if(total > out_capacity || !out) return total > out_capacity || total ? MH_ERR_CAPACITY : MH_OK;
+	cudaError_t ce = counts[r] ? cudaMemcpyAsync(out + before, c->d_hout, counts[r], cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+	if(ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+	g.status[r] = ce == cudaSuccess ? MH_OK : cuda_fail(ce, "D2H of the decoded bytes");
+	g.barrier();
+	for(uint64_t q = 0; q < W; ++q)
+		if(g.status[q] != MH_OK) return g.status[q];
 	return MH_OK;
 }
 

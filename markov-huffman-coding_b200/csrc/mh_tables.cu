@@ -1,0 +1,246 @@
+// mh_tables.cu — the encoder's tables built ON THE DEVICE from the device-resident histogram.
+//
+// The reference builds its (up to) 256 Huffman trees on the host (huffman_table::build, src/huffman.cpp:131-164, on
+// min_pq, src/min_pq.tpp:4-52) — microsecond work, but between the histogram and the encoder it is a device-to-host
+// copy of the counts, ~0.3 ms of host work and a host-to-device copy of the tables, all on the critical path of a
+// compress. Here one warp per context runs the SAME algorithm next to the data: the reference's array heap with its
+// strict comparisons (the tie-breaking is part of the format), int32 wrapping weights, the
+// "shallower subtree goes left" swap (src/huffman.cpp:147-149), the single-symbol fake root (:154-162) and the
+// pre-order code assignment (:97-123) — and writes the encoder's two flat tables straight into the codebook handle:
+//   wide   u64[ntab * 256]  len << 56 | code                                  (CodingTable::flatten_codebook)
+//   ctx    u32[rows * 256]  len << 27 | next row << 16 | code, + the null row  (CodingTable::flatten_ctx)
+// The host still builds its own mh_table from the same counts (for the table file and the decoder's tables), but off
+// the critical path, while the encoder runs; tests compare the device-built tables with the host-built ones bit by bit.
+// The serial part of a tree (heap operations) is done by lane 0 of the context's warp in shared memory; the warp
+// reads the counts and writes the table rows together. All contexts run in parallel on different SMs.
+//
+// meta (u32[8], device): [0] context rows incl. the null row, [1] status (0, or a negative mh_status: a live count that
+// wrapped to 0, a codeword longer than 56 bits), [2] longest codeword, [3] live contexts.
+#include "mh_internal.hpp"
+
+namespace mh {
+namespace {
+
+constexpr uint32_t kNoCode = 0;
+
+struct TreeScratch {
+	int32_t heap_w[256];
+	int16_t heap_n[256];
+	int16_t left[512], right[512];
+	int32_t weight[512];
+	int16_t height[512];
+	uint8_t symbol[256];      // of leaf i (leaves are nodes 0 .. n_leaves - 1, in ascending symbol order)
+	int16_t stack_node[260];
+	uint8_t stack_stage[260];
+	uint8_t len[256];
+	unsigned long long code[256];
+};
+
+// min_pq::insert (src/min_pq.tpp:4-8, swim :29-36): move up while the parent is strictly heavier
+__device__ __forceinline__ void heap_push(TreeScratch& S, int& hs, int32_t w, int node) {
+	int i = hs++;
+	S.heap_w[i] = w;
+	S.heap_n[i] = int16_t(node);
+	while(i > 0) {
+		const int up = (i - 1) >> 1;
+		if(!(S.heap_w[up] > S.heap_w[i])) break;
+		const int32_t tw = S.heap_w[up]; S.heap_w[up] = S.heap_w[i]; S.heap_w[i] = tw;
+		const int16_t tn = S.heap_n[up]; S.heap_n[up] = S.heap_n[i]; S.heap_n[i] = tn;
+		i = up;
+	}
+}
+
+// min_pq::pop_min (src/min_pq.tpp:9-27, sink :38-52): the right child only if strictly lighter than the left one, and a
+// swap only if the candidate is strictly lighter than the node
+__device__ __forceinline__ int heap_pop(TreeScratch& S, int& hs) {
+	const int top = S.heap_n[0];
+	--hs;
+	S.heap_w[0] = S.heap_w[hs];
+	S.heap_n[0] = S.heap_n[hs];
+	int i = 0;
+	for(;;) {
+		const int l = 2 * i + 1, r = l + 1;
+		const int pick = (r < hs && S.heap_w[r] < S.heap_w[l]) ? r : l;
+		if(pick >= hs || !(S.heap_w[pick] < S.heap_w[i])) break;
+		const int32_t tw = S.heap_w[pick]; S.heap_w[pick] = S.heap_w[i]; S.heap_w[i] = tw;
+		const int16_t tn = S.heap_n[pick]; S.heap_n[pick] = S.heap_n[i]; S.heap_n[i] = tn;
+		i = pick;
+	}
+	return top;
+}
+
+// One tree from S.weight[0 .. n_leaves) / S.symbol (lane 0). Fills S.len / S.code; returns 0 or a negative mh_status.
+__device__ int build_tree(TreeScratch& S, int n_leaves, uint32_t& max_len) {
+	int hs = 0, n = n_leaves;
+	for(int i = 0; i < n_leaves; ++i) {
+		S.left[i] = S.right[i] = -1;
+		S.height[i] = 0;
+		heap_push(S, hs, S.weight[i], i);   // ascending symbol order fixes the initial heap layout (src/huffman.cpp:134-138)
+	}
+	while(hs > 1) {
+		int a = heap_pop(S, hs), b = heap_pop(S, hs);
+		if(S.height[a] > S.height[b]) { const int t = a; a = b; b = t; }   // shallower subtree on the left (src/huffman.cpp:147-149)
+		S.left[n] = int16_t(a);
+		S.right[n] = int16_t(b);
+		S.weight[n] = int32_t(uint32_t(S.weight[a]) + uint32_t(S.weight[b]));   // int weight: wraps (src/tree.h:14,20)
+		S.height[n] = int16_t((S.height[a] > S.height[b] ? S.height[a] : S.height[b]) + 1);
+		heap_push(S, hs, S.weight[n], n);
+		++n;
+	}
+	const int root = heap_pop(S, hs);
+	if(S.left[root] < 0) {   // one live symbol: fake root over two copies of the leaf, the right copy ("1") wins (src/huffman.cpp:154-162)
+		S.len[S.symbol[root]] = 1;
+		S.code[S.symbol[root]] = 1ull;
+		max_len = 1;
+		return 0;
+	}
+	// pre-order walk, left edge 0, right edge 1 (src/huffman.cpp:97-123); stage 0 entering, 1 left done, 2 right done
+	int sp = 0, status = 0;
+	unsigned long long path = 0;
+	uint32_t longest = 0;
+	S.stack_node[0] = int16_t(root);
+	S.stack_stage[0] = 0;
+	while(sp >= 0) {
+		const int node = S.stack_node[sp];
+		if(S.left[node] < 0) {
+			const uint32_t depth = uint32_t(sp);
+			S.len[S.symbol[node]] = uint8_t(depth);
+			S.code[S.symbol[node]] = path;
+			if(depth > longest) longest = depth;
+			if(depth > uint32_t(MH_MAX_CODE_BITS)) status = MH_ERR_CODE_TOO_LONG;
+			--sp;
+			path >>= 1;
+			continue;
+		}
+		const int stage = S.stack_stage[sp];
+		if(stage == 0) {
+			S.stack_stage[sp] = 1;
+			path = path << 1;
+			++sp;
+			S.stack_node[sp] = S.left[node];
+			S.stack_stage[sp] = 0;
+		} else if(stage == 1) {
+			S.stack_stage[sp] = 2;
+			path = (path << 1) | 1ull;
+			++sp;
+			S.stack_node[sp] = S.right[node];
+			S.stack_stage[sp] = 0;
+		} else {
+			--sp;
+			path >>= 1;
+		}
+	}
+	max_len = longest;
+	return status;
+}
+
+// Which contexts have a tree, their rows, and the wrap check. One CTA of 256 threads: thread p looks at row p.
+__global__ void __launch_bounds__(256) tables_scan_kernel(const unsigned long long* __restrict__ counts, int order, uint32_t* __restrict__ meta,
+                                                           uint8_t* __restrict__ rank) {
+	__shared__ uint32_t warp_live[8];
+	const uint32_t p = threadIdx.x, lane = p & 31, warp = p >> 5;
+	bool live = false, wrapped = false;
+	if(order || p == 0) {
+		const unsigned long long* row = counts + size_t(p) * 256;
+		for(int s = 0; s < 256; ++s) {
+			const unsigned long long c = row[s];
+			live |= uint32_t(c) != 0;                        // the reference counts in `int` (src/main.cpp:166,174): the low 32 bits
+			wrapped |= c != 0 && uint32_t(c) == 0;           // a live count that its int counter shows as 0: the reference would lose the symbol
+		}
+	}
+	const uint32_t ballot = __ballot_sync(0xffffffffu, live);
+	if(lane == 0) warp_live[warp] = ballot;
+	const bool any_wrapped = __syncthreads_or(wrapped ? 1 : 0) != 0;
+	uint32_t before = __popc(ballot & ((1u << lane) - 1u)), total = 0;
+	for(uint32_t w = 0; w < 8; ++w) {
+		const uint32_t n = __popc(warp_live[w]);
+		if(w < warp) before += n;
+		total += n;
+	}
+	rank[p] = live ? uint8_t(before) : uint8_t(0xff);
+	if(p == 0) {
+		meta[0] = total + 1;                                 // + the null row
+		meta[1] = any_wrapped ? uint32_t(MH_ERR_COUNT_WRAPPED) : 0u;
+		meta[2] = 0;
+		meta[3] = total;
+	}
+}
+
+// One warp per context: tree, codes, and the context's rows of the two encoder tables.
+__global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long long* __restrict__ counts, int order, uint32_t* __restrict__ meta,
+                                                           const uint8_t* __restrict__ rank, unsigned long long* __restrict__ enc, uint32_t* __restrict__ ctx,
+                                                           uint32_t max_ctx_rows) {
+	__shared__ TreeScratch S;
+	__shared__ int s_leaves, s_status;
+	__shared__ uint32_t s_longest;
+	const uint32_t p = blockIdx.x, lane = threadIdx.x;
+	const uint32_t live = meta[3], rows = meta[0];
+	const bool ctx_fits = rows <= max_ctx_rows;
+	const uint32_t my_row = rank[p];
+	auto next_of = [&](uint32_t c) -> uint32_t { return order ? (rank[c] != 0xff ? uint32_t(rank[c]) : live) : 0u; };
+	if(blockIdx.x == gridDim.x - 1) {   // the extra block writes the null row
+		if(ctx_fits)
+			for(uint32_t c = lane; c < 256; c += 32) ctx[size_t(live) * 256 + c] = next_of(c) << 16;
+		return;
+	}
+	unsigned long long* enc_row = enc + size_t(p) * 256;
+	if(my_row == 0xff || meta[1] != 0) {   // no tree for this context (or the counts are unusable): no codewords
+		for(uint32_t c = lane; c < 256; c += 32) enc_row[c] = 0;
+		return;
+	}
+	const unsigned long long* row = counts + size_t(p) * 256;
+	for(uint32_t c = lane; c < 256; c += 32) { S.len[c] = 0; S.code[c] = 0; }
+	__syncwarp();
+	if(lane == 0) {
+		int n = 0;
+		for(int s = 0; s < 256; ++s) {
+			const int32_t w = int32_t(uint32_t(row[s]));
+			if(w != 0) { S.weight[n] = w; S.symbol[n] = uint8_t(s); ++n; }   // `if(counts[i])`: a wrapped-negative count is still a leaf
+		}
+		s_leaves = n;
+		uint32_t longest = 0;
+		s_status = build_tree(S, n, longest);
+		s_longest = longest;
+		atomicMax(meta + 2, longest);
+		if(s_status) meta[1] = uint32_t(s_status);
+	}
+	__syncwarp();
+	for(uint32_t c = lane; c < 256; c += 32) {
+		const uint32_t len = S.len[c];
+		const unsigned long long code = S.code[c];
+		enc_row[c] = len ? (static_cast<unsigned long long>(len) << 56) | code : 0ull;
+		if(ctx_fits)
+			ctx[size_t(my_row) * 256 + c] = len > 16 ? (31u << 27) | (next_of(c) << 16) : (len << 27) | (next_of(c) << 16) | (len ? uint32_t(code) : 0u);
+	}
+}
+
+}  // namespace
+
+// Builds cb's device tables from d_counts (u64[256] order 0 / u64[65536] order 1, device) on `st`. The handle must own
+// its device buffers (mh_codebook_create / a session / a comm). Nothing is copied to the host and the host does not wait.
+int launch_build_codebook(const unsigned long long* d_counts, int order, mh_codebook* cb, cudaStream_t st) {
+	if(!d_counts || !cb || (order != 0 && order != 1)) return MH_ERR_INVALID_ARG;
+	if(!cb->d_enc) MH_CUDA(cudaMalloc(&cb->d_enc, 65536 * sizeof(uint64_t)));
+	if(!cb->d_ctx) MH_CUDA(cudaMalloc(&cb->d_ctx, size_t(kEncCtxMaxRows) * 256 * sizeof(uint32_t)));
+	if(!cb->d_meta) MH_CUDA(cudaMalloc(&cb->d_meta, 8 * sizeof(uint32_t) + 256));
+	uint8_t* d_rank = reinterpret_cast<uint8_t*>(cb->d_meta + 8);
+	{
+		ProfScope p("tables_scan_kernel", st);
+		tables_scan_kernel<<<1, 256, 0, st>>>(d_counts, order, cb->d_meta, d_rank);
+	}
+	{
+		ProfScope p("tables_build_kernel", st);
+		tables_build_kernel<<<order ? 257 : 2, 32, 0, st>>>(d_counts, order, cb->d_meta, d_rank, reinterpret_cast<unsigned long long*>(cb->d_enc), cb->d_ctx,
+		                                                      uint32_t(kEncCtxMaxRows));
+	}
+	count_launch(2);
+	MH_CUDA(cudaGetLastError());
+	cb->order = order;
+	cb->device_built = true;
+	cb->has_box = false;
+	cb->ctx_rows = 0;   // unknown on the host: the encoder reads them from d_meta
+	cb->max_bits = 0;
+	return MH_OK;
+}
+
+}  // namespace mh

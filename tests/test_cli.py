@@ -134,3 +134,32 @@ def test_cli_streams_files_larger_than_its_device_buffers(tmp_path, simple, monk
     p = subprocess.run([CLI, out_c, "-o", out_d, "-xh" if simple else "-x", "-e", out_e], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode == 0, p.stderr
     assert open(out_d, "rb").read() == open(src, "rb").read()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("simple", [False, True], ids=["markov", "huffman"])
+@pytest.mark.parametrize("ranks", ["2", "3"])
+def test_cli_cuts_a_file_over_several_ranks(tmp_path, simple, ranks, monkeypatch):
+    """SURVEY §8e through the command line: MH_CLI_GPUS ranks (one host thread each; on a box with fewer GPUs they share
+    devices through the in-process transport) compress ONE file by byte ranges and extract it by bit ranges cut at
+    arbitrary bits. Same files as the reference binary writes."""
+    if not os.path.exists(o.REF_STOCK):
+        pytest.skip("oracle/_ref not present")
+    src = os.path.join(INPUTS, "input_wiki_cpp.html")      # 343 KB
+    mode = ["-h"] if simple else []
+    ref_c, ref_e = str(tmp_path / "ref.c"), str(tmp_path / "ref.e")
+    assert run([src, "-o", ref_c] + mode + ["-d", ref_e], exe=o.REF_STOCK).returncode == 0
+    monkeypatch.setenv("MH_CLI_GPUS", ranks)
+    out_c, out_e, out_d = str(tmp_path / "mine.c"), str(tmp_path / "mine.e"), str(tmp_path / "mine.d")
+    p = subprocess.run([CLI, src, "-o", out_c] + mode + ["-d", out_e], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr
+    assert open(out_c, "rb").read() == open(ref_c, "rb").read()
+    assert open(out_e, "rb").read() == open(ref_e, "rb").read()
+    p = subprocess.run([CLI, out_c, "-o", out_d, "-xh" if simple else "-x", "-e", out_e], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr
+    assert open(out_d, "rb").read() == open(src, "rb").read()
+    # a file too short to cut falls back to one GPU without a word
+    tiny = os.path.join(INPUTS, "input_b.txt")
+    assert run([tiny, "-o", out_c, "-d", out_e]).returncode == 0
+    assert run([out_c, "-o", out_d, "-x", "-e", out_e]).returncode == 0
+    assert open(out_d, "rb").read() == open(tiny, "rb").read()

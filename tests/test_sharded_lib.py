@@ -125,6 +125,34 @@ def test_speculative_mode_refuses_shards_shorter_than_the_warm_up(text):
             c.close()
 
 
+@pytest.mark.parametrize("order", [1, 0], ids=["markov", "huffman"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_host_buffer_calls_of_a_multi_gpu_driver(text, world, order):
+    """mh_sharded_compress_host / _decompress_host: all ranks of one process work on the SAME host buffers (what the CLI
+    does with several GPUs). The stream equals the oracle's; extraction cuts the payload at arbitrary bits."""
+    data = np.frombuffer(text, dtype=np.uint8)
+    want_stream, want_table = o.compress_from_input(text, bool(order))
+    out = np.zeros(len(text) + len(text) // 8 + 4200, dtype=np.uint8)
+    back = np.zeros(len(text) + 16, dtype=np.uint8)
+    comms = mh.Comm.create_local(world, devices=[0] * world, use_nccl=0)
+    try:
+        res = run_ranks(comms, lambda r, c: c.compress_host(data, order, out))
+        n = res[0][0]
+        assert all(x[0] == n for x in res) and res[0][1] is not None and all(x[1] is None for x in res[1:])
+        assert out[:n].tobytes() == want_stream
+        provider = res[0][1]
+        assert provider.write_coding_tree() == want_table
+        stream = out[:n].copy()
+        got = run_ranks(comms, lambda r, c: c.decompress_host(provider, stream, back))
+        assert all(x == len(text) for x in got) and back[:len(text)].tobytes() == text
+        small = np.frombuffer(want_stream[:2000], dtype=np.uint8)
+        with pytest.raises(AssertionError, match="invalid argument"):
+            run_ranks(comms, lambda r, c: c.decompress_host(provider, small, back))
+    finally:
+        for c in comms:
+            c.close()
+
+
 def test_nccl_ranks_one_per_gpu_equal_the_unsharded_stream(text):
     """>= 2 GPUs: the same through NCCL (ncclCommInitAll, one host thread per GPU)."""
     import torch
