@@ -110,7 +110,7 @@ void mh_codebook_destroy(mh_codebook* cb);
 /* The encoder's tables built ON THE DEVICE from the device-resident histogram (d_counts as mh_gpu_histogram writes it):
  * the same heap, tie-breaking and int32 weight arithmetic as the host's (src/huffman.cpp:131-164, src/min_pq.tpp), one
  * warp per context, stream-ordered, no copy to the host and no host wait between the histogram and the encoder. The
- * host's mh_table (table file, decoder tables) can be built from a copy of the counts meanwhile. mh_gpu_encode checks
+ * host's table object (for the table file and the decoder tables) can be built from a copy of the counts meanwhile. mh_gpu_encode checks
  * that its launch fits the tables that were built; when it does not (more than ~59 live contexts, a codeword longer
  * than 28 bits, a count that wrapped to 0) it writes nothing and sets d_result[3] != 0: encode again with a codebook
  * made from the host table (mh_codebook_update). mh_codebook_create_empty makes a handle without a table. */

@@ -822,15 +822,20 @@ static int session_compress_pipelined(mh_session* s, const mh_table* given, cons
 			                      reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream, /*accumulate=*/true);
 			if(rc != MH_OK) { drain_session(s); return rc; }
 		}
-		MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-		MH_CUDA_DRAIN(s, cudaStreamSynchronize(s->stream));
-		rc = mh_table_from_counts(s->h_counts, order, &built);
-		if(rc != MH_OK) return rc;
-		t = built;
+		// The encoder's tables are built on the device from the accumulated counts (mh_tables.cu): the first encode chunk
+		// follows the last histogram chunk without a host round trip. The counts travel to the host on the D2H stream
+		// meanwhile; the host builds its table (table file, header) while that chunk is encoded.
+		MH_CUDA_DRAIN(s, cudaEventRecord(s->ev_in[1], s->stream));
+		MH_CUDA_DRAIN(s, cudaStreamWaitEvent(s->d2h, s->ev_in[1], 0));
+		MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->d2h));
+		rc = launch_build_codebook(reinterpret_cast<const unsigned long long*>(s->d_counts), order, &s->book, s->stream);
+		if(rc != MH_OK) { drain_session(s); return rc; }
 	}
 	auto fail = [&](int code) { drain_session(s); if(built) mh_table_destroy(built); return code; };
-	rc = upload_codebook(t, &s->book, s->stream);
-	if(rc != MH_OK) return fail(rc);
+	if(given) {
+		rc = upload_codebook(t, &s->book, s->stream);
+		if(rc != MH_OK) return fail(rc);
+	}
 	if(given && n) {   // the first chunk starts its trip now
 		const uint64_t len = n < chunk ? n : chunk;
 		if(cudaMemcpyAsync(s->d_raw, in, len, cudaMemcpyHostToDevice, s->h2d) != cudaSuccess || cudaEventRecord(s->ev_in[0], s->h2d) != cudaSuccess)
@@ -859,9 +864,24 @@ static int session_compress_pipelined(mh_session* s, const mh_table* given, cons
 		rc = launch_encode(s->d_raw + off, len, off ? in[off - 1] : uint8_t(MH_PREV0), &s->book, bit_base, d_half, half,
 		                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
 		if(rc != MH_OK) return fail(rc);
-		if(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
-		   cudaStreamSynchronize(s->stream) != cudaSuccess)
+		if(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess)
 			return fail(cuda_fail(cudaGetLastError(), "pipelined compress: result"));
+		if(!t) {   // the host's table, built while the first chunk is encoded from the device-built tables
+			if(cudaStreamSynchronize(s->d2h) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "pipelined compress: counts"));
+			rc = mh_table_from_counts(s->h_counts, order, &built);
+			if(rc != MH_OK) return fail(rc);
+			t = built;
+		}
+		if(cudaStreamSynchronize(s->stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "pipelined compress: result"));
+		if(s->h_result[3]) {   // the device-built tables did not fit the encoder's launch: the host's tables, this chunk again
+			rc = upload_codebook(t, &s->book, s->stream);
+			if(rc == MH_OK) rc = launch_encode(s->d_raw + off, len, off ? in[off - 1] : uint8_t(MH_PREV0), &s->book, bit_base, d_half, half,
+			                                   reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
+			if(rc != MH_OK) return fail(rc);
+			if(cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+			   cudaStreamSynchronize(s->stream) != cudaSuccess)
+				return fail(cuda_fail(cudaGetLastError(), "pipelined compress: result"));
+		}
 		if(s->h_result[2]) return fail(MH_ERR_WORKSPACE);
 		const uint64_t bits = s->h_result[0];
 		drop += s->h_result[1];
@@ -881,6 +901,12 @@ static int session_compress_pipelined(mh_session* s, const mh_table* given, cons
 		if(ce == cudaSuccess) ce = cudaEventRecord(s->ev_out[cur], s->d2h);
 		if(ce != cudaSuccess) return fail(cuda_fail(ce, "pipelined compress: D2H"));
 		bit_base += bits;
+	}
+	if(!t) {   // an empty input: no chunk was encoded
+		if(cudaStreamSynchronize(s->d2h) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "pipelined compress: counts"));
+		rc = mh_table_from_counts(s->h_counts, order, &built);
+		if(rc != MH_OK) return fail(rc);
+		t = built;
 	}
 	drain_session(s);
 	for(const Seam& sm : seams) out[sm.at] = uint8_t(out[sm.at] | (s->h_seam[sm.k] & (0xFFu >> sm.phase)));
@@ -915,16 +941,43 @@ int mh_session_compress(mh_session* s, const uint8_t* in, uint64_t n, int order,
 		const int prc = session_compress_pipelined(s, nullptr, in, n, order, out, out_capacity, out_len, nullptr, table_out);
 		if(prc != MH_ERR_WORKSPACE) return prc;
 	}
+	if(out_capacity < 1) return MH_ERR_CAPACITY;
+	int rc = ensure_pipe_streams(s);
+	if(rc != MH_OK) return rc;
 	if(n) MH_CUDA(cudaMemcpyAsync(s->d_raw, in, n, cudaMemcpyHostToDevice, s->stream));
-	int rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
+	rc = launch_histogram(s->d_raw, n, MH_PREV0, order, reinterpret_cast<unsigned long long*>(s->d_counts), s->ws, s->stream);
 	if(rc != MH_OK) return rc;
 	const size_t bins = order ? 65536 : 256;
-	MH_CUDA(cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-	MH_CUDA(cudaStreamSynchronize(s->stream));
+	// histogram -> encoder tables on the device -> encoder, without a host round trip; the counts travel to the host on
+	// the side stream, where the host's table (table file, header) is built while the encoder runs
+	MH_CUDA(cudaEventRecord(s->ev_in[1], s->stream));
+	MH_CUDA(cudaStreamWaitEvent(s->d2h, s->ev_in[1], 0));
+	MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->h_counts, s->d_counts, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->d2h));
+	rc = launch_build_codebook(reinterpret_cast<const unsigned long long*>(s->d_counts), order, &s->book, s->stream);
+	if(rc == MH_OK) rc = launch_encode(s->d_raw, n, MH_PREV0, &s->book, 0, s->d_payload, s->payload_cap, reinterpret_cast<unsigned long long*>(s->d_result), s->ws, s->stream);
+	if(rc != MH_OK) { drain_session(s); return rc; }
+	MH_CUDA_DRAIN(s, cudaMemcpyAsync(s->h_result, s->d_result, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+	MH_CUDA_DRAIN(s, cudaStreamSynchronize(s->d2h));
 	mh_table* t = nullptr;
 	rc = mh_table_from_counts(s->h_counts, order, &t);
-	if(rc != MH_OK) return rc;
-	rc = session_encode(s, t, n, out, out_capacity, out_len, nullptr);
+	if(rc != MH_OK) { drain_session(s); return rc; }
+	MH_CUDA_DRAIN(s, cudaStreamSynchronize(s->stream));
+	if(s->h_result[3]) {   // the device-built tables did not fit the encoder's launch: the host's tables
+		rc = session_encode(s, t, n, out, out_capacity, out_len, nullptr);
+	} else if(s->h_result[2]) {
+		rc = MH_ERR_CAPACITY;
+	} else {
+		const uint64_t bits = s->h_result[0], bytes = (bits + 7) / 8;
+		*out_len = 1 + bytes;
+		if(1 + bytes > out_capacity) rc = MH_ERR_CAPACITY;
+		else {
+			out[0] = stream_header(order, bits);
+			if(bytes) {
+				MH_CUDA_DRAIN(s, cudaMemcpyAsync(out + 1, s->d_payload, bytes, cudaMemcpyDeviceToHost, s->stream));
+				MH_CUDA_DRAIN(s, cudaStreamSynchronize(s->stream));
+			}
+		}
+	}
 	if(rc == MH_OK && table_out) *table_out = t;
 	else mh_table_destroy(t);
 	return rc;

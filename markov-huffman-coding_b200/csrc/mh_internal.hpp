@@ -48,7 +48,7 @@ constexpr int kEncCtaThreads = kEncThreads + 32;      // + the scanner warp (dec
 constexpr int kEncStageMaxWords = 14336;              // at most 56 KiB of staged output bits per tile
 constexpr int kEncBoxSmemLimit = 72 * 1024;           // largest u32 box table staged in shared memory (R <= 135)
 constexpr int kEncBoxMaxBits = 27;                    // u32 entry: 5-bit length | 27-bit right-aligned code
-constexpr int kEncCtxMaxBits = 28;                    // context-row entry: 5-bit length | 8-bit next row | 16-bit code; longer codewords (<= 28) escape to the wide table
+constexpr int kEncCtxMaxBits = 29;                    // context-row entry: 5-bit length | 8-bit next row | 16-bit code; longer codewords (<= 29: 480 x 32 symbols of them still fit the staging area) escape to the wide table
 constexpr int kEncCtxMaxRows = 96;                    // live contexts + null row; table + staging must leave room for 2 CTAs/SM
 constexpr int kEncCtxSmemLimit = 112 * 1024;          // table + staging area of one CTA
 constexpr int kDecThreads = 1024;                     // subsequences per chunk (one thread each)

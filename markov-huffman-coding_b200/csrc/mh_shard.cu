@@ -7,11 +7,14 @@
 //   1. every rank counts its byte range (mh_gpu_histogram's kernels), guessing ' ' as the byte before it, and appends
 //      its first and last byte: ONE all-gather of 65,538 x u64 per rank carries everything the phase needs;
 //   2. a kernel sums the gathered histograms and moves the one seam pair per shard to the context it really has (the
-//      predecessor's last byte), in the sum and in the shard's own row; the sum goes to the host, which builds the
-//      (identical) trees — the only host round trip between the gather and the encoder;
-//   3. a kernel multiplies every rank's counts with the code lengths of the uploaded codebook: every rank knows every
-//      shard's payload size and bit offset without another exchange, and the encoder reads its bit phase from that
-//      device word (launch_encode's d_bit_base) — the host learns the layout when the encoder has finished.
+//      predecessor's last byte), in the sum and in the shard's own row; the encoder's tables are built from the sum ON
+//      THE DEVICE (mh_tables.cu), identically on every rank — no host round trip between the gather and the encoder;
+//      the sum also travels to the host on a side stream, where the (identical) host table is built while the encoder
+//      runs (table file, decoder tables);
+//   3. a kernel multiplies every rank's counts with the code lengths of the codebook: every rank knows every
+//      shard's payload size and bit offset without another exchange, and the encoder reads its bit phase and its
+//      first context from device words (launch_encode's d_bit_base / d_prev0) — the host learns the layout when the
+//      encoder has finished.
 // decompress (bit-range shards)
 //   exact mode: the layout's cuts are codeword boundaries with known contexts (what compress produces): no exchange
 //   at all beyond one all-gather of the symbol counts (output offsets).
@@ -257,6 +260,8 @@ struct mh_comm {
 	std::shared_ptr<LocalGroup> host;    // ranks created together in one process share this (host barrier, seam bytes)
 	// device buffers of the host-buffer calls (mh_sharded_*_host), grown on demand outside the hot path
 	cudaStream_t stream = nullptr;
+	cudaStream_t side = nullptr;         // carries the summed counts to the host while the caller's stream encodes
+	cudaEvent_t ev_side = nullptr;
 	uint8_t *d_hin = nullptr, *d_hlocal = nullptr, *d_hout = nullptr;
 	uint64_t hin_cap = 0, hlocal_cap = 0, hout_cap = 0;
 	// per-rank state, sized on first use (mh_comm_reserve) — nothing is allocated on the hot path afterwards
@@ -509,6 +514,8 @@ void mh_comm_destroy(mh_comm* c) {
 	release_dectable(&c->dec);
 	mh_workspace_destroy(c->ws);
 	if(c->stream) cudaStreamDestroy(c->stream);
+	if(c->side) cudaStreamDestroy(c->side);
+	if(c->ev_side) cudaEventDestroy(c->ev_side);
 	void* dptrs[] = {c->d_msg, c->d_gather, c->d_total, c->d_bits, c->d_layout, c->d_result, c->d_seams, c->d_halo, c->d_halos, c->d_hin, c->d_hlocal, c->d_hout};
 	for(void* p : dptrs)
 		if(p) cudaFree(p);
@@ -563,37 +570,58 @@ int mh_sharded_compress(mh_comm* c, const uint8_t* d_in, uint64_t n, int order, 
 	shard_seam_kernel<<<1, 1, 0, st>>>(c->d_gather, world, order, c->d_total, c->d_total + 65536);
 	count_launch(2);
 	MH_CUDA(cudaGetLastError());
-	MH_CUDA(cudaMemcpyAsync(c->h_total, c->d_total, bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-	MH_CUDA(cudaMemcpyAsync(c->h_total + 65536, c->d_total + 65536, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-	MH_CUDA(cudaStreamSynchronize(st));
-	add_elapsed(c, kStatGather, 0);
-	const double t0 = now_us();
-	mh_table* t = nullptr;
-	rc = mh_table_from_counts(reinterpret_cast<const uint64_t*>(c->h_total), order, &t);   // identical on every rank
+	// 3. The encoder's tables are built on the device from the summed counts (mh_tables.cu) and every shard's payload
+	//    size and bit offset follow from the gathered counts x code lengths: nothing between the gather and the encoder
+	//    waits for the host. The counts travel to the host on a side stream meanwhile; the host builds its (identical)
+	//    table from them while the encoder runs — the table file, the decoder's tables and the layout need it, not the encoder.
+	if(!c->side) MH_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+	if(!c->ev_side) MH_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+	MH_CUDA(cudaEventRecord(c->ev_side, st));
+	MH_CUDA(cudaStreamWaitEvent(c->side, c->ev_side, 0));
+	MH_CUDA(cudaMemcpyAsync(c->h_total, c->d_total, bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->side));
+	MH_CUDA(cudaMemcpyAsync(c->h_total + 65536, c->d_total + 65536, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->side));
+	rc = launch_build_codebook(c->d_total, order, &c->book, st);
 	if(rc != MH_OK) return rc;
-	const double t1 = now_us();
-	rc = upload_codebook_for(t, &c->book, st);
-	const double t2 = now_us();
-	if(rc != MH_OK) { mh_table_destroy(t); return rc; }
-	c->stats[kStatTrees] += t1 - t0;
-	c->stats[kStatCodebook] += t2 - t1;
-	// 3. every shard's payload size and bit offset from the gathered counts; the encoder takes its bit phase from there
 	shard_bits_kernel<<<world, 256, 0, st>>>(c->d_gather, reinterpret_cast<const unsigned long long*>(c->book.d_enc), bins, c->d_bits);
 	shard_scan_kernel<<<1, 32, 0, st>>>(c->d_bits, world, c->d_layout);
 	count_launch(2);
-	const uint8_t prev0 = uint8_t(c->h_total[65536 + c->rank]);
-	rc = launch_encode(d_in, n, prev0, &c->book, 0, d_local + kShardPad, pay_cap, c->d_result, c->ws, st, c->d_layout + c->rank);
-	if(rc != MH_OK) { mh_table_destroy(t); return rc; }
+	rc = launch_encode(d_in, n, MH_PREV0, &c->book, 0, d_local + kShardPad, pay_cap, c->d_result, c->ws, st, c->d_layout + c->rank, c->d_total + 65536 + c->rank);
+	if(rc != MH_OK) return rc;
 	unsigned long long* h_layout = c->h_small;
 	unsigned long long* h_result = c->h_small + 2 * world;
 	MH_CUDA(cudaMemcpyAsync(h_layout, c->d_layout, 2 * world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 	MH_CUDA(cudaMemcpyAsync(h_result, c->d_result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	MH_CUDA(cudaStreamSynchronize(c->side));   // the counts have arrived (the encoder is still running)
+	add_elapsed(c, kStatGather, 0);
+	const double t0 = now_us();
+	mh_table* t = nullptr;
+	rc = mh_table_from_counts(reinterpret_cast<const uint64_t*>(c->h_total), order, &t);   // identical on every rank
+	if(rc != MH_OK) { cudaStreamSynchronize(st); return rc; }
+	c->stats[kStatTrees] += now_us() - t0;
 	if(prepare_decode) {   // the decoder's tables are flattened on the host while the encoder runs
 		const double t3 = now_us();
 		rc = upload_dectable_for(t, &c->dec, st);
 		c->stats[kStatDectable] += now_us() - t3;
 		if(rc != MH_OK) { mh_table_destroy(t); return rc; }
 		c->dec_serial = table_serial(t);
+	}
+	MH_CUDA(cudaStreamSynchronize(st));
+	if(h_result[3]) {
+		// the device-built tables did not fit the encoder's launch (many live contexts, very long codewords): the host's
+		// tables, the classic way. Every rank sees the same tables and takes this branch together.
+		const double t1 = now_us();
+		rc = upload_codebook_for(t, &c->book, st);
+		c->stats[kStatCodebook] += now_us() - t1;
+		if(rc == MH_OK) {
+			shard_bits_kernel<<<world, 256, 0, st>>>(c->d_gather, reinterpret_cast<const unsigned long long*>(c->book.d_enc), bins, c->d_bits);
+			shard_scan_kernel<<<1, 32, 0, st>>>(c->d_bits, world, c->d_layout);
+			count_launch(2);
+			rc = launch_encode(d_in, n, uint8_t(c->h_total[65536 + c->rank]), &c->book, 0, d_local + kShardPad, pay_cap, c->d_result, c->ws, st, c->d_layout + c->rank);
+		}
+		if(rc != MH_OK) { mh_table_destroy(t); return rc; }
+		MH_CUDA(cudaMemcpyAsync(h_layout, c->d_layout, 2 * world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		MH_CUDA(cudaMemcpyAsync(h_result, c->d_result, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+		MH_CUDA(cudaStreamSynchronize(st));
 	}
 	MH_CUDA(cudaStreamSynchronize(st));
 	c->stats[kStatCalls] += 1;

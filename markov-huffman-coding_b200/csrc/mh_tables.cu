@@ -21,8 +21,6 @@
 namespace mh {
 namespace {
 
-constexpr uint32_t kNoCode = 0;
-
 struct TreeScratch {
 	int32_t heap_w[256];
 	int16_t heap_n[256];
@@ -134,57 +132,66 @@ __device__ int build_tree(TreeScratch& S, int n_leaves, uint32_t& max_len) {
 	return status;
 }
 
-// Which contexts have a tree, their rows, and the wrap check. One CTA of 256 threads: thread p looks at row p.
-__global__ void __launch_bounds__(256) tables_scan_kernel(const unsigned long long* __restrict__ counts, int order, uint32_t* __restrict__ meta,
-                                                           uint8_t* __restrict__ rank) {
-	__shared__ uint32_t warp_live[8];
-	const uint32_t p = threadIdx.x, lane = p & 31, warp = p >> 5;
+// Which contexts have a tree, and the wrap check: one warp per context row, coalesced. flags[p]: bit 0 live, bit 1 a
+// live count that the reference's int counter shows as 0.
+__global__ void __launch_bounds__(32) tables_scan_kernel(const unsigned long long* __restrict__ counts, uint8_t* __restrict__ flags) {
+	const uint32_t p = blockIdx.x, lane = threadIdx.x;
+	const unsigned long long* row = counts + size_t(p) * 256;
 	bool live = false, wrapped = false;
-	if(order || p == 0) {
-		const unsigned long long* row = counts + size_t(p) * 256;
-		for(int s = 0; s < 256; ++s) {
-			const unsigned long long c = row[s];
-			live |= uint32_t(c) != 0;                        // the reference counts in `int` (src/main.cpp:166,174): the low 32 bits
-			wrapped |= c != 0 && uint32_t(c) == 0;           // a live count that its int counter shows as 0: the reference would lose the symbol
-		}
+#pragma unroll
+	for(int k = 0; k < 8; ++k) {
+		const unsigned long long c = row[k * 32 + lane];
+		live |= uint32_t(c) != 0;                        // the reference counts in `int` (src/main.cpp:166,174): the low 32 bits
+		wrapped |= c != 0 && uint32_t(c) == 0;           // the reference would lose this symbol
 	}
-	const uint32_t ballot = __ballot_sync(0xffffffffu, live);
-	if(lane == 0) warp_live[warp] = ballot;
-	const bool any_wrapped = __syncthreads_or(wrapped ? 1 : 0) != 0;
-	uint32_t before = __popc(ballot & ((1u << lane) - 1u)), total = 0;
-	for(uint32_t w = 0; w < 8; ++w) {
-		const uint32_t n = __popc(warp_live[w]);
-		if(w < warp) before += n;
-		total += n;
-	}
-	rank[p] = live ? uint8_t(before) : uint8_t(0xff);
-	if(p == 0) {
-		meta[0] = total + 1;                                 // + the null row
-		meta[1] = any_wrapped ? uint32_t(MH_ERR_COUNT_WRAPPED) : 0u;
-		meta[2] = 0;
-		meta[3] = total;
-	}
+	live = __any_sync(0xffffffffu, live);
+	wrapped = __any_sync(0xffffffffu, wrapped);
+	if(lane == 0) flags[p] = uint8_t((live ? 1 : 0) | (wrapped ? 2 : 0));
 }
 
 // One warp per context: tree, codes, and the context's rows of the two encoder tables.
 __global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long long* __restrict__ counts, int order, uint32_t* __restrict__ meta,
-                                                           const uint8_t* __restrict__ rank, unsigned long long* __restrict__ enc, uint32_t* __restrict__ ctx,
+                                                           const uint8_t* __restrict__ flags, unsigned long long* __restrict__ enc, uint32_t* __restrict__ ctx,
                                                            uint32_t max_ctx_rows) {
 	__shared__ TreeScratch S;
-	__shared__ int s_leaves, s_status;
-	__shared__ uint32_t s_longest;
+	__shared__ uint8_t rank[256];   // row of every byte value as a context (0xff: no tree)
+	__shared__ int s_status;
 	const uint32_t p = blockIdx.x, lane = threadIdx.x;
-	const uint32_t live = meta[3], rows = meta[0];
+	// every block ranks the live contexts itself (256 flag bytes): lane l owns the values 8 l .. 8 l + 7
+	uint32_t mine = 0, bad = 0;
+	for(uint32_t k = 0; k < 8; ++k) {
+		const uint32_t f = (order || lane * 8 + k == 0) ? flags[lane * 8 + k] : 0u;
+		mine |= (f & 1u) << k;
+		bad |= f & 2u;
+	}
+	uint32_t before = __popc(mine);
+	for(int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, before, d);
+		if(lane >= uint32_t(d)) before += t;
+	}
+	const uint32_t live = __shfl_sync(0xffffffffu, before, 31), rows = live + 1;
+	before -= __popc(mine);
+	for(uint32_t k = 0; k < 8; ++k) {
+		rank[lane * 8 + k] = (mine >> k) & 1u ? uint8_t(before) : uint8_t(0xff);
+		before += (mine >> k) & 1u;
+	}
+	const bool wrapped = __any_sync(0xffffffffu, bad != 0);
+	__syncwarp();
 	const bool ctx_fits = rows <= max_ctx_rows;
-	const uint32_t my_row = rank[p];
+	const uint32_t my_row = rank[p & 255u];
 	auto next_of = [&](uint32_t c) -> uint32_t { return order ? (rank[c] != 0xff ? uint32_t(rank[c]) : live) : 0u; };
-	if(blockIdx.x == gridDim.x - 1) {   // the extra block writes the null row
+	if(blockIdx.x == gridDim.x - 1) {   // the extra block writes the null row and the summary
 		if(ctx_fits)
 			for(uint32_t c = lane; c < 256; c += 32) ctx[size_t(live) * 256 + c] = next_of(c) << 16;
+		if(lane == 0) {
+			meta[0] = rows;
+			meta[3] = live;
+			if(wrapped) meta[1] = uint32_t(MH_ERR_COUNT_WRAPPED);
+		}
 		return;
 	}
 	unsigned long long* enc_row = enc + size_t(p) * 256;
-	if(my_row == 0xff || meta[1] != 0) {   // no tree for this context (or the counts are unusable): no codewords
+	if(my_row == 0xff || wrapped) {   // no tree for this context (or the counts are unusable): no codewords
 		for(uint32_t c = lane; c < 256; c += 32) enc_row[c] = 0;
 		return;
 	}
@@ -197,10 +204,8 @@ __global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long lo
 			const int32_t w = int32_t(uint32_t(row[s]));
 			if(w != 0) { S.weight[n] = w; S.symbol[n] = uint8_t(s); ++n; }   // `if(counts[i])`: a wrapped-negative count is still a leaf
 		}
-		s_leaves = n;
 		uint32_t longest = 0;
 		s_status = build_tree(S, n, longest);
-		s_longest = longest;
 		atomicMax(meta + 2, longest);
 		if(s_status) meta[1] = uint32_t(s_status);
 	}
@@ -223,15 +228,16 @@ int launch_build_codebook(const unsigned long long* d_counts, int order, mh_code
 	if(!cb->d_enc) MH_CUDA(cudaMalloc(&cb->d_enc, 65536 * sizeof(uint64_t)));
 	if(!cb->d_ctx) MH_CUDA(cudaMalloc(&cb->d_ctx, size_t(kEncCtxMaxRows) * 256 * sizeof(uint32_t)));
 	if(!cb->d_meta) MH_CUDA(cudaMalloc(&cb->d_meta, 8 * sizeof(uint32_t) + 256));
-	uint8_t* d_rank = reinterpret_cast<uint8_t*>(cb->d_meta + 8);
+	uint8_t* d_flags = reinterpret_cast<uint8_t*>(cb->d_meta + 8);
+	MH_CUDA(cudaMemsetAsync(cb->d_meta, 0, 8 * sizeof(uint32_t), st));
 	{
 		ProfScope p("tables_scan_kernel", st);
-		tables_scan_kernel<<<1, 256, 0, st>>>(d_counts, order, cb->d_meta, d_rank);
+		tables_scan_kernel<<<order ? 256 : 1, 32, 0, st>>>(d_counts, d_flags);
 	}
 	{
 		ProfScope p("tables_build_kernel", st);
-		tables_build_kernel<<<order ? 257 : 2, 32, 0, st>>>(d_counts, order, cb->d_meta, d_rank, reinterpret_cast<unsigned long long*>(cb->d_enc), cb->d_ctx,
-		                                                      uint32_t(kEncCtxMaxRows));
+		tables_build_kernel<<<order ? 257 : 2, 32, 0, st>>>(d_counts, order, cb->d_meta, d_flags, reinterpret_cast<unsigned long long*>(cb->d_enc), cb->d_ctx,
+		                                                   uint32_t(kEncCtxMaxRows));
 	}
 	count_launch(2);
 	MH_CUDA(cudaGetLastError());
