@@ -104,6 +104,8 @@ const TunableDef kTunables[kTunCount] = {
     {"pipe_chunk_bytes", "MH_PIPE_CHUNK_BYTES"},
     {"enc_pipe_chunk_bytes", "MH_ENC_PIPE_CHUNK_BYTES"},
     {"dec_fused", "MH_DEC_FUSED"},
+    {"enc_tma", "MH_ENC_TMA"},
+    {"dec_cp_geo", "MH_DEC_CP_GEO"},
 };
 std::atomic<long long> g_tunables[kTunCount];
 struct TunableInit {

@@ -285,7 +285,7 @@ __device__ __forceinline__ uint32_t pack_cp(uint32_t rel_bits, uint32_t ctx) { r
 
 template <int ORDER>
 __device__ __forceinline__ bool walk_subsequence(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
-                                                 const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t seg_bits, uint32_t span,
+                                                 const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t unit, uint64_t cp_tab, uint32_t span,
                                                  uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
 	uint32_t cp_end = sub_begin, cnt = 0, trip = 0;
 	int j = -1;   // segment being decoded; the first pass through the record branch only sets up segment 0
@@ -302,7 +302,7 @@ __device__ __forceinline__ bool walk_subsequence(Cursor& cur, uint32_t lut_s, co
 				cnt = 0;
 			}
 			if(++j == kCp) return false;
-			cp_end = sub_begin + uint32_t(j + 1) * seg_bits;
+			cp_end = sub_begin + (uint32_t(cp_tab >> (8 * j)) & 255u) * unit;   // checkpoint j, in units of 1/32 subsequence
 			if(cp_end > span) cp_end = span;
 			continue;
 		}
@@ -442,7 +442,7 @@ __device__ __forceinline__ uint32_t pair_step_one(Cursor& cur, const PairTab& T,
 // Checkpoints record the ROW (not the context byte): equality is all the comparison needs.
 template <int ORDER>
 __device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
-                                                      const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t seg_bits, uint32_t span,
+                                                      const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t unit, uint64_t cp_tab, uint32_t span,
                                                       uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
 	uint32_t cp_end = sub_begin, cnt = 0, trip = 0;
 	int j = -1;
@@ -459,7 +459,7 @@ __device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab
 				cnt = 0;
 			}
 			if(++j == kCp) return false;
-			cp_end = sub_begin + uint32_t(j + 1) * seg_bits;
+			cp_end = sub_begin + (uint32_t(cp_tab >> (8 * j)) & 255u) * unit;   // checkpoint j, in units of 1/32 subsequence
 			if(cp_end > span) cp_end = span;
 			continue;
 		}
@@ -681,7 +681,7 @@ __device__ __forceinline__ bool decode_emit(Cursor& cur, uint32_t lut_s, const u
 // ---------------------------------------------------------------------------------------------------------
 // D1: speculative decode + intra-chunk synchronisation
 //
-// Each subsequence carries kCp checkpoints (every sub_bits / kCp bits). Checkpoint j records the decoder state at
+// Each subsequence carries kCp checkpoints (at 1, 2, 4, 8, 12, 16, 24, 32 thirty-seconds of its length). Checkpoint j records the decoder state at
 // the first codeword boundary at or after it, and how many symbols started in the segment before it. A thread
 // that takes over its successor's subsequence stops at the first checkpoint where its own state equals the
 // recorded one: from there on the recorded trajectory is its own. Per-segment counts (not running totals) make
@@ -691,13 +691,14 @@ template <int ORDER, bool PAIR>
 __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
     const uint32_t* __restrict__ words, uint64_t n_bits, uint64_t buf_bytes, uint32_t start0, const uint16_t* __restrict__ lut_g,
     const uint32_t* __restrict__ walk, const uint32_t* __restrict__ pair_g, uint32_t pair_rows, uint32_t pair_ctx_rows,
-    uint32_t* __restrict__ state, uint32_t* __restrict__ count, uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm, uint32_t lut_smem_bytes) {
+    uint32_t* __restrict__ state, uint32_t* __restrict__ count, uint32_t* __restrict__ seam, uint32_t sub_bits, uint64_t n_subs, uint32_t n_chunks, uint32_t warm, uint32_t lut_smem_bytes,
+    uint64_t cp_tab) {
 	extern __shared__ __align__(16) uint16_t lut_s[];   // table, then the payload rings (kRingBytesPerThread each)
 	__shared__ uint16_t cp_state[kCp][kDecThreads];   // [checkpoint][slot]: conflict-free across a warp
 	__shared__ uint16_t cp_count[kCp][kDecThreads];
 	const uint32_t tid = threadIdx.x;
 	const uint32_t chunk_subs = kDecThreads - warm;
-	const uint32_t seg_bits = sub_bits / kCp;
+	const uint32_t unit = sub_bits / 32;
 	PairTab T = {};
 	if(PAIR) {
 		T = stage_pair_table(reinterpret_cast<uint32_t*>(lut_s), pair_g, pair_rows, pair_ctx_rows);
@@ -739,8 +740,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 			const uint32_t pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
 			if(ORDER && my_sub == 0) row = PAIR ? pair_row_of<ORDER>(T, start0 & 255u) : lut_sa + ((start0 & 255u) << 9);   // the stream's own start (exact, or a shard's guess)
 			cur.seek(origin + pos, pos);
-			if(PAIR) walk_subsequence_pair<ORDER>(cur, T, lut_g, walk, pos, seg_bits, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
-			else walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, pos, seg_bits, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
+			if(PAIR) walk_subsequence_pair<ORDER>(cur, T, lut_g, walk, pos, unit, cp_tab, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
+			else walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, pos, unit, cp_tab, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
 		}
 		__syncthreads();
 		// rounds: walk the successor's checkpoints until my state equals the recorded one
@@ -750,8 +751,8 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 			if(active) {
 				const uint32_t slot = uint32_t(k - first_sub);
 				const uint32_t begin = uint32_t(uint64_t(k - origin_sub) * sub_bits);
-				const bool hit = PAIR ? walk_subsequence_pair<ORDER>(cur, T, lut_g, walk, begin, seg_bits, span32, row, &cp_state[0][slot], &cp_count[0][slot], true)
-				                      : walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, begin, seg_bits, span32, row, &cp_state[0][slot], &cp_count[0][slot], true);
+				const bool hit = PAIR ? walk_subsequence_pair<ORDER>(cur, T, lut_g, walk, begin, unit, cp_tab, span32, row, &cp_state[0][slot], &cp_count[0][slot], true)
+				                      : walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, begin, unit, cp_tab, span32, row, &cp_state[0][slot], &cp_count[0][slot], true);
 				if(hit) active = false;
 			}
 			if(!__syncthreads_or(active ? 1 : 0)) break;
@@ -1017,13 +1018,18 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 		                             PAIR ? max_smem_optin() - 1024 : int(lut_bytes) + ring_bytes));   // pair path: the launcher fits the thread count
 	}
 	const int sms = sm_count();
+	// Checkpoints inside a subsequence, in 1/32 of its length. A walker that took over its successor's subsequence stops
+	// at the first checkpoint where its state equals the recorded one: dense near the start, where re-synchronisation
+	// usually happens (1, 2, 4, 8, 12, 16, 24, 32: -8 % on D1 with -h, where streams re-synchronise within tens of bits;
+	// no change for Markov text), or evenly spaced (4, 8, .. 32) with the tunable dec_cp_geo = 0.
+	const uint64_t cp_tab = tunable(kTunDecCpGeo) != 0 ? 0x2018100c08040201ull : 0x201c1814100c0804ull;
 	const uint32_t grid = n_chunks < uint32_t(sms) ? n_chunks : uint32_t(sms);
 	MH_CUDA(cudaMemsetAsync(ws->dec_flags, 0, 8 * sizeof(uint32_t), st));
 	MH_CUDA(cudaMemsetAsync(ws->counters + 4, 0, sizeof(unsigned long long), st));   // D4's work ticket
 	{
 		ProfScope p("dec_sync_kernel", st);
 		dec_sync_kernel<ORDER, PAIR><<<grid, kDecThreads, lut_bytes + size_t(kDecThreads) * kRingBytesPerThread, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, dt->d_pair,
-		    dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm, uint32_t(lut_bytes));
+		    dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm, uint32_t(lut_bytes), cp_tab);
 	}
 	count_launch(1);
 	int last_flag = -1;

@@ -63,6 +63,29 @@ __device__ __forceinline__ uint4 ld_stream_128(const void* p) {
 	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
 	return r;
 }
+// ---- bulk copy (TMA) of a tile's input into shared memory, completion through an mbarrier -----------------------
+// One thread arms the barrier with the byte count and issues ONE cp.async.bulk for the whole tile (SASS: UBLKCP +
+// SYNCS): no worker issues a global load for its input, and the copy of the next tile runs while this one is packed.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load_tile(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "WAIT_%=:\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+	    "@!p bra WAIT_%=;\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+	uint4 r;
+	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+	return r;
+}
+
 // Shared memory through explicit 32-bit shared-space addresses: keeps generic-address arithmetic out of the hot
 // loops.
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -101,7 +124,8 @@ struct EncArgs {
 	const unsigned long long* bit_base_dev;   // optional: the global bit offset lives in device memory (its low 3 bits replace bit0)
 	const unsigned long long* prev0_dev;      // optional: the byte before in[0] lives in device memory
 	const uint32_t* meta;                     // optional: tables built on the device: rows / status / longest codeword live there
-	uint32_t launched_bits;                   // ... and this launch was sized for at most ctx_rows rows and launched_bits-bit codewords
+	uint32_t launched_bits;                   // ... and this launch was sized for at most launched_bits-bit codewords (tile size) ...
+	uint32_t smem_bytes;                      // ... and smem_bytes of dynamic shared memory (table + staging area + input tile)
 	uint32_t stage_words;
 	uint32_t* out_words;
 	uint64_t out_capacity_words;
@@ -262,9 +286,13 @@ struct Packer32 {
 	}
 };
 
-template <int SPT, int FMT, bool ALIGNED, int ORDER = 1>
+constexpr uint32_t kEncInbufLead = 16;   // the 16 bytes in front of a tile travel with it: the byte before the tile's first is its context
+
+template <int SPT, int FMT, bool ALIGNED, int ORDER = 1, bool TMA = false>
 __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode_kernel(const EncArgs A) {   // context rows: two CTAs per SM (<= 64 registers)
 	constexpr int NWORDS = SPT / 4;
+	constexpr uint32_t kTileBytes = kEncThreads * SPT;
+	__shared__ __align__(8) unsigned long long s_mbar;
 	extern __shared__ uint32_t smem[];
 	uint32_t* table = smem;   // FMT_BOX_SMEM: [(R + 1)^2] or [256]
 	__shared__ uint32_t warp_sums[kEncThreads / 32];
@@ -276,11 +304,13 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t bit0 = A.bit_base_dev ? uint32_t(__ldg(A.bit_base_dev) & 7ull) : A.bit0;
 	const uint32_t first_prev = A.prev0_dev ? uint32_t(__ldg(A.prev0_dev) & 255ull) : A.prev0;
-	uint32_t ctx_rows = A.ctx_rows;
+	uint32_t ctx_rows = A.ctx_rows, stage_words = A.stage_words;
 	if(FMT == FMT_CTX && A.meta) {   // device-built tables: check that this launch's shared memory and tile size fit them
 		ctx_rows = __ldg(A.meta);
 		const uint32_t status = __ldg(A.meta + 1), longest = __ldg(A.meta + 2);
-		if(status != 0 || ctx_rows > A.ctx_rows || longest > A.launched_bits) {
+		stage_words = (kEncThreads * (SPT / 32) * (longest ? longest : 1u) + 7u) & ~3u;   // as launch_encode sizes it for host-built tables
+		const uint32_t need = ctx_rows * 1024u + (stage_words + 8u) * 4u + (TMA ? kTileBytes + kEncInbufLead + 16u : 0u);
+		if(status != 0 || ctx_rows > uint32_t(kEncCtxMaxRows) || longest > A.launched_bits || need > A.smem_bytes) {
 			if(blockIdx.x == 0 && tid == 0) A.result[3] = status ? (unsigned long long) (long long) (int) status : 1ull;   // the caller takes the host-built path
 			return;
 		}
@@ -297,9 +327,25 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	uint32_t* stage = smem + ((table_entries + 3) & ~3u) + 4;   // [stage_words + 4], after four zero words: stage[-1] reads as "no bits"
 	const uint32_t table_sa = uint32_t(__cvta_generic_to_shared(table));
 	const uint32_t stage_sa = uint32_t(__cvta_generic_to_shared(stage));
-	for(uint32_t i = tid; i < A.stage_words + 8; i += kEncCtaThreads) stage[int(i) - 4] = 0;
+	for(uint32_t i = tid; i < stage_words + 8; i += kEncCtaThreads) stage[int(i) - 4] = 0;
 	if(tid == 0) s_tile[0] = atomicAdd(A.ticket, 1u);
+	// input tile buffer (TMA): behind the staging area, 16-byte aligned; tiles that are complete travel by bulk copy
+	const uint32_t inbuf_sa = (stage_sa + (stage_words + 4u) * 4u + 15u) & ~15u;
+	const uint32_t mbar_sa = uint32_t(__cvta_generic_to_shared(&s_mbar));
+	const uint32_t full_tiles = uint32_t(A.n / kTileBytes);
+	auto issue_tile = [&](uint32_t tile) {   // one thread: the tile's bytes and the 16 before them (its first context)
+		if(tile >= full_tiles) return;
+		const uint64_t at = uint64_t(tile) * kTileBytes;
+		if(tile) bulk_load_tile(inbuf_sa, A.in + at - kEncInbufLead, kTileBytes + kEncInbufLead, mbar_sa);
+		else bulk_load_tile(inbuf_sa + kEncInbufLead, A.in, kTileBytes, mbar_sa);
+	};
+	if(TMA && tid == 0) {
+		mbar_init(mbar_sa, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
 	__syncthreads();
+	if(TMA && tid == kEncThreads) issue_tile(s_tile[0]);
+	uint32_t in_parity = 0;
 
 	// ---- the scanner warp: resolves every tile's global bit offset as soon as its bit count is known, one iteration
 	// before the workers need it, so that nobody ever waits for the chained scan ----
@@ -323,6 +369,9 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 		};
 		for(uint32_t it = 0;; ++it) {
 			bar_wait(2 + (it & 1));
+			// the workers have taken this tile's bytes out of the input buffer and the next ticket is known: its bytes travel
+			// while this tile is scanned, copied out and packed
+			if(TMA && lane == 0) issue_tile(s_tile[(it + 1) & 1]);
 			const uint32_t tile = s_pub_tile[it & 1];
 			const uint32_t head = s_head[(it - 1) & 1];   // of the tile packed in iteration it - 1 (read before the workers can reuse the slot)
 			if(tile < A.n_tiles) {
@@ -384,7 +433,17 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 #pragma unroll
 			for(int k = 0; k < NWORDS; ++k) w[k] = 0;
 			int live = 0;
-			if(my < A.n) {
+			const bool from_smem = TMA && tile < full_tiles;
+			if(from_smem) {   // the tile came by bulk copy: wait for it, then 2 x 16 bytes per thread from shared memory
+				mbar_wait(mbar_sa, in_parity);
+				in_parity ^= 1u;
+				live = SPT;
+#pragma unroll
+				for(int k = 0; k < SPT / 16; ++k) {
+					const uint4 v = lds128(inbuf_sa + kEncInbufLead + tid * SPT + 16 * k);
+					w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+				}
+			} else if(my < A.n) {
 				live = A.n - my >= uint64_t(SPT) ? SPT : int(A.n - my);
 				if(ALIGNED && live == SPT) {
 #pragma unroll
@@ -399,7 +458,11 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				}
 			}
 			uint32_t prev = __shfl_up_sync(0xffffffffu, w[NWORDS - 1] >> 24, 1);
-			if(lane == 0 && my < A.n) prev = my == 0 ? first_prev : uint32_t(A.in[my - 1]);
+			if(lane == 0 && my < A.n) {
+				if(my == 0) prev = first_prev;
+				else if(TMA && tile < full_tiles) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(prev) : "r"(inbuf_sa + kEncInbufLead + tid * SPT - 1u) : "memory");
+				else prev = uint32_t(A.in[my - 1]);
+			}
 			uint32_t my_bits = 0;
 			if constexpr(FMT == FMT_CTX) {
 				// One shared-memory lookup per symbol; the entry names the next context's row, so inside a quad the
@@ -530,7 +593,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 			bar_arrive(2 + (it & 1));   // the scanner takes it from here
 			// the next ticket is visible since the scan's barrier: pull that tile's input into L2 while this one packs
 			const uint32_t next_tile = s_tile[(it + 1) & 1];
-			if((tid & 3) == 0 && next_tile < A.n_tiles) {
+			if((!TMA || next_tile >= full_tiles) && (tid & 3) == 0 && next_tile < A.n_tiles) {
 				const uint64_t off = uint64_t(next_tile) * (kEncThreads * SPT) + uint64_t(tid) * SPT;
 				if(off < A.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.in + off));
 			}
@@ -634,9 +697,9 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	if(lane == 0 && dropped) atomicAdd(A.result + 1, (unsigned long long) dropped);
 }
 
-template <int SPT, int FMT, int ORDER = 1>
+template <int SPT, int FMT, int ORDER = 1, bool TMA = false>
 int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStream_t st) {
-	auto kern = aligned ? encode_kernel<SPT, FMT, true, ORDER> : encode_kernel<SPT, FMT, false, ORDER>;
+	auto kern = aligned ? encode_kernel<SPT, FMT, true, ORDER, TMA> : encode_kernel<SPT, FMT, false, ORDER, false>;
 	MH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
 	int per_sm = 0;
 	MH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEncCtaThreads, smem_bytes));
@@ -666,11 +729,11 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	if(n == 0) return MH_OK;
 
 	// table format
-	// Device-built tables: the host knows neither the rows nor the longest codeword. The launch is sized for the largest
-	// context-row table that still leaves two CTAs per SM with kEncCtxMaxBits-bit codewords; the kernel checks the real
-	// values (d_meta) and reports through d_result[3] when they do not fit — the caller then takes the host-built path.
+	// Device-built tables: the host knows neither the rows nor the longest codeword. The launch gets the shared memory
+	// that still leaves two CTAs per SM (kEncCtxSmemLimit) and the tile size for kEncCtxMaxBits-bit codewords; the kernel
+	// lays table, staging area and input tile out from the real values (d_meta) and reports through d_result[3] when
+	// they do not fit — the caller then takes the host-built path.
 	const bool dev = cb->device_built;
-	const uint32_t dev_rows = uint32_t((size_t(kEncCtxSmemLimit) - (size_t(kEncThreads) * kEncCtxMaxBits + 64) * 4) / 1024);
 	const int maxb = dev ? kEncCtxMaxBits : (cb->max_bits > 0 ? cb->max_bits : 1);
 	const int force_fmt = int(tunable(kTunEncFmt));   // experiments / tests: force a table format (0: box in shared memory, 1: box in global, 2: wide)
 	int fmt = FMT_WIDE;
@@ -685,10 +748,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 		fmt = FMT_CTX;
 		table_bytes = size_t(cb->ctx_rows) * 1024;
 	}
-	if(dev) {
-		fmt = FMT_CTX;
-		table_bytes = size_t(dev_rows) * 1024;
-	}
+	if(dev) fmt = FMT_CTX;
 	// Tile size: the staged bits of one tile must fit the staging area whatever the input, so symbols per tile x
 	// longest codeword bounds it: 32 symbols per thread while that bound stays within kEncStageMaxWords.
 	int spt = 16;
@@ -705,7 +765,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.in = d_in; a.n = n; a.prev0 = prev0; a.order = cb->order;
 	a.wide = reinterpret_cast<const unsigned long long*>(cb->d_enc);
 	a.box = cb->d_box; a.box_lo = cb->box_lo; a.box_r = cb->box_r;
-	a.ctx = cb->d_ctx; a.ctx_rows = dev ? dev_rows : cb->ctx_rows;
+	a.ctx = cb->d_ctx; a.ctx_rows = cb->ctx_rows;
 	a.meta = dev ? cb->d_meta : nullptr;
 	a.launched_bits = uint32_t(maxb);
 	a.prev0_dev = d_prev0;
@@ -721,8 +781,16 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.result = d_result;
 	a.n_tiles = uint32_t(tiles);
 	const bool aligned = (reinterpret_cast<uint64_t>(d_in) & 15) == 0;
-	const size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 8) * sizeof(uint32_t);
+	size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 8) * sizeof(uint32_t);
+	// Context rows + aligned input: whole tiles travel into shared memory by bulk copy (TMA), one tile ahead, when the
+	// input buffer still fits next to table and staging area with two CTAs per SM.
+	const size_t inbuf_bytes = size_t(kEncThreads) * 32 + 32;
+	bool tma = fmt == FMT_CTX && aligned && tunable(kTunEncTma) != 0 && (dev || smem + inbuf_bytes <= size_t(kEncCtxSmemLimit));
+	if(tma) smem += inbuf_bytes;
+	if(dev) smem = size_t(kEncCtxSmemLimit);
+	a.smem_bytes = uint32_t(smem);
 
+	if(fmt == FMT_CTX && tma) return cb->order ? launch_variant<32, FMT_CTX, 1, true>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0, true>(aligned, a, smem, st);
 	if(fmt == FMT_CTX) return cb->order ? launch_variant<32, FMT_CTX, 1>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0>(aligned, a, smem, st);
 	if(fmt == FMT_WIDE) return launch_variant<16, FMT_WIDE>(aligned, a, smem, st);
 	if(fmt == FMT_BOX_SMEM) return spt == 32 ? launch_variant<32, FMT_BOX_SMEM>(aligned, a, smem, st) : launch_variant<16, FMT_BOX_SMEM>(aligned, a, smem, st);

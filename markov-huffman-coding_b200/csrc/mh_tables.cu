@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long lo
                                                            const uint8_t* __restrict__ flags, unsigned long long* __restrict__ enc, uint32_t* __restrict__ ctx,
                                                            uint32_t max_ctx_rows) {
 	__shared__ TreeScratch S;
-	__shared__ uint8_t rank[256];   // row of every byte value as a context (0xff: no tree)
+	__shared__ uint8_t rank[256];   // row of every byte value as a context (meaningful where has[] is set and the rows fit a byte)
+	__shared__ uint8_t has[256];    // the context has a tree
 	__shared__ int s_status;
 	const uint32_t p = blockIdx.x, lane = threadIdx.x;
 	// every block ranks the live contexts itself (256 flag bytes): lane l owns the values 8 l .. 8 l + 7
@@ -172,14 +173,16 @@ __global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long lo
 	const uint32_t live = __shfl_sync(0xffffffffu, before, 31), rows = live + 1;
 	before -= __popc(mine);
 	for(uint32_t k = 0; k < 8; ++k) {
-		rank[lane * 8 + k] = (mine >> k) & 1u ? uint8_t(before) : uint8_t(0xff);
+		rank[lane * 8 + k] = uint8_t(before);
+		has[lane * 8 + k] = uint8_t((mine >> k) & 1u);
 		before += (mine >> k) & 1u;
 	}
 	const bool wrapped = __any_sync(0xffffffffu, bad != 0);
 	__syncwarp();
 	const bool ctx_fits = rows <= max_ctx_rows;
 	const uint32_t my_row = rank[p & 255u];
-	auto next_of = [&](uint32_t c) -> uint32_t { return order ? (rank[c] != 0xff ? uint32_t(rank[c]) : live) : 0u; };
+	const bool my_tree = has[p & 255u] != 0;
+	auto next_of = [&](uint32_t c) -> uint32_t { return order ? (has[c] ? uint32_t(rank[c]) : live) : 0u; };
 	if(blockIdx.x == gridDim.x - 1) {   // the extra block writes the null row and the summary
 		if(ctx_fits)
 			for(uint32_t c = lane; c < 256; c += 32) ctx[size_t(live) * 256 + c] = next_of(c) << 16;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long lo
 		return;
 	}
 	unsigned long long* enc_row = enc + size_t(p) * 256;
-	if(my_row == 0xff || wrapped) {   // no tree for this context (or the counts are unusable): no codewords
+	if(!my_tree || wrapped) {   // no tree for this context (or the counts are unusable): no codewords
 		for(uint32_t c = lane; c < 256; c += 32) enc_row[c] = 0;
 		return;
 	}

@@ -64,6 +64,13 @@ def test_corpus_histograms(name, order):
     check(counts, order)
 
 
+def test_all_256_contexts_live():
+    """K = 256 data: every context has a tree (rank 255 must not be mistaken for 'no tree')."""
+    rng = np.random.default_rng(11)
+    c = rng.integers(1, 50, 65536).astype(np.uint64)
+    check(c, 1)
+
+
 def test_wrapped_count_is_reported_and_the_encoder_refuses():
     import torch
     c = np.zeros(65536, dtype=np.uint64)
