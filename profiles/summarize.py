@@ -49,6 +49,11 @@ def src_stalls(rep, top=14):
     return p.stdout
 
 
+def regions(rep):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "inst_regions.py"), rep], stdout=subprocess.PIPE, text=True)
+    return p.stdout
+
+
 def launch_list(path):
     rows = list(csv.reader(open(path)))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -75,9 +80,9 @@ def main():
     if os.path.exists(ll):
         with open(os.path.join(ROOT, "profiles", "%s_launches.txt" % tag), "w") as fh:
             fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n")
-            fh.write("# command: python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e (1 GiB)\n")
+            fh.write("# command: python bench.py --config markov --steps 1 --warmup 3 --no-cpu-baseline --no-e2e (1 GiB)\n")
             fh.write(launch_list(ll) + "\n")
-    for k in ("hist_lane_kernel", "hist_kernel", "encode_kernel", "dec_sync_kernel", "dec_write_kernel"):
+    for k in ("hist_lane_kernel", "hist_kernel", "tables_build_kernel", "encode_kernel", "dec_sync_kernel", "dec_write_kernel"):
         rep = os.path.join(OUT, "%s_%s.ncu-rep" % (tag, k))
         if not os.path.exists(rep):
             continue
@@ -85,6 +90,7 @@ def main():
             fh.write("# ncu --set full --clock-control none --import-source on, 1 launch after warm-up, the bench workload (1 GiB Markov text)\n")
             fh.write(raw_metrics(rep) + "\n\n# warp stall samples by SASS instruction\n" + stalls(rep))
             fh.write("\n# warp stall samples by source line (-lineinfo)\n" + src_stalls(rep))
+            fh.write("\n# executed warp instructions by code region (runs of SASS instructions with the same execution count)\n" + regions(rep))
         print("wrote", k)
 
 
