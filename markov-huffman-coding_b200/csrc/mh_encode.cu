@@ -286,6 +286,10 @@ struct Packer32 {
 	}
 };
 
+// Context rows sit kCtxPitch bytes apart in shared memory, not 1024: with 256-word rows the bank of (row, c) is c mod 32,
+// and 32 lanes that look the SAME frequent byte up in DIFFERENT contexts — the common case in text — hit one bank
+// (4.8 wavefronts per warp lookup on the bench text); five words of padding rotate every row by 5 banks: 3.1.
+constexpr uint32_t kCtxPitch = (256 + 5) * 4;
 constexpr uint32_t kEncInbufLead = 16;   // the 16 bytes in front of a tile travel with it: the byte before the tile's first is its context
 
 template <int SPT, int FMT, bool ALIGNED, int ORDER = 1, bool TMA = false>
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	constexpr int NWORDS = SPT / 4;
 	constexpr uint32_t kTileBytes = kEncThreads * SPT;
 	__shared__ __align__(8) unsigned long long s_mbar;
+	__shared__ uint8_t s_rank[256];   // FMT_CTX: row of every byte value as a context (what the null row's entries name)
 	extern __shared__ uint32_t smem[];
 	uint32_t* table = smem;   // FMT_BOX_SMEM: [(R + 1)^2] or [256]
 	__shared__ uint32_t warp_sums[kEncThreads / 32];
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 		ctx_rows = __ldg(A.meta);
 		const uint32_t status = __ldg(A.meta + 1), longest = __ldg(A.meta + 2);
 		stage_words = (kEncThreads * (SPT / 32) * (longest ? longest : 1u) + 7u) & ~3u;   // as launch_encode sizes it for host-built tables
-		const uint32_t need = ctx_rows * 1024u + (stage_words + 8u) * 4u + (TMA ? kTileBytes + kEncInbufLead + 16u : 0u);
+		const uint32_t need = ((ctx_rows * kCtxPitch + 15u) & ~15u) + (stage_words + 8u) * 4u + (TMA ? kTileBytes + kEncInbufLead + 16u : 0u);
 		if(status != 0 || ctx_rows > uint32_t(kEncCtxMaxRows) || longest > A.launched_bits || need > A.smem_bytes) {
 			if(blockIdx.x == 0 && tid == 0) A.result[3] = status ? (unsigned long long) (long long) (int) status : 1ull;   // the caller takes the host-built path
 			return;
@@ -321,8 +326,11 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 		for(uint32_t i = tid; i < table_entries; i += kEncCtaThreads) table[i] = __ldg(A.box + i);
 	}
 	if(FMT == FMT_CTX) {
-		table_entries = ctx_rows * 256u;
-		for(uint32_t i = tid; i < table_entries / 4; i += kEncCtaThreads) reinterpret_cast<uint4*>(table)[i] = __ldg(reinterpret_cast<const uint4*>(A.ctx) + i);
+		table_entries = ctx_rows * (kCtxPitch / 4);
+		for(uint32_t i = tid; i < ctx_rows * 256u; i += kEncCtaThreads) table[(i >> 8) * (kCtxPitch / 4) + (i & 255u)] = __ldg(A.ctx + i);
+		// A quad restarts its lookup chain from the byte before it: that byte's row comes from this byte map — four rows to a
+		// word, so the 32 lanes of a warp touch a handful of words (the null row's u32 entries cost ~3 wavefronts a lookup)
+		if(tid < 256) s_rank[tid] = uint8_t(__ldg(A.ctx + (ctx_rows - 1) * 256u + tid) >> 16);
 	}
 	uint32_t* stage = smem + ((table_entries + 3) & ~3u) + 4;   // [stage_words + 4], after four zero words: stage[-1] reads as "no bits"
 	const uint32_t table_sa = uint32_t(__cvta_generic_to_shared(table));
@@ -470,16 +478,21 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				// the byte before it (its row comes from the null row), so the eight quads of a thread are independent.
 				// Codewords are merged on the fly: pairs (<= 32 bits), then quads kept as (hi:lo, length) — a quad
 				// longer than 32 bits goes out in two steps.
-				const uint32_t null_row = table_sa + (ctx_rows - 1) * 1024u;
+				const uint32_t rank_sa = uint32_t(__cvta_generic_to_shared(s_rank));
+				auto row_of = [&](uint32_t byte) -> uint32_t {
+					uint32_t r;
+					asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_sa + byte));
+					return table_sa + r * kCtxPitch;
+				};
 				uint32_t row = table_sa;
-				if(ORDER) row = table_sa + __byte_perm(lds32(null_row + prev * 4), 0, 0x4442) * 1024u;
+				if(ORDER) row = row_of(prev);
 				uint32_t floor = 0xffffffffu, ceil = 0;
 				auto lookup = [&](int i, bool checked) -> uint32_t {
 					const uint32_t c = __byte_perm(w[i >> 2], 0, 0x4440 + (i & 3));
 					uint32_t ent = 0;
 					if(!checked || i < live) {
 						ent = lds32(row + c * 4);
-						if(ORDER) row = table_sa + __byte_perm(ent, 0, 0x4442) * 1024u;
+						if(ORDER) row = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
 						floor = min(floor, ent);
 						ceil = max(ceil, ent);
 					}
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				auto quads = [&](bool checked) {
 #pragma unroll
 					for(int q = 0; q < SPT / 4; ++q) {
-						if(ORDER && q) row = table_sa + __byte_perm(lds32(null_row + __byte_perm(w[q - 1], 0, 0x4443) * 4), 0, 0x4442) * 1024u;
+						if(ORDER && q) row = row_of(__byte_perm(w[q - 1], 0, 0x4443));
 						const uint32_t e0 = lookup(4 * q, checked), e1 = lookup(4 * q + 1, checked), e2 = lookup(4 * q + 2, checked), e3 = lookup(4 * q + 3, checked);
 						const uint32_t l1 = e1 >> 27, l3 = e3 >> 27;
 						const uint32_t lp0 = (e0 >> 27) + l1, lp1 = (e2 >> 27) + l3;
@@ -531,12 +544,12 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				}
 				if(floor < (1u << 27)) {   // rare: some symbol has no codeword; count them exactly (context rows again)
 					uint32_t r2 = table_sa;
-					if(ORDER) r2 = table_sa + __byte_perm(lds32(null_row + prev * 4), 0, 0x4442) * 1024u;
+					if(ORDER) r2 = row_of(prev);
 #pragma unroll 1
 					for(int i = 0; i < live; ++i) {
 						const uint32_t c = A.in[my + i];   // re-read: indexing w[] dynamically would push it to local memory
 						const uint32_t ent = lds32(r2 + c * 4);
-						if(ORDER) r2 = table_sa + __byte_perm(ent, 0, 0x4442) * 1024u;
+						if(ORDER) r2 = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
 						dropped += (ent >> 27) == 0 ? 1u : 0u;
 					}
 				}
@@ -744,9 +757,9 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	}
 	if(fmt != FMT_BOX_SMEM) table_bytes = 0;
 	// context rows (live contexts only, <= 16-bit codewords): preferred whenever table + staging fit two CTAs per SM
-	if(cb->ctx_rows && force_fmt < 0 && size_t(cb->ctx_rows) * 1024 + (size_t(kEncThreads) * maxb + 64) * 4 <= size_t(kEncCtxSmemLimit)) {
+	if(cb->ctx_rows && force_fmt < 0 && size_t(cb->ctx_rows) * kCtxPitch + (size_t(kEncThreads) * maxb + 64) * 4 <= size_t(kEncCtxSmemLimit)) {
 		fmt = FMT_CTX;
-		table_bytes = size_t(cb->ctx_rows) * 1024;
+		table_bytes = size_t(cb->ctx_rows) * kCtxPitch;
 	}
 	if(dev) fmt = FMT_CTX;
 	// Tile size: the staged bits of one tile must fit the staging area whatever the input, so symbols per tile x
