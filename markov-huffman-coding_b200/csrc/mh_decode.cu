@@ -272,69 +272,106 @@ __device__ __forceinline__ bool decode_until(Cursor& cur, uint32_t lut_s, const 
 }
 
 // D1's walker: decode one subsequence of kCp segments in ONE flat loop, so the lanes of a warp only wait for each
-// other at the end of the subsequence, not at every checkpoint. Each iteration decodes four symbols speculatively
-// (as decode_four) and commits those that START before the current segment end `cp_end` (at least one; all four
-// unless the group straddles the checkpoint — the rest is simply decoded again by the next iteration). A lane that
-// has reached `cp_end` records the checkpoint (state at the first codeword boundary at or after it, symbols that
-// started in the segment) in its next iteration. With `compare`, the walk stops at the first checkpoint whose
-// recorded state equals the walker's (the recorded trajectory is then its own). `cp_st` / `cp_cn` point at this
-// subsequence's column of the [kCp][kDecThreads] checkpoint arrays. Returns true when it stopped on a match.
+// other at the end of the subsequence, not at every checkpoint. A trip decodes four symbols speculatively (as
+// decode_four) and commits all of them while the group ends before the current checkpoint `cp_end` and holds no deep
+// or null entry — the only test on the main path. Otherwise ONE divergent block finishes the job in the same trip: it
+// commits the leading entries that end before the checkpoint, then exactly one more symbol (through the full path if
+// its entry is flagged). If that symbol ends at or after the checkpoint the walker now rests on the first codeword
+// boundary at or after it — the state a checkpoint records, with the symbols that started in the segment. (Until
+// round 2 a group that straddled a checkpoint was cut and the walker crept up to the boundary over several trips:
+// rare per lane, but with 32 lanes and 8 checkpoints a third of the warp's trips stepped through those paths.)
+// With `compare`, the walk stops at the first checkpoint whose recorded state equals the walker's (the recorded
+// trajectory is then its own). `cp_st` / `cp_cn` point at this subsequence's column of the [kCp][kDecThreads]
+// checkpoint arrays. Returns true when it stopped on a match.
 constexpr int kCp = 8;
 
 __device__ __forceinline__ uint32_t pack_cp(uint32_t rel_bits, uint32_t ctx) { return ((rel_bits > 255u ? 255u : rel_bits) << 8) | ctx; }
+
+// The walker rests on a codeword boundary at `at` (relative to the CTA's origin): record every checkpoint at or before
+// it. 0: go on, 1: a recorded state equalled the walker's, 2: that was the subsequence's last checkpoint.
+struct CpWalk {
+	uint32_t sub_begin, unit, span, cp_end;
+	uint64_t cp_tab;
+	int j;
+	__device__ __forceinline__ void start(uint32_t sub_begin_, uint32_t unit_, uint64_t cp_tab_, uint32_t span_) {
+		sub_begin = sub_begin_; unit = unit_; cp_tab = cp_tab_; span = span_;
+		j = 0;
+		set_end();
+	}
+	__device__ __forceinline__ void set_end() {   // checkpoint j, in units of 1/32 subsequence
+		cp_end = sub_begin + (uint32_t(cp_tab >> (8 * j)) & 255u) * unit;
+		if(cp_end > span) cp_end = span;
+	}
+	__device__ __forceinline__ int cross(uint32_t at, uint32_t ctx_or_row, uint32_t& cnt, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
+		while(at >= cp_end) {
+			const uint16_t st = uint16_t(pack_cp(at - cp_end, ctx_or_row));
+			cp_cn[j * kDecThreads] = uint16_t(cnt);
+			if(compare && cp_st[j * kDecThreads] == st) return 1;
+			cp_st[j * kDecThreads] = st;
+			cnt = 0;
+			if(++j == kCp) return 2;
+			set_end();
+		}
+		return 0;
+	}
+};
 
 template <int ORDER>
 __device__ __forceinline__ bool walk_subsequence(Cursor& cur, uint32_t lut_s, const uint16_t* __restrict__ lut_g,
                                                  const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t unit, uint64_t cp_tab, uint32_t span,
                                                  uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
-	uint32_t cp_end = sub_begin, cnt = 0, trip = 0;
-	int j = -1;   // segment being decoded; the first pass through the record branch only sets up segment 0
+	uint32_t cnt = 0, trip = 0;
 	bool clean = true;
+	CpWalk cw;
+	cw.start(sub_begin, unit, cp_tab, span);
 	cur.refill_round();
+	if(cur.pos >= cw.cp_end) {   // a walker that came out of the previous subsequence beyond this one's first checkpoint (tiny subsequences, long codewords)
+		const int s = cw.cross(cur.pos, ORDER ? (row - lut_s) >> 9 : 0u, cnt, cp_st, cp_cn, compare);
+		if(s) return s == 1;
+	}
 	for(;;) {
 		if((++trip & (kRefillEvery - 1)) == 0) cur.refill_round();   // every lane of the warp in the same trip
-		if(j < 0 || cur.pos >= cp_end) {
-			if(j >= 0) {
-				const uint16_t st = uint16_t(pack_cp(cur.pos - cp_end, ORDER ? (row - lut_s) >> 9 : 0u));
-				cp_cn[j * kDecThreads] = uint16_t(cnt);
-				if(compare && cp_st[j * kDecThreads] == st) return true;
-				cp_st[j * kDecThreads] = st;
-				cnt = 0;
-			}
-			if(++j == kCp) return false;
-			cp_end = sub_begin + (uint32_t(cp_tab >> (8 * j)) & 255u) * unit;   // checkpoint j, in units of 1/32 subsequence
-			if(cp_end > span) cp_end = span;
-			continue;
-		}
 		// four speculative LUT hits
-		uint32_t a[5], r[5], flg = 0;
+		uint32_t e[4], a[5], r[5], flg = 0;
 		a[0] = 0; r[0] = row;
 #pragma unroll
 		for(int i = 0; i < 4; ++i) {
 			const uint32_t t = __funnelshift_l(cur.lo, cur.hi, a[i]);
-			uint32_t e;
-			asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(r[i] + ((t >> 24) << 1)));
-			a[i + 1] = a[i] + e;
-			flg |= e;
-			r[i + 1] = ORDER ? lut_s + ((e & 0xff00u) << 1) : row;
+			asm("ld.shared.u16 %0, [%1];" : "=r"(e[i]) : "r"(r[i] + ((t >> 24) << 1)));
+			a[i + 1] = a[i] + e[i];
+			flg |= e[i];
+			r[i + 1] = ORDER ? lut_s + ((e[i] & 0xff00u) << 1) : row;
 		}
-		if(flg & (kDeep | kNull)) {   // rare: one symbol through the full path
-			uint32_t row_off = row - lut_s;
-			decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean);
-			row = lut_s + row_off;
-			++cnt;
-		} else if(cur.pos + (a[3] & 63u) < cp_end) {   // the fourth symbol still starts inside the segment
+		const uint32_t room = cw.cp_end - cur.pos;   // > 0
+		if(!(flg & (kDeep | kNull)) && (a[4] & 63u) < room) {   // the whole group ends before the checkpoint
 			cur.take_group(a[4] & 63u);
 			row = r[4];
 			cnt += 4;
-		} else {   // the group straddles the checkpoint: keep the symbols that start before it
-			const uint32_t room = cp_end - cur.pos;
-			const int n = (a[2] & 63u) < room ? 3 : ((a[1] & 63u) < room ? 2 : 1);
-			cur.take_group((n == 3 ? a[3] : (n == 2 ? a[2] : a[1])) & 63u);
-			row = n == 3 ? r[3] : (n == 2 ? r[2] : r[1]);
-			cnt += n;
+			cur.top_up();
+			continue;
 		}
-		cur.top_up();
+		// the leading entries that end before the checkpoint, then one symbol more
+		const bool c0 = !(e[0] & (kDeep | kNull)) && (a[1] & 63u) < room;
+		const bool c1 = c0 && !(e[1] & (kDeep | kNull)) && (a[2] & 63u) < room;
+		// (a trip may consume 32 bits at most — the ring's refill cadence counts on it: three entries are committed only
+		// before an ordinary fourth one; a flagged one, up to 16 bits without the walk, waits for the next trip)
+		const bool c2 = c1 && !((e[2] | e[3]) & (kDeep | kNull)) && (a[3] & 63u) < room;
+		const uint32_t n = uint32_t(c0) + uint32_t(c1) + uint32_t(c2);
+		const uint32_t x = c2 ? e[3] : (c1 ? e[2] : (c0 ? e[1] : e[0]));
+		cur.take_group((c2 ? a[3] : (c1 ? a[2] : (c0 ? a[1] : 0u))) & 63u);
+		row = c2 ? r[3] : (c1 ? r[2] : (c0 ? r[1] : r[0]));
+		cnt += n + 1;
+		if(x & (kDeep | kNull)) {   // rare: through the full path
+			uint32_t row_off = row - lut_s;
+			decode_one<ORDER, true>(cur, lut_s, lut_g, walk, row_off, clean);
+			row = lut_s + row_off;
+		} else {
+			cur.take(x & 15u);
+			if(ORDER) row = lut_s + ((x & 0xff00u) << 1);
+		}
+		cur.top_up();   // before a return: the caller walks on into the next subsequence with this window
+		const int s = cw.cross(cur.pos, ORDER ? (row - lut_s) >> 9 : 0u, cnt, cp_st, cp_cn, compare);
+		if(s) return s == 1;
 	}
 }
 
@@ -436,57 +473,78 @@ __device__ __forceinline__ uint32_t pair_step_one(Cursor& cur, const PairTab& T,
 	return sym;
 }
 
-// walk_subsequence over the pair table. A group (or its first 3 / 2 / 1 lookups) is committed when all its bits lie
-// before the segment end — then every symbol in it starts before the end — and it does not stop on a prefix entry,
-// so the walker only ever rests on codeword boundaries; whatever is left before the end goes one symbol at a time.
+// walk_subsequence over the pair table. The main path commits a whole group that ends before the checkpoint (it may end
+// on a prefix entry: the walker then rests inside a codeword, in its prefix row, and the next trip completes it). The
+// divergent block commits the leading entries that end before the checkpoint and then exactly one codeword: a flagged
+// entry through the global tables, a prefix entry together with its completion, a single entry as it is, and of a pair
+// both symbols only if the first one still ends before the checkpoint (its length comes from len1) — so the walker rests
+// on the first codeword boundary at or after the checkpoint whenever it has passed it.
 // Checkpoints record the ROW (not the context byte): equality is all the comparison needs.
 template <int ORDER>
 __device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
                                                       const uint32_t* __restrict__ walk, uint32_t sub_begin, uint32_t unit, uint64_t cp_tab, uint32_t span,
                                                       uint32_t& row, uint16_t* cp_st, uint16_t* cp_cn, bool compare) {
-	uint32_t cp_end = sub_begin, cnt = 0, trip = 0;
-	int j = -1;
+	uint32_t cnt = 0, trip = 0;
 	bool clean = true;
+	CpWalk cw;
+	cw.start(sub_begin, unit, cp_tab, span);
 	cur.refill_round();
+	if(cur.pos >= cw.cp_end) {   // a walker that came out of the previous subsequence beyond this one's first checkpoint (tiny subsequences, long codewords)
+		const int s = cw.cross(cur.pos, row >> 10, cnt, cp_st, cp_cn, compare);
+		if(s) return s == 1;
+	}
 	for(;;) {
 		if((++trip & (kRefillEvery - 1)) == 0) cur.refill_round();   // every lane of the warp in the same trip
-		if(j < 0 || cur.pos >= cp_end) {
-			if(j >= 0) {
-				const uint16_t st = uint16_t(pack_cp(cur.pos - cp_end, row >> 10));
-				cp_cn[j * kDecThreads] = uint16_t(cnt);
-				if(compare && cp_st[j * kDecThreads] == st) return true;
-				cp_st[j * kDecThreads] = st;
-				cnt = 0;
-			}
-			if(++j == kCp) return false;
-			cp_end = sub_begin + (uint32_t(cp_tab >> (8 * j)) & 255u) * unit;   // checkpoint j, in units of 1/32 subsequence
-			if(cp_end > span) cp_end = span;
-			continue;
-		}
 		uint32_t e[4], a[5], r[5];
 		pair_lookups<ORDER>(cur, T, row, e, a, r);
-		const uint32_t room = cp_end - cur.pos;
-		const uint32_t f2 = e[0] | e[1], f3 = f2 | e[2], f4 = f3 | e[3];
-		if(!(f4 & kPairFlags) && (a[4] & 63u) <= room && (e[3] & kPairCount)) {
+		const uint32_t room = cw.cp_end - cur.pos;   // > 0
+		if(!((e[0] | e[1] | e[2] | e[3]) & kPairFlags) && (a[4] & 63u) < room) {
 			cur.take_group(a[4] & 63u);
 			row = r[4];
 			cnt += (a[4] >> 6) & 15u;
-		} else {
-			int n = 0;
-			if(!(f3 & kPairFlags) && (a[3] & 63u) <= room && (e[2] & kPairCount)) n = 3;
-			else if(!(f2 & kPairFlags) && (a[2] & 63u) <= room && (e[1] & kPairCount)) n = 2;
-			else if(!(e[0] & kPairFlags) && (a[1] & 63u) <= room && (e[0] & kPairCount)) n = 1;
-			if(n) {
-				const uint32_t an = n == 3 ? a[3] : (n == 2 ? a[2] : a[1]);
-				cur.take_group(an & 63u);
-				row = n == 3 ? r[3] : (n == 2 ? r[2] : r[1]);
-				cnt += (an >> 6) & 15u;
-			} else {
-				pair_step_one<ORDER>(cur, T, lut_g, walk, e[0], row, clean);
-				++cnt;
-			}
+			cur.top_up();
+			continue;
 		}
-		cur.top_up();
+		const bool c0 = !(e[0] & kPairFlags) && (a[1] & 63u) < room;
+		const bool c1 = c0 && !(e[1] & kPairFlags) && (a[2] & 63u) < room;
+		// (a trip may consume 32 bits at most — the ring's refill cadence counts on it: three entries are committed only
+		// before an ordinary fourth one; a flagged or prefix entry, up to 16 bits, waits for the next trip)
+		const bool c2 = c1 && !((e[2] | e[3]) & kPairFlags) && (e[3] & kPairCount) && (a[3] & 63u) < room;
+		const uint32_t an = c2 ? a[3] : (c1 ? a[2] : (c0 ? a[1] : 0u));
+		const uint32_t x = c2 ? e[3] : (c1 ? e[2] : (c0 ? e[1] : e[0]));
+		const uint32_t x1 = c1 ? e[3] : (c0 ? e[2] : e[1]);   // the entry after x (unless x is the group's last)
+		cur.take_group(an & 63u);
+		row = c2 ? r[3] : (c1 ? r[2] : (c0 ? r[1] : r[0]));
+		cnt += (an >> 6) & 15u;
+		const uint32_t left = room - (an & 63u);   // bits from here to the checkpoint (> 0)
+		if(x & kPairFlags) {
+			pair_slow_one<ORDER>(cur, T, lut_g, walk, row, clean);
+			++cnt;
+		} else if(!(x & kPairCount)) {   // the first 8 bits of a longer codeword: it ends with the next entry (one symbol of the prefix row)
+			if(!c2) {
+				cur.take_group(8u + (x1 & 15u));
+				row = x1 & 0xfc00u;
+				++cnt;
+			}   // else: the group's last entry — the next trip starts with it
+		} else if(x & 0x80u) {   // two symbols
+			const uint32_t l1 = lds_u8(T.len1 + (row >> 2) + (cur.hi >> 24));
+			if(l1 >= left) {   // the first one already reaches the checkpoint
+				cur.take(l1);
+				row = pair_row_of<ORDER>(T, (x >> 16) & 255u);
+				++cnt;
+			} else {
+				cur.take(x & 15u);
+				row = x & 0xfc00u;
+				cnt += 2;
+			}
+		} else {
+			cur.take(x & 15u);
+			row = x & 0xfc00u;
+			++cnt;
+		}
+		cur.top_up();   // before a return: the caller walks on into the next subsequence with this window
+		const int s = cw.cross(cur.pos, row >> 10, cnt, cp_st, cp_cn, compare);
+		if(s) return s == 1;
 	}
 }
 
@@ -739,6 +797,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		if(active) {
 			const uint32_t pos = uint32_t(uint64_t(my_sub - origin_sub) * sub_bits);
 			if(ORDER && my_sub == 0) row = PAIR ? pair_row_of<ORDER>(T, start0 & 255u) : lut_sa + ((start0 & 255u) << 9);   // the stream's own start (exact, or a shard's guess)
+			cur.set_reach(origin + uint64_t(end_sub - origin_sub) * sub_bits + 64);   // a thread walks at most to the end of its chunk
 			cur.seek(origin + pos, pos);
 			if(PAIR) walk_subsequence_pair<ORDER>(cur, T, lut_g, walk, pos, unit, cp_tab, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
 			else walk_subsequence<ORDER>(cur, lut_sa, lut_g, walk, pos, unit, cp_tab, span32, row, &cp_state[0][tid], &cp_count[0][tid], false);
