@@ -106,6 +106,7 @@ const TunableDef kTunables[kTunCount] = {
     {"dec_fused", "MH_DEC_FUSED"},
     {"enc_tma", "MH_ENC_TMA"},
     {"dec_cp_geo", "MH_DEC_CP_GEO"},
+    {"enc_warp", "MH_ENC_WARP"},
 };
 std::atomic<long long> g_tunables[kTunCount];
 struct TunableInit {
@@ -495,7 +496,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 	WS_CUDA(cudaMemset(ws->counters, 0, 16 * sizeof(uint32_t)));
 	WS_CUDA(cudaMemset(ws->hist_params, 0, 8 * sizeof(uint32_t)));
 	ws->enc_tiles_cap = encode_tiles_for(max_input_bytes) + 1;
-	WS_CUDA(cudaMalloc(&ws->enc_desc, ws->enc_tiles_cap * (2 * sizeof(uint64_t) + sizeof(uint32_t))));
+	WS_CUDA(cudaMalloc(&ws->enc_desc, ws->enc_tiles_cap * (2 * sizeof(uint64_t) + sizeof(uint32_t)) + 4096));   // 20 bytes per tile cover either kernel's descriptors (K2w: 16 per tile + 136 per 64 tiles)
 	ws->dec_subs_cap = decode_max_subs(max_payload_bytes);
 	ws->dec_chunks_cap = ws->dec_subs_cap / (kDecThreads - kDecWarmSubs) + 2;
 	WS_CUDA(cudaMalloc(&ws->dec_state, ws->dec_subs_cap * sizeof(uint32_t)));

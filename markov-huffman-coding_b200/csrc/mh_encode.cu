@@ -131,6 +131,8 @@ struct EncArgs {
 	uint64_t out_capacity_words;
 	unsigned long long* agg;
 	unsigned long long* inc;
+	unsigned long long* grp_acc;   // warp-private tiles: per group of tiles, tiles counted << 48 | bits (one per 128-byte line)
+	unsigned long long* grp_inc;   // ... and valid << 63 | bits up to and including the group
 	uint32_t* tail;
 	uint32_t* ticket;
 	unsigned long long* result;
@@ -710,6 +712,412 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	if(lane == 0 && dropped) atomicAdd(A.result + 1, (unsigned long long) dropped);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K2w: the context-row encoder with WARP-PRIVATE tiles (round 2; opt-in with the tunable enc_warp = 1).
+// One CTA of 32 warps per SM; after the table is staged there is no CTA-wide barrier, no per-CTA scanner warp and no
+// block scan: every warp pulls its own tiles of 32 x 32 input bytes from the atomic ticket and takes each of them through
+// the whole pipeline by itself, so the 32 warps of an SM are independent instruction streams:
+//   input     one bulk copy (TMA) per tile into the warp's own shared-memory buffer, issued by lane 0 one tile ahead,
+//             completion through the warp's own mbarrier; or 2 x 128-bit loads per lane (unaligned input, ragged tile)
+//   lookup    as in encode_kernel: context rows, eight independent quads per lane, merged on the fly
+//   scan      warp shuffles; the tile's bit count goes out at once: a relaxed store of the tile's aggregate word and one
+//             RED into the accumulator of its GROUP of 64 consecutive tiles (tiles counted << 48 | bits)
+//   pack      into the warp's own zeroed staging area (shared-memory OR of completed words), then the tile's last 31 bits
+//             are published (the successor needs them for the output word the two tiles share)
+//   prefix    ONE scan warp in the whole grid (warp 31 of the CTA that wins an election, so it is certainly running) turns
+//             complete group accumulators into inclusive prefixes, 32 groups per step, in order
+//   write-out one iteration later (software pipeline as in encode_kernel): bits before the tile = the scan warp's prefix of
+//             the group before (one word) + the aggregates of the lower tiles of its own group (one poll); funnel shift by
+//             the global bit phase, byte swap, coalesced 32-bit stores; the word shared with the predecessor is completed
+//             with the predecessor's tail bits, so every output word still has one writer; the staging words are
+//             re-zeroed in the same pass
+// A tile only ever waits for tiles with smaller tickets, which are running: no deadlock whatever the residency.
+//
+// What it measured (1 GiB Markov text, same box, alternating): 1.145 ms against 1.203 ms for encode_kernel — and
+// 1.22 / 1.10 ms with -h, 0.36 / 0.33 and 0.49 / 0.34 ms on the 256 MiB Fibonacci streams, so it stays opt-in. On the way:
+//   * a decoupled look-back per warp tile: 5.4 ms — with ~4700 tiles in flight the nearest inclusive prefix is thousands of
+//     tiles back (148 polls of 32); with groups and a look-back over group descriptors 1.38 ms (5.6 polls per tile, and
+//     every warp polls the same few L2 lines); walkers that publish what they found: 14 ms (stores into polled lines);
+//   * a ticket worth two tiles: 377 ms — the second tile stays reserved but unstarted for a tile time, its bit count comes
+//     as late as its successors need it, every wait delays the next publication and the delays feed each other;
+//   * one coordinator warp per CTA, chunks of 31 tiles per ticket, mbarrier hand-offs (chunk / bit counts / base) in
+//     shared memory, no global protocol traffic from the workers: 1.18 ms (the workers wait for the next chunk);
+//   * two staging areas per warp, write-out two iterations later (no bulk-copied input then: shared memory): the waits
+//     for the prefix disappear, 1.20-1.37 ms.
+// The instruction count per tile is no lower than encode_kernel's (about 1000 against 897 warp instructions per 1024
+// symbols: the per-tile bookkeeping is paid per warp instead of per CTA), and what is gained on barriers is lost on
+// L2 round trips (ticket, prefix, tail, group poll): this path is bound by its instruction count, not by its barriers.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kEncWarpThreads = 1024;
+constexpr uint32_t kWarpTileBytes = 32 * 32;
+constexpr uint32_t kEncGroupTiles = 64;                    // tiles per look-back group
+constexpr uint32_t kGroupAccStride = 16;                   // u64 words between two groups' accumulators: a 128-byte line each
+constexpr unsigned long long kGroupBitsMask = (1ull << 48) - 1;   // group accumulator: tiles counted << 48 | bits
+constexpr unsigned long long kTail64Valid = 1ull << 63;   // tail word: valid | min(bits, 31) << 32 | the tile's last bits
+
+__host__ __device__ __forceinline__ uint32_t warp_stage_words(uint32_t longest) {   // staged words of one warp tile, whatever the input
+	return ((kWarpTileBytes * (longest ? longest : 1u) + 31u) / 32u + 3u) & ~3u;
+}
+// dynamic shared memory: table, 32 x (4 zero words + stage_words + 4 words of slack), 32 input buffers (TMA)
+__host__ __device__ __forceinline__ uint32_t warp_kernel_smem(uint32_t ctx_rows, uint32_t stage_words, bool tma) {
+	return ((ctx_rows * kCtxPitch + 15u) & ~15u) + (kEncWarpThreads / 32) * (stage_words + 8u) * 4u + (tma ? (kEncWarpThreads / 32) * (kWarpTileBytes + kEncInbufLead) : 0u);
+}
+
+// The last min(bits before this tile, 31) bits of the stream before `tile` (one lane).
+__device__ __forceinline__ uint32_t predecessor_tail64(uint32_t tile, const unsigned long long* tails) {
+	if(tile == 0) return 0;
+	unsigned long long tv;
+	do { tv = ld_relaxed(tails + tile - 1); } while(!(tv & kTail64Valid));
+	uint32_t t_tail = uint32_t(tv) & uint32_t(kLow31), t_bits = uint32_t(tv >> 32) & 63u;
+	// Rare (a predecessor produced fewer than 31 bits: dropped symbols): keep prepending older tiles.
+	for(long long j = (long long) tile - 2; j >= 0 && t_bits < 31; --j) {
+		do { tv = ld_relaxed(tails + j); } while(!(tv & kTail64Valid));
+		const uint32_t b = uint32_t(tv >> 32) & 63u;
+		t_tail = uint32_t(((uint64_t(uint32_t(tv) & uint32_t(kLow31)) << t_bits) | t_tail) & kLow31);
+		t_bits = b + t_bits > 31 ? 31u : b + t_bits;
+	}
+	return t_tail;
+}
+
+template <int ORDER, bool TMA>
+__global__ void __launch_bounds__(kEncWarpThreads, 1) encode_warp_kernel(const EncArgs A) {
+	constexpr int SPT = 32, NWORDS = SPT / 4;
+	constexpr uint32_t NW = kEncWarpThreads / 32;
+	__shared__ uint8_t s_rank[256];   // row of every byte value as a context
+	__shared__ __align__(8) unsigned long long s_mbar[NW];
+	extern __shared__ uint32_t smem[];
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t bit0 = A.bit_base_dev ? uint32_t(__ldg(A.bit_base_dev) & 7ull) : A.bit0;
+	const uint32_t first_prev = A.prev0_dev ? uint32_t(__ldg(A.prev0_dev) & 255ull) : A.prev0;
+	uint32_t ctx_rows = A.ctx_rows, stage_words = A.stage_words;
+	if(A.meta) {   // device-built tables: check that this launch's shared memory fits them
+		ctx_rows = __ldg(A.meta);
+		const uint32_t status = __ldg(A.meta + 1), longest = __ldg(A.meta + 2);
+		stage_words = warp_stage_words(longest);
+		if(status != 0 || ctx_rows > uint32_t(kEncCtxMaxRows) || longest > uint32_t(kEncCtxMaxBits) || warp_kernel_smem(ctx_rows, stage_words, TMA) > A.smem_bytes) {
+			if(blockIdx.x == 0 && tid == 0) A.result[3] = status ? (unsigned long long) (long long) (int) status : 1ull;   // the caller takes the host-built path
+			return;
+		}
+	}
+	for(uint32_t i = tid; i < ctx_rows * 256u; i += kEncWarpThreads) smem[(i >> 8) * (kCtxPitch / 4) + (i & 255u)] = __ldg(A.ctx + i);
+	if(tid < 256) s_rank[tid] = uint8_t(__ldg(A.ctx + (ctx_rows - 1) * 256u + tid) >> 16);
+	const uint32_t table_words = ((ctx_rows * kCtxPitch + 15u) & ~15u) / 4u;
+	const uint32_t per_warp = stage_words + 8u;
+	for(uint32_t i = tid; i < per_warp * NW; i += kEncWarpThreads) smem[table_words + i] = 0;
+	const uint32_t table_sa = uint32_t(__cvta_generic_to_shared(smem));
+	const uint32_t rank_sa = uint32_t(__cvta_generic_to_shared(s_rank));
+	uint32_t* stage = smem + table_words + warp * per_warp + 4;   // stage[-1] reads as "no bits"
+	const uint32_t stage_sa = uint32_t(__cvta_generic_to_shared(stage));
+	const uint32_t inbuf_sa = table_sa + (table_words + per_warp * NW) * 4u + warp * (kWarpTileBytes + kEncInbufLead);
+	const uint32_t mbar_sa = uint32_t(__cvta_generic_to_shared(&s_mbar[warp]));
+	const uint32_t full_tiles = uint32_t(A.n / kWarpTileBytes);
+	if(TMA && lane == 0) {
+		mbar_init(mbar_sa, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();   // the only CTA-wide barrier
+
+	auto issue_tile = [&](uint32_t t) {   // lane 0: the tile's bytes and the 16 before them (its first context)
+		if(t >= full_tiles) return;
+		const uint64_t at = uint64_t(t) * kWarpTileBytes;
+		if(t) bulk_load_tile(inbuf_sa, A.in + at - kEncInbufLead, kWarpTileBytes + kEncInbufLead, mbar_sa);
+		else bulk_load_tile(inbuf_sa + kEncInbufLead, A.in, kWarpTileBytes, mbar_sa);
+	};
+	auto row_of = [&](uint32_t byte) -> uint32_t {
+		uint32_t r;
+		asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_sa + byte));
+		return table_sa + r * kCtxPitch;
+	};
+
+	// ---- the scan warp: ONE warp of the whole grid (warp 31 of the CTA that wins the election, so it is certainly running)
+	// turns the groups' complete accumulators into inclusive prefixes, 32 groups per step, in order. The tiles then read
+	// ONE word each. (Tiles that walk back over the group descriptors themselves — a decoupled look-back per warp — were
+	// 15 % slower at best: with ~4700 tiles in flight everybody polls the same few L2 lines, and the walk is 5 polls long.)
+	if(warp == NW - 1) {
+		uint32_t won = 0;
+		if(lane == 0) won = atomicCAS(A.ticket + 1, 0u, 1u) == 0u ? 1u : 0u;
+		if(__shfl_sync(0xffffffffu, won, 0)) {
+			const uint32_t n_groups = (A.n_tiles + kEncGroupTiles - 1) / kEncGroupTiles;
+			unsigned long long running = 0;
+			for(uint32_t g0 = 0; g0 < n_groups;) {
+				const uint32_t g = g0 + lane;
+				const uint32_t want = g < n_groups ? (A.n_tiles - g * kEncGroupTiles < kEncGroupTiles ? A.n_tiles - g * kEncGroupTiles : kEncGroupTiles) : 0xffffffffu;
+				const unsigned long long acc = g < n_groups ? ld_relaxed(A.grp_acc + size_t(g) * kGroupAccStride) : 0ull;
+				const unsigned open = __ballot_sync(0xffffffffu, uint32_t(acc >> 48) != want);   // lanes beyond the last group always count as open
+				const uint32_t done = open ? uint32_t(__ffs(open) - 1) : 32u;   // complete groups in front
+				if(done == 0) { __nanosleep(100); continue; }   // poll again
+				unsigned long long incl = acc & kGroupBitsMask;
+#pragma unroll
+				for(int d = 1; d < 32; d <<= 1) {
+					const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+					if(lane >= uint32_t(d)) incl += t;
+				}
+				if(lane < done) st_relaxed(A.grp_inc + g, kTail64Valid | (running + incl));
+				running += __shfl_sync(0xffffffffu, incl, done - 1);
+				g0 += done;
+			}
+			return;
+		}
+	}
+
+	uint32_t dropped = 0, in_parity = 0;
+	uint32_t tile = 0;
+	if(lane == 0) {
+		tile = atomicAdd(A.ticket, 1u);
+		if(TMA && tile < A.n_tiles) issue_tile(tile);
+	}
+	tile = __shfl_sync(0xffffffffu, tile, 0);
+	// Software pipeline, as in encode_kernel: a tile is written out one iteration after it was packed — after the NEXT
+	// tile has been loaded, looked up, counted and published. By then every tile with a smaller ticket has long published
+	// its bit count (a tile publishes well within one tile time of its ticket, the look-back runs two tile times after it),
+	// so the look-back never waits; and the next tile's bit count is out as early as it can be.
+	bool pending = false;   // a packed tile is waiting in the staging area
+	uint32_t p_tile = 0, p_bits = 0;
+	for(;;) {
+		const bool valid = tile < A.n_tiles;
+		if(!valid && !pending) break;
+		uint32_t next_ticket = tile;   // lane 0 only; the atomic's answer is first looked at after the lookups
+		// (one tile per ticket: a ticket worth two tiles keeps the second one reserved but unstarted for a whole tile time, its
+		// bit count comes as late as its successors' look-back, every look-back waits a little, the delays feed each other
+		// and the kernel all but serialises: measured 377 ms)
+		if(valid && lane == 0) next_ticket = atomicAdd(A.ticket, 1u);
+		const uint64_t my = uint64_t(tile) * kWarpTileBytes + lane * SPT;
+		uint32_t q_hi[SPT / 4], q_lo[SPT / 4], q_len[SPT / 4];
+		uint32_t esc_mask = 0, pos = 0, tile_bits = 0;
+		if(valid) {
+		// ================= phase A: load, look up, count, publish (tile `tile`) =================
+		// ---- input ----
+		uint32_t w[NWORDS];
+#pragma unroll
+		for(int k = 0; k < NWORDS; ++k) w[k] = 0;
+		int live = 0;
+		uint32_t prev = 0;
+		const bool from_smem = TMA && tile < full_tiles;
+		if(from_smem) {
+			mbar_wait(mbar_sa, in_parity);
+			in_parity ^= 1u;
+			live = SPT;
+#pragma unroll
+			for(int k = 0; k < SPT / 16; ++k) {
+				const uint4 v = lds128(inbuf_sa + kEncInbufLead + lane * SPT + 16 * k);
+				w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+			}
+			if(lane == 0 && tile) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(prev) : "r"(inbuf_sa + kEncInbufLead - 1u) : "memory");
+		} else if(my < A.n) {
+			live = A.n - my >= uint64_t(SPT) ? SPT : int(A.n - my);
+			if(live == SPT && ((reinterpret_cast<uint64_t>(A.in) & 15) == 0)) {
+#pragma unroll
+				for(int k = 0; k < SPT / 16; ++k) {
+					const uint4 v = ld_stream_128(A.in + my + 16 * k);
+					w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+				}
+			} else {
+#pragma unroll
+				for(int i = 0; i < SPT; ++i)
+					if(i < live) w[i >> 2] |= uint32_t(A.in[my + i]) << (8 * (i & 3));
+			}
+			if(lane == 0 && my) prev = uint32_t(A.in[my - 1]);
+		}
+		{
+			const uint32_t up = __shfl_up_sync(0xffffffffu, w[NWORDS - 1] >> 24, 1);
+			if(lane) prev = up;
+			else if(my == 0) prev = first_prev;
+		}
+
+		// ---- lookup + merge: quads as (hi:lo, length); see encode_kernel ----
+		uint32_t my_bits = 0;
+		{
+			uint32_t row = table_sa;
+			if(ORDER) row = row_of(prev);
+			uint32_t floor = 0xffffffffu, ceil = 0;
+			auto lookup = [&](int i, bool checked) -> uint32_t {
+				const uint32_t c = __byte_perm(w[i >> 2], 0, 0x4440 + (i & 3));
+				uint32_t ent = 0;
+				if(!checked || i < live) {
+					ent = lds32(row + c * 4);
+					if(ORDER) row = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
+					floor = min(floor, ent);
+					ceil = max(ceil, ent);
+				}
+				return ent;
+			};
+			auto quads = [&](bool checked) {
+#pragma unroll
+				for(int q = 0; q < SPT / 4; ++q) {
+					if(ORDER && q) row = row_of(__byte_perm(w[q - 1], 0, 0x4443));
+					const uint32_t e0 = lookup(4 * q, checked), e1 = lookup(4 * q + 1, checked), e2 = lookup(4 * q + 2, checked), e3 = lookup(4 * q + 3, checked);
+					const uint32_t l1 = e1 >> 27, l3 = e3 >> 27;
+					const uint32_t lp0 = (e0 >> 27) + l1, lp1 = (e2 >> 27) + l3;
+					const uint32_t p0 = ((e0 & 0xffffu) << l1) | (e1 & 0xffffu);
+					const uint32_t p1 = ((e2 & 0xffffu) << l3) | (e3 & 0xffffu);
+					uint32_t lo;
+					asm("shl.b32 %0, %1, %2;" : "=r"(lo) : "r"(p0), "r"(lp1));   // lp1 may be 32
+					q_lo[q] = lo | p1;
+					q_hi[q] = __funnelshift_lc(p0, 0u, lp1);
+					q_len[q] = lp0 + lp1;
+					my_bits += lp0 + lp1;
+				}
+			};
+			if(live == SPT) quads(false);
+			else quads(true);
+			if((ceil >> 27) == 31u) {   // rare: a codeword longer than 16 bits (length marker 31) somewhere in this lane
+#pragma unroll
+				for(int q = 0; q < SPT / 4; ++q) {
+					if(q_len[q] >= 31u) {
+						uint32_t p = q ? __byte_perm(w[q ? q - 1 : 0], 0, 0x4443) : prev, sum = 0;
+						bool big = false;
+#pragma unroll
+						for(int i = 0; i < 4; ++i) {
+							if(4 * q + i < live) {
+								const uint32_t c = __byte_perm(w[q], 0, 0x4440 + i);
+								const uint32_t len = uint32_t(__ldg(A.wide + ((ORDER ? p : 0u) << 8) + c) >> 56);
+								big |= len > 16u;
+								sum += len;
+								p = c;
+							}
+						}
+						if(big) {
+							esc_mask |= 1u << q;
+							my_bits += sum - q_len[q];
+						}
+					}
+				}
+			}
+			if(floor < (1u << 27)) {   // rare: some symbol has no codeword; count them exactly (context rows again)
+				uint32_t r2 = table_sa;
+				if(ORDER) r2 = row_of(prev);
+#pragma unroll 1
+				for(int i = 0; i < live; ++i) {
+					const uint32_t c = A.in[my + i];
+					const uint32_t ent = lds32(r2 + c * 4);
+					if(ORDER) r2 = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
+					dropped += (ent >> 27) == 0 ? 1u : 0u;
+				}
+			}
+		}
+		// ---- the next tile's input: every lane has long taken this tile's bytes out of the buffer ----
+		if(TMA && lane == 0) issue_tile(next_ticket);
+		if(!TMA) {   // no bulk copy: pull it into L2 while this tile is packed
+			const uint32_t nt = __shfl_sync(0xffffffffu, next_ticket, 0);
+			const uint64_t off = uint64_t(nt) * kWarpTileBytes + uint64_t(lane) * 128u;
+			if(lane < kWarpTileBytes / 128 && nt < A.n_tiles && off < A.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.in + off));
+		}
+		// ---- warp scan; the tile's bit count is published right away ----
+		uint32_t incl = my_bits;
+#pragma unroll
+		for(int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+			if(lane >= uint32_t(d)) incl += t;
+		}
+		tile_bits = __shfl_sync(0xffffffffu, incl, 31);
+		pos = incl - my_bits;
+		// Tiles come in groups of kEncGroupTiles consecutive tickets. Thousands of warp tiles are in flight at once, and a
+		// look-back over single tiles would have to walk back through all of them to the nearest inclusive prefix (measured:
+		// 5.4 ms per GiB); with groups it reads its own group's tiles (one poll) and ~20 group descriptors (one poll).
+		// A group's aggregate is complete when its accumulator has counted all its tiles (no return value: a RED).
+		if(lane == 0) {
+			st_relaxed(A.agg + tile, kAgg | tile_bits);
+			atomicAdd(A.grp_acc + size_t(tile / kEncGroupTiles) * kGroupAccStride, (1ull << 48) | tile_bits);   // a RED: nobody waits for it
+		}
+		}   // phase A
+		const uint32_t next_tile = __shfl_sync(0xffffffffu, next_ticket, 0);
+
+		// ================= phase B: write out the pending tile (packed in the previous iteration) =================
+		if(pending) {
+		const uint32_t group = p_tile / kEncGroupTiles, gi = p_tile % kEncGroupTiles, gbase = group * kEncGroupTiles;
+		// ---- look-back, two levels: the lower tiles of this tile's group, then the groups before it ----
+		unsigned long long excl;
+		{
+			for(;;) {   // (a) tiles gbase .. tile - 1 (smaller tickets: running, and they publish before they wait for anyone)
+				const unsigned long long v0 = lane < gi ? ld_relaxed(A.agg + gbase + lane) : kAgg;
+				const unsigned long long v1 = lane + 32 < gi ? ld_relaxed(A.agg + gbase + 32 + lane) : kAgg;
+				if(!__all_sync(0xffffffffu, (v0 >> 62) != 0 && (v1 >> 62) != 0)) { __nanosleep(100); continue; }   // poll again
+				excl = warp_sum((v0 & kDescValueMask) + (v1 & kDescValueMask));
+				break;
+			}
+			if(group) {   // (b) the bits before this group: the scan warp's running prefix (one word, normally there long since)
+				unsigned long long inc = 0;
+				if(lane == 0) while(!((inc = ld_relaxed(A.grp_inc + group - 1)) >> 63)) __nanosleep(200);
+				excl += __shfl_sync(0xffffffffu, inc, 0) & ~kTail64Valid;
+			}
+			if(lane == 0) {
+				if(p_tile == A.n_tiles - 1) A.result[0] = excl + p_bits;
+			}
+		}
+
+		// ---- copy-out: funnel shift by the global bit phase; the staging words are re-zeroed on the way ----
+		{
+			const unsigned long long g0 = bit0 + excl, g1 = g0 + p_bits;
+			const uint32_t s = uint32_t(g0 & 31);
+			const unsigned long long w0 = g0 >> 5;
+			unsigned long long w1 = g1 >> 5;                               // words [w0, w1) are completed by this tile
+			if(p_tile == A.n_tiles - 1 && (g1 & 31)) ++w1;                   // the stream's last partial word, zero padded
+			uint32_t nw = uint32_t(w1 - w0);
+			if(w1 > A.out_capacity_words) {
+				if(lane == 0) A.result[2] = 1;                             // capacity error; this tile writes nothing
+				nw = 0;
+			}
+			const uint32_t used = (p_bits + 31) >> 5;                   // staging words that hold bits (nw <= used + 1)
+			// the word shared with the predecessor: its last s bits open word w0
+			uint32_t carry = 0;
+			if(lane == 0 && s && nw) carry = predecessor_tail64(p_tile, A.inc) & ((1u << s) - 1u);
+			uint32_t* dp = A.out_words + w0 + lane;
+			for(uint32_t j = lane; j - lane <= used; j += 32, dp += 32) {
+				const uint32_t cur = j <= used ? lds32(stage_sa + j * 4) : 0u;   // word `used` is a zero word
+				uint32_t before = __shfl_up_sync(0xffffffffu, cur, 1);
+				if(lane == 0) before = carry;
+				carry = __shfl_sync(0xffffffffu, cur, 31);
+				if(j < nw) *dp = __byte_perm(__funnelshift_r(cur, before, s), 0, 0x0123);
+				if(j < used) stage[j] = 0;
+			}
+		}
+		__syncwarp();   // the staging area is clean before the next tile is packed into it
+		pending = false;
+		}   // phase B
+
+		// ================= phase C: pack tile `tile` into the staging area =================
+		if(valid) {
+		// ---- pack into the warp's staging area ----
+		{
+			Packer32 pk;
+			pk.start(stage_sa, pos);
+#pragma unroll
+			for(int q = 0; q < SPT / 4; ++q) {
+				if(esc_mask & (1u << q)) {   // rare: the quad holds a codeword of 17..29 bits: one unit per symbol, from the wide table
+					const uint64_t at = my + 4 * q;
+					uint32_t p = at == 0 ? first_prev : uint32_t(A.in[at - 1]);
+#pragma unroll 1
+					for(int i = 0; i < 4 && at + i < A.n; ++i) {
+						const uint32_t c = A.in[at + i];
+						const unsigned long long ent = __ldg(A.wide + ((ORDER ? p : 0u) << 8) + c);
+						pk.put(uint32_t(ent), uint32_t(ent >> 56));
+						p = c;
+					}
+				} else if(q_len[q] <= 32) {
+					pk.put(q_lo[q], q_len[q]);
+				} else {   // a quad of long codewords: the top q_len - 32 bits, then the low word
+					pk.put(q_hi[q], q_len[q] - 32);
+					pk.put(q_lo[q], 32);
+				}
+			}
+			pk.finish();
+		}
+		__syncwarp();   // staged bits visible to the whole warp
+		if(lane == 0) {   // the tail goes out now: the successor needs it when it writes its first word, an iteration from now
+			const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
+			st_relaxed(A.inc + tile, kTail64Valid | (uint64_t(tcount) << 32) | stage_bits(stage, tile_bits - tcount, tcount));
+		}
+
+		pending = true;
+		p_tile = tile;
+		p_bits = tile_bits;
+		}   // phase C
+		tile = next_tile;
+	}
+	dropped = uint32_t(warp_sum(dropped));
+	if(lane == 0 && dropped) atomicAdd(A.result + 1, (unsigned long long) dropped);
+}
+
 template <int SPT, int FMT, int ORDER = 1, bool TMA = false>
 int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStream_t st) {
 	auto kern = aligned ? encode_kernel<SPT, FMT, true, ORDER, TMA> : encode_kernel<SPT, FMT, false, ORDER, false>;
@@ -730,7 +1138,7 @@ int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStr
 
 }  // namespace
 
-uint64_t encode_tiles_for(uint64_t n) { return (n + kEncThreads * 16 - 1) / (kEncThreads * 16); }
+uint64_t encode_tiles_for(uint64_t n) { return (n + kWarpTileBytes - 1) / kWarpTileBytes + 1; }   // the smallest tiles any variant uses (K2w: 1 KiB)
 
 int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codebook* cb, uint64_t bit_base,
                   uint8_t* d_out, uint64_t out_capacity, unsigned long long* d_result, mh_workspace* ws, cudaStream_t st,
@@ -770,9 +1178,10 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	const uint64_t tile_bytes = uint64_t(kEncThreads) * spt;
 	const uint64_t tiles = (n + tile_bytes - 1) / tile_bytes;
 	if(tiles > ws->enc_tiles_cap || tiles > 0x7fffffffull) return MH_ERR_WORKSPACE;
-	// descriptors: aggregate words, inclusive words, tail words
-	MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, tiles * (2 * sizeof(uint64_t) + sizeof(uint32_t)), st));
-	MH_CUDA(cudaMemsetAsync(ws->counters, 0, sizeof(uint32_t), st));
+	// descriptors: aggregate words, inclusive words, tail words (the warp-private kernel lays its own out below)
+	const bool warp_tiles = fmt == FMT_CTX && tunable(kTunEncWarp) > 0;   // opt-in (enc_warp = 1): see the K2w header for what it measured
+	if(!warp_tiles) MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, tiles * (2 * sizeof(uint64_t) + sizeof(uint32_t)), st));
+	MH_CUDA(cudaMemsetAsync(ws->counters, 0, 2 * sizeof(uint32_t), st));   // the tile ticket, the scan warp's election flag
 
 	EncArgs a;
 	a.in = d_in; a.n = n; a.prev0 = prev0; a.order = cb->order;
@@ -789,6 +1198,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.out_capacity_words = out_capacity / 4;
 	a.agg = reinterpret_cast<unsigned long long*>(ws->enc_desc);
 	a.inc = a.agg + tiles;
+	a.grp_acc = a.grp_inc = nullptr;
 	a.tail = reinterpret_cast<uint32_t*>(a.inc + tiles);
 	a.ticket = ws->counters;
 	a.result = d_result;
@@ -803,6 +1213,44 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	if(dev) smem = size_t(kEncCtxSmemLimit);
 	a.smem_bytes = uint32_t(smem);
 
+	if(warp_tiles) {   // warp-private tiles (K2w)
+		const uint64_t wtiles = (n + kWarpTileBytes - 1) / kWarpTileBytes;
+		if(wtiles > ws->enc_tiles_cap || wtiles > 0x7fffffffull) return MH_ERR_WORKSPACE;
+		const uint64_t wgroups = (wtiles + kEncGroupTiles - 1) / kEncGroupTiles;
+		MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, (wtiles * 2 + wgroups * (kGroupAccStride + 1) + 16) * sizeof(uint64_t), st));   // tile aggregates, tile tails, group prefixes, group accumulators
+		a.agg = reinterpret_cast<unsigned long long*>(ws->enc_desc);
+		a.inc = a.agg + wtiles;   // the tail words
+		a.grp_inc = a.inc + wtiles;
+		a.grp_acc = a.grp_inc + ((wgroups + 15) & ~uint64_t(15));   // one accumulator per 128-byte line: 64 additions each, and the scan warp polls them
+		a.tail = nullptr;
+		a.n_tiles = uint32_t(wtiles);
+		a.stage_words = warp_stage_words(uint32_t(maxb));
+		const bool wtma = aligned && tunable(kTunEncTma) != 0;
+		const size_t room = size_t(max_smem_optin()) - 2048;   // one CTA per SM (the kernel's static shared memory is ~1.2 KiB): the device-built path takes all of it
+		size_t wsmem = dev ? room : size_t(warp_kernel_smem(cb->ctx_rows, a.stage_words, wtma));
+		if(wsmem <= room) {
+			a.smem_bytes = uint32_t(wsmem);
+			auto kern = cb->order ? (wtma ? encode_warp_kernel<1, true> : encode_warp_kernel<1, false>) : (wtma ? encode_warp_kernel<0, true> : encode_warp_kernel<0, false>);
+			MH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wsmem)));
+			uint64_t grid = uint64_t(sm_count());
+			const uint64_t ctas_needed = (wtiles + kEncWarpThreads / 32 - 1) / (kEncWarpThreads / 32);
+			if(grid > ctas_needed) grid = ctas_needed;
+			{
+				ProfScope p("encode_kernel", st);
+				kern<<<unsigned(grid), kEncWarpThreads, wsmem, st>>>(a);
+			}
+			count_launch(1);
+			MH_CUDA(cudaGetLastError());
+			return MH_OK;
+		}
+		// a host-built table too large for one CTA's shared memory: the CTA-wide kernel below
+		a.agg = reinterpret_cast<unsigned long long*>(ws->enc_desc);
+		a.inc = a.agg + tiles;
+		a.tail = reinterpret_cast<uint32_t*>(a.inc + tiles);
+		a.n_tiles = uint32_t(tiles);
+		a.stage_words = stage_words;
+		MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, tiles * (2 * sizeof(uint64_t) + sizeof(uint32_t)), st));
+	}
 	if(fmt == FMT_CTX && tma) return cb->order ? launch_variant<32, FMT_CTX, 1, true>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0, true>(aligned, a, smem, st);
 	if(fmt == FMT_CTX) return cb->order ? launch_variant<32, FMT_CTX, 1>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0>(aligned, a, smem, st);
 	if(fmt == FMT_WIDE) return launch_variant<16, FMT_WIDE>(aligned, a, smem, st);

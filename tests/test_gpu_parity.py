@@ -194,6 +194,28 @@ def test_encoder_table_formats_agree(session, ipsum_counts, fmt, tunables):
         assert session.compress(data, order)[0] == want[order]
 
 
+def test_warp_private_encoder_agrees(session, ipsum_counts, tunables):
+    """The opt-in encoder with warp-private tiles (enc_warp = 1: one scan warp, tile groups, per-warp staging) writes the
+    same bytes: text at sizes around its 1 KiB tiles and 64-tile groups, with and without bulk-copied input, a
+    Fibonacci stream (codewords beyond 16 bits escape to the wide table), dropped symbols (tiles of very few bits)."""
+    text = o.synth_markov(ipsum_counts, 31, 65536, 0, (5 << 20) + 1029)
+    want = {(n, order): o.compress_from_input(text[:n], bool(order))[0]
+            for n in (1, 1023, 1024, 1025, 65536, 65537, (1 << 20) + 3, len(text)) for order in (0, 1)}
+    fib = o.synth_fibonacci(40, 48, 7, 0, (2 << 20) + 5)
+    want_fib = {order: o.compress_from_input(fib, bool(order))[0] for order in (0, 1)}
+    provider = mh.CodingProvider.from_counts_array(o.histogram(b"abracadabra" * 50, True).astype(np.uint64), 1)
+    holes = b"abraXcadabra" * 3000 + b"ZZZZ" * 5000 + b"abra"
+    want_holes = o.Table.from_counts(o.histogram(b"abracadabra" * 50, True), True).compress(holes, return_dropped=True)
+    tunables("enc_warp", "1")
+    for tma in ("1", "0"):
+        tunables("enc_tma", tma)
+        for (n, order), stream in want.items():
+            assert session.compress(text[:n], order)[0] == stream, "n=%d order=%d tma=%s" % (n, order, tma)
+        for order in (0, 1):
+            assert session.compress(fib, order)[0] == want_fib[order]
+        assert session.compress_with_table(provider, holes) == want_holes
+
+
 @pytest.mark.parametrize("pair", ["1", "0"], ids=["pair-table", "lut8"])
 @pytest.mark.parametrize("sub_bits", ["256", "1024", "8192"])
 def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, pair, tunables):
