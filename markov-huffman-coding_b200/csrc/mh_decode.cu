@@ -445,10 +445,33 @@ __device__ __forceinline__ void pair_lookups(const Cursor& cur, const PairTab& T
 }
 
 // One symbol through the reference's path (u16 LUT + walk table in global memory), keeping `row` in step.
-// `row` must be a context row or the null row.
+// `row` is a context row or the null row — or a prefix row, when the window selects a deep flag there: a codeword of 17
+// bits or more, of which the walker has taken the first 8; the flag names the tree node its next 8 bits lead to, and the
+// context whose tree that is, and the walk goes on from there bit by bit (src/coding.cpp:137-149).
 template <int ORDER>
 __device__ __forceinline__ uint32_t pair_slow_one(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
                                                   const uint32_t* __restrict__ walk, uint32_t& row, bool& clean) {
+	if(row > T.null_row) {
+		const uint32_t x = lds_u32(T.tab + (row | ((cur.hi >> 22) & 0x3fcu)));
+		cur.take(8);
+		const uint32_t* nodes = walk + (ORDER ? ((x >> 16) & 255u) << 9 : 0u);
+		uint32_t node = (x >> 6) & 511u, sym = ' ';
+		for(int guard = 0; guard < 256; ++guard) {
+			cur.top_up();
+			if((guard & 15) == 0) cur.refill_round();   // the walk tops the ring up itself
+			const uint32_t bit = cur.hi >> 31;
+			cur.take(1);
+			const uint32_t w = __ldg(nodes + node);
+			const uint32_t child = bit ? (w & 0xffffu) : (w >> 16);
+			if(child & 0x8000u) { sym = child & 255u; break; }
+			node = child;
+			if(guard == 255) clean = false;
+		}
+		cur.top_up();
+		if(ORDER) row = lds_u8(T.rank + sym) << 10;
+		else row = 0u;
+		return sym;
+	}
 	uint32_t row_off = ORDER ? lds_u8(T.live + (row >> 10)) << 9 : 0u;
 	const uint32_t sym = decode_one<ORDER, false>(cur, 0u, lut_g, walk, row_off, clean);
 	if(ORDER) row = lds_u8(T.rank + sym) << 10;
@@ -456,8 +479,8 @@ __device__ __forceinline__ uint32_t pair_slow_one(Cursor& cur, const PairTab& T,
 }
 
 // Exactly one symbol, given the entry e0 the window selects in `row`: a single-symbol entry is taken as it is, a
-// pair gives up its first symbol only (its length comes from len1), a prefix or flagged entry — which only live in
-// context rows — goes through the global tables.
+// pair gives up its first symbol only (its length comes from len1), a prefix or flagged entry goes through the global
+// tables (a flagged entry of a prefix row: from the node it names).
 template <int ORDER>
 __device__ __forceinline__ uint32_t pair_step_one(Cursor& cur, const PairTab& T, const uint16_t* __restrict__ lut_g,
                                                   const uint32_t* __restrict__ walk, uint32_t e0, uint32_t& row, bool& clean) {
@@ -522,8 +545,14 @@ __device__ __forceinline__ bool walk_subsequence_pair(Cursor& cur, const PairTab
 			++cnt;
 		} else if(!(x & kPairCount)) {   // the first 8 bits of a longer codeword: it ends with the next entry (one symbol of the prefix row)
 			if(!c2) {
-				cur.take_group(8u + (x1 & 15u));
-				row = x1 & 0xfc00u;
+				if(x1 & kPairFlags) {   // 17 bits or more: the prefix row names the node, the walk goes on from there
+					cur.take(8);
+					row = x & 0xfc00u;
+					pair_slow_one<ORDER>(cur, T, lut_g, walk, row, clean);
+				} else {
+					cur.take_group(8u + (x1 & 15u));
+					row = x1 & 0xfc00u;
+				}
 				++cnt;
 			}   // else: the group's last entry — the next trip starts with it
 		} else if(x & 0x80u) {   // two symbols

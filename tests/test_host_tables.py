@@ -247,3 +247,40 @@ def test_pair_table_entry_kinds_follow_the_8bit_lut():
                     n_prefix += 1
     assert n_prefix == rows - ctx_rows - 1 > 0      # every prefix row is reached from exactly one deep node
     assert rows <= 64
+
+
+def test_pair_table_prefix_rows_of_a_fibonacci_tree():
+    """A Fibonacci-shaped tree (codewords up to ~30 bits): its depth-8 node gets a prefix row although not every codeword
+    below it ends within 16 bits — those that do are one-symbol entries, the others deep flags naming the tree node reached
+    and the context ([14:6], [23:16]) — and a stream of <= 16-bit codewords decodes through the table without a flag."""
+    fib = np.zeros(256, dtype=np.uint64)
+    a, b = 1, 1
+    for i in range(32):
+        fib[65 + i] = a
+        a, b = b, a + b
+    p = mh.CodingProvider.from_counts_array(fib, 0)
+    assert p.max_code_bits() > 24
+    table, rank, live, len1, rows, ctx_rows = p.pair_lut()
+    assert ctx_rows == 1 and rows == 3            # the context row, the null row, one prefix row
+    t = table.reshape(rows, 256)
+    prefixes = [w for w in range(256) if not (int(t[0, w]) & 0x30) and ((int(t[0, w]) >> 6) & 15) == 0]
+    assert len(prefixes) == 1 and (int(t[0, prefixes[0]]) & 63) == 8 and ((int(t[0, prefixes[0]]) >> 10) & 63) == 2
+    singles = flags = 0
+    for w in range(256):
+        e = int(t[2, w])
+        if e & 0x10:
+            flags += 1
+            assert ((e >> 6) & 511) < 2 * 32 - 1 and ((e >> 16) & 255) == 0 and not (e & 0x20)
+        else:
+            singles += 1
+            assert ((e >> 6) & 15) == 1 and 1 <= (e & 15) <= 8 and ((e >> 10) & 63) == 0 and 65 <= ((e >> 16) & 255) < 97
+    assert singles > 0 and flags > 0
+    # symbols whose codewords stay within 16 bits: decoded through the table as the kernels' fast path does
+    lens = p.code_lengths()
+    short = [c for c in range(65, 97) if 0 < int(lens[c]) <= 16]
+    rng = np.random.default_rng(3)
+    data = bytes(rng.choice(short, 4000).astype(np.uint8))
+    stream = o.Table.from_counts(fib.astype(np.int64), False).compress(data)
+    payload = stream[1:]
+    got, pos = _pair_decode((table, rank, live, len1, rows, ctx_rows), payload, len(payload) * 8 - (stream[0] & 7), 0x20, False, len(data))
+    assert got == data
