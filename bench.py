@@ -505,7 +505,7 @@ def run_single(args, name, steps, dev, mh, want_e2e, want_cpu):
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": cfg["workload"] if n == cfg["bytes"] else cfg["workload"] + " [%d MiB]" % (n >> 20), "name": name, "bytes_per_gpu": n,
                    "baseline_config": "BASELINE.json configs[%d]" % cfg["baseline_config"],
-                   "step": "compress (histogram + host trees + encode) then extract (decode); 2 x bytes_per_gpu uncompressed bytes per step",
+                   "step": "compress (histogram + Huffman trees built on the device + encode) then extract (decode); 2 x bytes_per_gpu uncompressed bytes per step",
                    "l2": "inputs (>= 256 MiB) exceed the 126 MB L2; no flush needed", "compressed_ratio": c_bytes / n, "max_code_bits": state["provider"].max_code_bits(),
                    "sharding": "single GPU"},
         "encode_gbs": n * steps / (t_enc * 1e-3) / 1e9, "decode_gbs": n * steps / (t_dec * 1e-3) / 1e9,
