@@ -292,6 +292,11 @@ struct Packer32 {
 // and 32 lanes that look the SAME frequent byte up in DIFFERENT contexts — the common case in text — hit one bank
 // (4.8 wavefronts per warp lookup on the bench text); five words of padding rotate every row by 5 banks: 3.1.
 constexpr uint32_t kCtxPitch = (256 + 5) * 4;
+// Order 0 (-h) has ONE row, and 32 lanes that look 32 different bytes up in it collide like any 32 random banks (3.5
+// wavefronts per warp lookup). There the row is replicated per lane — entry c of lane l at word c * 32 + l, bank l — and
+// every lookup is one wavefront (32 KiB instead of 1 KiB).
+constexpr uint32_t kCtxOrder0Bytes = 256 * 32 * 4;
+__host__ __device__ __forceinline__ uint32_t ctx_table_bytes(uint32_t ctx_rows, int order) { return order ? ctx_rows * kCtxPitch : kCtxOrder0Bytes; }
 constexpr uint32_t kEncInbufLead = 16;   // the 16 bytes in front of a tile travel with it: the byte before the tile's first is its context
 
 template <int SPT, int FMT, bool ALIGNED, int ORDER = 1, bool TMA = false>
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 		ctx_rows = __ldg(A.meta);
 		const uint32_t status = __ldg(A.meta + 1), longest = __ldg(A.meta + 2);
 		stage_words = (kEncThreads * (SPT / 32) * (longest ? longest : 1u) + 7u) & ~3u;   // as launch_encode sizes it for host-built tables
-		const uint32_t need = ((ctx_rows * kCtxPitch + 15u) & ~15u) + (stage_words + 8u) * 4u + (TMA ? kTileBytes + kEncInbufLead + 16u : 0u);
+		const uint32_t need = ((ctx_table_bytes(ctx_rows, ORDER) + 15u) & ~15u) + (stage_words + 8u) * 4u + (TMA ? kTileBytes + kEncInbufLead + 16u : 0u);
 		if(status != 0 || ctx_rows > uint32_t(kEncCtxMaxRows) || longest > A.launched_bits || need > A.smem_bytes) {
 			if(blockIdx.x == 0 && tid == 0) A.result[3] = status ? (unsigned long long) (long long) (int) status : 1ull;   // the caller takes the host-built path
 			return;
@@ -328,8 +333,9 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 		for(uint32_t i = tid; i < table_entries; i += kEncCtaThreads) table[i] = __ldg(A.box + i);
 	}
 	if(FMT == FMT_CTX) {
-		table_entries = ctx_rows * (kCtxPitch / 4);
-		for(uint32_t i = tid; i < ctx_rows * 256u; i += kEncCtaThreads) table[(i >> 8) * (kCtxPitch / 4) + (i & 255u)] = __ldg(A.ctx + i);
+		table_entries = ctx_table_bytes(ctx_rows, ORDER) / 4;
+		if(ORDER) for(uint32_t i = tid; i < ctx_rows * 256u; i += kEncCtaThreads) table[(i >> 8) * (kCtxPitch / 4) + (i & 255u)] = __ldg(A.ctx + i);
+		else for(uint32_t i = tid; i < 256u * 32u; i += kEncCtaThreads) table[i] = __ldg(A.ctx + (i >> 5));   // the one row, once per lane
 		// A quad restarts its lookup chain from the byte before it: that byte's row comes from this byte map — four rows to a
 		// word, so the 32 lanes of a warp touch a handful of words (the null row's u32 entries cost ~3 wavefronts a lookup)
 		if(tid < 256) s_rank[tid] = uint8_t(__ldg(A.ctx + (ctx_rows - 1) * 256u + tid) >> 16);
@@ -486,14 +492,14 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 					asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_sa + byte));
 					return table_sa + r * kCtxPitch;
 				};
-				uint32_t row = table_sa;
+				uint32_t row = table_sa + lane * 4;
 				if(ORDER) row = row_of(prev);
 				uint32_t floor = 0xffffffffu, ceil = 0;
 				auto lookup = [&](int i, bool checked) -> uint32_t {
 					const uint32_t c = __byte_perm(w[i >> 2], 0, 0x4440 + (i & 3));
 					uint32_t ent = 0;
 					if(!checked || i < live) {
-						ent = lds32(row + c * 4);
+						ent = ORDER ? lds32(row + c * 4) : lds32(row + c * 128);   // order 0: `row` is the lane's column of the replicated row
 						if(ORDER) row = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
 						floor = min(floor, ent);
 						ceil = max(ceil, ent);
@@ -545,12 +551,12 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 					}
 				}
 				if(floor < (1u << 27)) {   // rare: some symbol has no codeword; count them exactly (context rows again)
-					uint32_t r2 = table_sa;
+					uint32_t r2 = table_sa + lane * 4;
 					if(ORDER) r2 = row_of(prev);
 #pragma unroll 1
 					for(int i = 0; i < live; ++i) {
 						const uint32_t c = A.in[my + i];   // re-read: indexing w[] dynamically would push it to local memory
-						const uint32_t ent = lds32(r2 + c * 4);
+						const uint32_t ent = ORDER ? lds32(r2 + c * 4) : lds32(r2 + c * 128);
 						if(ORDER) r2 = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
 						dropped += (ent >> 27) == 0 ? 1u : 0u;
 					}
@@ -1165,9 +1171,9 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	}
 	if(fmt != FMT_BOX_SMEM) table_bytes = 0;
 	// context rows (live contexts only, <= 16-bit codewords): preferred whenever table + staging fit two CTAs per SM
-	if(cb->ctx_rows && force_fmt < 0 && size_t(cb->ctx_rows) * kCtxPitch + (size_t(kEncThreads) * maxb + 64) * 4 <= size_t(kEncCtxSmemLimit)) {
+	if(cb->ctx_rows && force_fmt < 0 && size_t(ctx_table_bytes(cb->ctx_rows, cb->order)) + (size_t(kEncThreads) * maxb + 64) * 4 <= size_t(kEncCtxSmemLimit)) {
 		fmt = FMT_CTX;
-		table_bytes = size_t(cb->ctx_rows) * kCtxPitch;
+		table_bytes = size_t(ctx_table_bytes(cb->ctx_rows, cb->order));
 	}
 	if(dev) fmt = FMT_CTX;
 	// Tile size: the staged bits of one tile must fit the staging area whatever the input, so symbols per tile x
