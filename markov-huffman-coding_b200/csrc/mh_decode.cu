@@ -592,7 +592,7 @@ constexpr uint32_t kFlushEvery = 8;   // iterations between flush rounds. At a r
                                       // ring half of that unit again before the next round has written it out
 
 __device__ __forceinline__ void sts_u32_if(uint32_t addr, uint32_t v, bool go) {
-	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(uint32_t(go)) : "memory");
+	if(go) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");   // the compiler predicates the store on the comparison itself
 }
 
 // 16 bytes of a unit to global memory; only bytes [lo, hi) of the piece (0 <= lo, hi <= 16 after clamping) are written
@@ -683,37 +683,46 @@ __device__ __forceinline__ bool decode_emit_pair(Cursor& cur, const PairTab& T, 
 	uint32_t rem = count;
 	os.begin(out);
 	if(rem) cur.refill_round();
-	for(uint32_t it = 0; __any_sync(0xffffffffu, rem != 0); ++it) {
-		if(rem) {
-			if((it & (kRefillEvery - 1)) == kRefillEvery - 1) cur.refill_round();   // every lane of the warp in the same trip
-			uint32_t e[4], a[5], r[5];
-			pair_lookups<ORDER>(cur, T, row, e, a, r);
-			const uint32_t f4 = e[0] | e[1] | e[2] | e[3];
-			uint32_t gc = (a[4] >> 6) & 15u;
-			uint32_t g_lo, g_hi;
-			if(!(f4 & kPairFlags) && !(exact_end && gc > rem)) {
-				// selector by the number of symbols in the first entry of each half: 0 -> 0x3376, 1 -> 0x3762, 2 -> 0x7632
-				const uint32_t sel_a = __funnelshift_rc(0x37623376u, 0x7632u, (e[0] & kPairCount) >> 2);
-				const uint32_t sel_b = __funnelshift_rc(0x37623376u, 0x7632u, (e[2] & kPairCount) >> 2);
-				const uint32_t wa = __byte_perm(e[0], e[1], sel_a);
-				const uint32_t wb = __byte_perm(e[2], e[3], sel_b);
-				const uint32_t ca8 = (a[2] >> 3) & 0x78u;   // 8 x symbols of the first two entries (<= 32)
-				uint32_t up;
-				asm("shl.b32 %0, %1, %2;" : "=r"(up) : "r"(wb), "r"(ca8));   // clamps: 32 -> 0
-				g_lo = wa | up;
-				g_hi = __funnelshift_lc(wb, 0u, ca8);
-				gc = gc < rem ? gc : rem;
-				cur.take_group(a[4] & 63u);
-				row = r[4];
-			} else {
-				g_lo = pair_step_one<ORDER>(cur, T, lut_g, walk, e[0], row, clean);
-				g_hi = 0;
-				gc = 1;
-			}
-			rem -= gc;
-			os.append(g_lo, g_hi, gc);
-			cur.top_up();
+	// one trip of one lane; `tail`: the lane may be within a group of its last symbol (cut the group at `rem`, or step
+	// symbol by symbol when the exact end position is wanted)
+	auto trip = [&](uint32_t it, bool tail) {
+		if((it & (kRefillEvery - 1)) == kRefillEvery - 1) cur.refill_round();   // every lane of the warp in the same trip
+		uint32_t e[4], a[5], r[5];
+		pair_lookups<ORDER>(cur, T, row, e, a, r);
+		const uint32_t f4 = e[0] | e[1] | e[2] | e[3];
+		uint32_t gc = (a[4] >> 6) & 15u;
+		uint32_t g_lo, g_hi;
+		if(!(f4 & kPairFlags) && !(tail && exact_end && gc > rem)) {
+			// selector by the number of symbols in the first entry of each half: 0 -> 0x3376, 1 -> 0x3762, 2 -> 0x7632
+			const uint32_t sel_a = __funnelshift_rc(0x37623376u, 0x7632u, (e[0] & kPairCount) >> 2);
+			const uint32_t sel_b = __funnelshift_rc(0x37623376u, 0x7632u, (e[2] & kPairCount) >> 2);
+			const uint32_t wa = __byte_perm(e[0], e[1], sel_a);
+			const uint32_t wb = __byte_perm(e[2], e[3], sel_b);
+			const uint32_t ca8 = (a[2] >> 3) & 0x78u;   // 8 x symbols of the first two entries (<= 32)
+			uint32_t up;
+			asm("shl.b32 %0, %1, %2;" : "=r"(up) : "r"(wb), "r"(ca8));   // clamps: 32 -> 0
+			g_lo = wa | up;
+			g_hi = __funnelshift_lc(wb, 0u, ca8);
+			if(tail) gc = gc < rem ? gc : rem;
+			cur.take_group(a[4] & 63u);
+			row = r[4];
+		} else {
+			g_lo = pair_step_one<ORDER>(cur, T, lut_g, walk, e[0], row, clean);
+			g_hi = 0;
+			gc = 1;
 		}
+		rem -= gc;
+		os.append(g_lo, g_hi, gc);
+		cur.top_up();
+	};
+	uint32_t it = 0;
+	// while every lane of the warp has at least a whole group (8 symbols) to go: no lane test, no cut, no end check
+	for(; __all_sync(0xffffffffu, rem >= 8u); ++it) {
+		trip(it, false);
+		if((it & (kFlushEvery - 1)) == kFlushEvery - 1) os.flush(false);
+	}
+	for(; __any_sync(0xffffffffu, rem != 0); ++it) {
+		if(rem) trip(it, true);
 		if((it & (kFlushEvery - 1)) == kFlushEvery - 1) os.flush(false);
 	}
 	os.finish();
