@@ -455,7 +455,7 @@ __device__ __forceinline__ uint32_t pair_slow_one(Cursor& cur, const PairTab& T,
 		const uint32_t x = lds_u32(T.tab + (row | ((cur.hi >> 22) & 0x3fcu)));
 		cur.take(8);
 		const uint32_t* nodes = walk + (ORDER ? ((x >> 16) & 255u) << 9 : 0u);
-		uint32_t node = (x >> 6) & 511u, sym = ' ';
+		uint32_t node = (x >> 24) | ((x & 0x40u) << 2), sym = ' ';
 		for(int guard = 0; guard < 256; ++guard) {
 			cur.top_up();
 			if((guard & 15) == 0) cur.refill_round();   // the walk tops the ring up itself
@@ -1158,6 +1158,12 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 		uint32_t wt = decode_write_threads();
 		while(wt > 128 && lut_bytes + size_t(wt) * per_thread + 1024 > size_t(max_smem_optin())) wt -= 32;
 		const uint64_t warps_needed = (n_subs + 31) / 32;
+		// a stream with few subsequences: smaller CTAs on every SM rather than full ones on some of them (the 256 MiB
+		// Fibonacci stream has 86 k subsequences: 84 CTAs of 1024 threads, or 148 of 608)
+		if(tunable(kTunDecWriteThreads) <= 0 && warps_needed < uint64_t(sms) * (wt / 32)) {
+			const uint32_t per_sm = uint32_t((warps_needed + sms - 1) / sms) * 32u;
+			wt = per_sm < 128u ? 128u : (per_sm < wt ? per_sm : wt);
+		}
 		uint64_t wgrid = (warps_needed + wt / 32 - 1) / (wt / 32);
 		if(wgrid > uint64_t(sms)) wgrid = uint64_t(sms);
 		dec_write_kernel<ORDER, PAIR><<<unsigned(wgrid), wt, lut_bytes + size_t(wt) * per_thread, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk,

@@ -507,8 +507,9 @@ uint32_t CodingTable::flatten_pairlut(uint32_t* table, uint8_t* maps, uint32_t m
 	// Prefix rows go to the heaviest depth-8 nodes first (the node weight is the number of symbols coded below it;
 	// a table loaded from a file has no weights and takes them in table order). A codeword that ends within the row's 8
 	// bits is an ordinary one-symbol entry; one that does not (17 bits and more: rare even in a Fibonacci-shaped tree,
-	// 2^-16 of the symbols) is a deep flag that names the tree node reached and the context, [14:6] and [23:16]: the
-	// decoder takes the row's 8 bits and walks on from that node. (Round 1 gave rows only to nodes whose codewords all
+	// 2^-16 of the symbols) is a deep flag that names the tree node reached ([31:24], ninth bit in [6]) and the context
+	// ([23:16]); its next-row field stays 0, so whatever the decoder looks up speculatively behind it stays inside the
+	// table. The decoder takes the row's 8 bits and walks on from that node. (Round 1 gave rows only to nodes whose codewords all
 	// end within 16 bits: a Fibonacci-shaped tree then got none, and 0.4 % of its symbols took the slow path.)
 	std::stable_sort(deep.begin(), deep.end(), [](const DeepNode& x, const DeepNode& y) { return x.weight > y.weight; });
 	for(const DeepNode& dn : deep) {
@@ -521,7 +522,7 @@ uint32_t CodingTable::flatten_pairlut(uint32_t* table, uint8_t* maps, uint32_t m
 				cur = ((w2 >> (7 - d)) & 1) ? tr.nodes[cur].right : tr.nodes[cur].left;
 				++d;
 			}
-			if(tr.nodes[cur].internal) ext[w2] = kLutDeep | (uint32_t(cur) << 6) | (uint32_t(dn.ctx) << 16);
+			if(tr.nodes[cur].internal) ext[w2] = kLutDeep | ((uint32_t(cur) >> 8) << 6) | (uint32_t(dn.ctx) << 16) | ((uint32_t(cur) & 255u) << 24);
 			else ext[w2] = uint32_t(d) | (1u << 6) | (next_of(tr.nodes[cur].symbol) << 10) | (uint32_t(tr.nodes[cur].symbol) << 16);
 		}
 		table[size_t(rank[dn.ctx]) * 256 + dn.window] = 8u | (rows << 10);   // 8 bits, no symbol yet, continue in the prefix row

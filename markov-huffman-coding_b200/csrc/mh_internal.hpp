@@ -52,7 +52,7 @@ constexpr int kEncCtxMaxBits = 29;                    // context-row entry: 5-bi
 constexpr int kEncCtxMaxRows = 96;                    // live contexts + null row; table + staging must leave room for 2 CTAs/SM
 constexpr int kEncCtxSmemLimit = 112 * 1024;          // table + staging area of one CTA
 constexpr int kDecThreads = 1024;                     // subsequences per chunk (one thread each)
-constexpr int kDecWriteMaxThreads = 768;              // D4 threads per CTA (measured best of 512..960): table + 192 B of rings per thread
+constexpr int kDecWriteMaxThreads = 1024;             // D4 threads per CTA, as many as table + 192 B of rings per thread leave room for (text: 768)
 constexpr int kDecMinSubBits = 256;
 constexpr uint32_t kDecMaxSubBitsMarkov = 8192;       // measured best of 2048..16384 on the 1 GiB Markov text
 constexpr uint32_t kDecMaxSubBitsHuffman = 8192;      // 1 GiB text with -h: D1 1.48 ms at 2048, 1.23 at 4096, 1.05 at 8192

@@ -216,6 +216,22 @@ def test_warp_private_encoder_agrees(session, ipsum_counts, tunables):
         assert session.compress_with_table(provider, holes) == want_holes
 
 
+@pytest.mark.parametrize("threads", ["64", "128", "256"])
+def test_small_write_ctas_keep_speculative_lookups_inside_the_table(session, threads, tunables):
+    """D4 sizes its CTAs by the number of subsequences (small streams: small CTAs on every SM). With little shared
+    memory behind the pair table a speculative lookup behind a flagged prefix-row entry must not leave the table: such
+    entries keep their next-row field 0 (a -h table of HTML has them: 18-bit codewords)."""
+    tunables("dec_write_threads", threads)
+    data = golden_input("input_wiki_cpp.html")
+    for order in (0, 1):
+        stream, provider = session.compress(data, order)
+        assert session.decompress(provider, stream) == data
+    fib = o.synth_fibonacci(40, 48, 11, 0, (1 << 20) + 7)
+    for order in (0, 1):
+        stream, provider = session.compress(fib, order)
+        assert session.decompress(provider, stream) == fib
+
+
 @pytest.mark.parametrize("pair", ["1", "0"], ids=["pair-table", "lut8"])
 @pytest.mark.parametrize("sub_bits", ["256", "1024", "8192"])
 def test_decoder_subsequence_sizes_agree(ipsum_counts, sub_bits, pair, tunables):

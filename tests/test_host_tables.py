@@ -252,7 +252,7 @@ def test_pair_table_entry_kinds_follow_the_8bit_lut():
 def test_pair_table_prefix_rows_of_a_fibonacci_tree():
     """A Fibonacci-shaped tree (codewords up to ~30 bits): its depth-8 node gets a prefix row although not every codeword
     below it ends within 16 bits — those that do are one-symbol entries, the others deep flags naming the tree node reached
-    and the context ([14:6], [23:16]) — and a stream of <= 16-bit codewords decodes through the table without a flag."""
+    and the context ([31:24] + bit 6, [23:16]; the next-row field stays 0: speculative lookups behind a flag stay in the table) — and a stream of <= 16-bit codewords decodes through the table without a flag."""
     fib = np.zeros(256, dtype=np.uint64)
     a, b = 1, 1
     for i in range(32):
@@ -270,7 +270,7 @@ def test_pair_table_prefix_rows_of_a_fibonacci_tree():
         e = int(t[2, w])
         if e & 0x10:
             flags += 1
-            assert ((e >> 6) & 511) < 2 * 32 - 1 and ((e >> 16) & 255) == 0 and not (e & 0x20)
+            assert ((e >> 24) | ((e & 0x40) << 2)) < 2 * 32 - 1 and ((e >> 16) & 255) == 0 and not (e & 0x20) and ((e >> 10) & 63) == 0
         else:
             singles += 1
             assert ((e >> 6) & 15) == 1 and 1 <= (e & 15) <= 8 and ((e >> 10) & 63) == 0 and 65 <= ((e >> 16) & 255) < 97
