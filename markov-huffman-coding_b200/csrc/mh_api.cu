@@ -499,6 +499,7 @@ int mh_workspace_create(uint64_t max_input_bytes, uint64_t max_payload_bytes, mh
 	WS_CUDA(cudaMalloc(&ws->enc_desc, ws->enc_tiles_cap * (2 * sizeof(uint64_t) + sizeof(uint32_t)) + 4096));   // 20 bytes per tile cover either kernel's descriptors (K2w: 16 per tile + 136 per 64 tiles)
 	ws->dec_subs_cap = decode_max_subs(max_payload_bytes);
 	ws->dec_chunks_cap = ws->dec_subs_cap / (kDecThreads - kDecWarmSubs) + 2;
+	if(ws->dec_chunks_cap < 1024) ws->dec_chunks_cap = 1024;   // short streams are cut into one chunk per SM
 	WS_CUDA(cudaMalloc(&ws->dec_state, ws->dec_subs_cap * sizeof(uint32_t)));
 	WS_CUDA(cudaMalloc(&ws->dec_count, ws->dec_subs_cap * sizeof(uint32_t)));
 	WS_CUDA(cudaMalloc(&ws->dec_prefix, ws->dec_subs_cap * sizeof(uint32_t)));

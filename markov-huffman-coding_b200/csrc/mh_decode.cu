@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 	__shared__ uint16_t cp_state[kCp][kDecThreads];   // [checkpoint][slot]: conflict-free across a warp
 	__shared__ uint16_t cp_count[kCp][kDecThreads];
 	const uint32_t tid = threadIdx.x;
-	const uint32_t chunk_subs = kDecThreads - warm;
+	const uint32_t chunk_subs = blockDim.x - warm;   // launched with up to kDecThreads threads (fewer for streams with few subsequences)
 	const uint32_t unit = sub_bits / 32;
 	PairTab T = {};
 	if(PAIR) {
@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) dec_sync_kernel(
 		const uint32_t n16 = ORDER ? 65536u : 256u;
 		const uint4* src = reinterpret_cast<const uint4*>(lut_g);
 		uint4* dst = reinterpret_cast<uint4*>(lut_s);
-		for(uint32_t i = tid; i < n16 / 8; i += kDecThreads) dst[i] = src[i];
+		for(uint32_t i = tid; i < n16 / 8; i += blockDim.x) dst[i] = src[i];
 	}
 	__syncthreads();
 	uint32_t lut_sa;
@@ -1102,7 +1102,15 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	// the next chunk re-decodes the last `warm` subsequences (>= 8192 bits) of this one as warm-up
 	uint32_t warm = 8192 / sub_bits;
 	warm = warm < 1 ? 1 : (warm > uint32_t(kDecWarmSubs) ? uint32_t(kDecWarmSubs) : warm);
-	const uint32_t chunk_subs = kDecThreads - warm;
+	const int sms = sm_count();
+	// D1 threads per CTA = subsequences per chunk + warm-up: kDecThreads, or fewer when that would leave SMs without a chunk
+	// (the 256 MiB Fibonacci stream has 86 k subsequences: 85 chunks of 1016, or 148 of 580)
+	uint32_t d1_threads = uint32_t(kDecThreads);
+	if((n_subs + (kDecThreads - warm) - 1) / (kDecThreads - warm) < uint64_t(sms)) {
+		const uint64_t per = ((n_subs + sms - 1) / sms + warm + 31) & ~uint64_t(31);
+		d1_threads = uint32_t(per < 256 ? 256 : (per > uint64_t(kDecThreads) ? uint64_t(kDecThreads) : per));
+	}
+	const uint32_t chunk_subs = d1_threads - warm;
 	const uint64_t chunks64 = (n_subs + chunk_subs - 1) / chunk_subs;
 	if(n_subs > ws->dec_subs_cap || chunks64 > ws->dec_chunks_cap) return MH_ERR_WORKSPACE;
 	const uint32_t n_chunks = uint32_t(chunks64);
@@ -1114,7 +1122,6 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 		MH_CUDA(cudaFuncSetAttribute(dec_write_kernel<ORDER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		                             PAIR ? max_smem_optin() - 1024 : int(lut_bytes) + ring_bytes));   // pair path: the launcher fits the thread count
 	}
-	const int sms = sm_count();
 	// Checkpoints inside a subsequence, in 1/32 of its length. A walker that took over its successor's subsequence stops
 	// at the first checkpoint where its state equals the recorded one: dense near the start, where re-synchronisation
 	// usually happens (1, 2, 4, 8, 12, 16, 24, 32: -8 % on D1 with -h, where streams re-synchronise within tens of bits;
@@ -1125,7 +1132,7 @@ int run_decode(const uint32_t* words, uint64_t n_bits, uint64_t buf_bytes, uint3
 	MH_CUDA(cudaMemsetAsync(ws->counters + 4, 0, sizeof(unsigned long long), st));   // D4's work ticket
 	{
 		ProfScope p("dec_sync_kernel", st);
-		dec_sync_kernel<ORDER, PAIR><<<grid, kDecThreads, lut_bytes + size_t(kDecThreads) * kRingBytesPerThread, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, dt->d_pair,
+		dec_sync_kernel<ORDER, PAIR><<<grid, d1_threads, lut_bytes + size_t(d1_threads) * kRingBytesPerThread, st>>>(words, n_bits, buf_bytes, start0, dt->d_lut, dt->d_walk, dt->d_pair,
 		    dt->pair_rows, dt->pair_ctx_rows, ws->dec_state, ws->dec_count, ws->dec_seam, sub_bits, n_subs, n_chunks, warm, uint32_t(lut_bytes), cp_tab);
 	}
 	count_launch(1);
