@@ -321,7 +321,7 @@ def phases_and_roofline(prof, n, c_bytes, name):
     kern = {k: v["ms"] / max(1, v["launches"]) for k, v in prof.items()}
     per_step = {k: v["ms"] for k, v in prof.items()}
     algo = {"hist_lane_kernel": n, "hist0_lane_kernel": n, "encode_kernel": n + c_bytes, "dec_sync_kernel": c_bytes,
-            "dec_write_kernel": c_bytes + n, "dec_fused_kernel": c_bytes + n}
+            "dec_write_kernel": c_bytes + n}
     phase = {
         "histogram": {"algorithmic_bytes": n, "ms": sum(v for k, v in kern.items() if k.startswith("hist"))},
         "encode": {"algorithmic_bytes": n + c_bytes, "ms": sum(v for k, v in kern.items() if k.startswith("encode"))},

@@ -103,7 +103,6 @@ const TunableDef kTunables[kTunCount] = {
     {"pipe_min_bytes", "MH_PIPE_MIN_BYTES"},
     {"pipe_chunk_bytes", "MH_PIPE_CHUNK_BYTES"},
     {"enc_pipe_chunk_bytes", "MH_ENC_PIPE_CHUNK_BYTES"},
-    {"dec_fused", "MH_DEC_FUSED"},
     {"enc_tma", "MH_ENC_TMA"},
     {"dec_cp_geo", "MH_DEC_CP_GEO"},
     {"enc_warp", "MH_ENC_WARP"},
