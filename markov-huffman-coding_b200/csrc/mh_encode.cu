@@ -137,6 +137,7 @@ struct EncArgs {
 	uint32_t* ticket;
 	unsigned long long* result;
 	uint32_t n_tiles;
+	uint32_t full_tiles;   // tiles that are complete (n / tile bytes): computed on the host — in the kernel the 64-bit division was redone every tile
 };
 
 // Warp-wide decoupled look-back over a window of kWin x 32 predecessors per poll (one warp-load measured best). All 32 lanes of warp 0 call this.
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	// input tile buffer (TMA): behind the staging area, 16-byte aligned; tiles that are complete travel by bulk copy
 	const uint32_t inbuf_sa = (stage_sa + (stage_words + 4u) * 4u + 15u) & ~15u;
 	const uint32_t mbar_sa = uint32_t(__cvta_generic_to_shared(&s_mbar));
-	const uint32_t full_tiles = uint32_t(A.n / kTileBytes);
+	const uint32_t full_tiles = A.full_tiles;
 	auto issue_tile = [&](uint32_t tile) {   // one thread: the tile's bytes and the 16 before them (its first context)
 		if(tile >= full_tiles) return;
 		const uint64_t at = uint64_t(tile) * kTileBytes;
@@ -644,11 +645,13 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				uint32_t j = tid + (s ? 1u : 0u);
 				uint32_t* dp = A.out_words + w0 + j;
 				const uint32_t* sp = stage + j;
+#pragma unroll 1
 				for(; j < nw; j += kEncThreads, dp += kEncThreads, sp += kEncThreads)
 					*dp = __byte_perm(__funnelshift_r(sp[0], sp[-1], s), 0, 0x0123);   // sp[-1] of word 0 is the zero word in front
 			}
 			bar_workers();
 			const uint32_t used4 = ((p_bits + 31) / 32 + 1 + 3) / 4;   // 16 bytes per store; the staging area has the slack
+#pragma unroll 1   // one trip for text (a tile stages ~400 such stores): unrolled, the trip-count arithmetic cost more than the stores
 			for(uint32_t j = tid; j < used4; j += kEncThreads) reinterpret_cast<uint4*>(stage)[j] = make_uint4(0, 0, 0, 0);
 			bar_workers();   // the staging area is clean before the next tile is packed into it
 			pending = false;
@@ -816,7 +819,7 @@ __global__ void __launch_bounds__(kEncWarpThreads, 1) encode_warp_kernel(const E
 	const uint32_t stage_sa = uint32_t(__cvta_generic_to_shared(stage));
 	const uint32_t inbuf_sa = table_sa + (table_words + per_warp * NW) * 4u + warp * (kWarpTileBytes + kEncInbufLead);
 	const uint32_t mbar_sa = uint32_t(__cvta_generic_to_shared(&s_mbar[warp]));
-	const uint32_t full_tiles = uint32_t(A.n / kWarpTileBytes);
+	const uint32_t full_tiles = A.full_tiles;
 	if(TMA && lane == 0) {
 		mbar_init(mbar_sa, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1209,6 +1212,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.ticket = ws->counters;
 	a.result = d_result;
 	a.n_tiles = uint32_t(tiles);
+	a.full_tiles = uint32_t(n / tile_bytes);
 	const bool aligned = (reinterpret_cast<uint64_t>(d_in) & 15) == 0;
 	size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 8) * sizeof(uint32_t);
 	// Context rows + aligned input: whole tiles travel into shared memory by bulk copy (TMA), one tile ahead, when the
@@ -1230,6 +1234,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 		a.grp_acc = a.grp_inc + ((wgroups + 15) & ~uint64_t(15));   // one accumulator per 128-byte line: 64 additions each, and the scan warp polls them
 		a.tail = nullptr;
 		a.n_tiles = uint32_t(wtiles);
+		a.full_tiles = uint32_t(n / kWarpTileBytes);
 		a.stage_words = warp_stage_words(uint32_t(maxb));
 		const bool wtma = aligned && tunable(kTunEncTma) != 0;
 		const size_t room = size_t(max_smem_optin()) - 2048;   // one CTA per SM (the kernel's static shared memory is ~1.2 KiB): the device-built path takes all of it
@@ -1254,6 +1259,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 		a.inc = a.agg + tiles;
 		a.tail = reinterpret_cast<uint32_t*>(a.inc + tiles);
 		a.n_tiles = uint32_t(tiles);
+		a.full_tiles = uint32_t(n / tile_bytes);
 		a.stage_words = stage_words;
 		MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, tiles * (2 * sizeof(uint64_t) + sizeof(uint32_t)), st));
 	}
