@@ -391,33 +391,44 @@ def run_single(args, name, steps, dev, mh, want_e2e, want_cpu):
         ev[1].record()
         ev_counts.synchronize()
         th0 = time.perf_counter()
-        provider = mh.CodingProvider.from_counts_array(h_counts.numpy().view(np.uint64)[:bins], order)
+        counts_u64 = h_counts.numpy().view(np.uint64)[:bins]
+        provider = mh.CodingProvider.from_counts_array(counts_u64, order)
         th1 = time.perf_counter()
         if state["dectab"] is None:
             state["dectab"] = mh.DecodeTable(provider)
         th3 = time.perf_counter()
         state["dectab"].update(provider, stream)     # flattened on the host while the encoder runs
         th4 = time.perf_counter()
-        main.synchronize()
-        if int(h_res[3]) != 0:                       # the device-built tables did not fit the encoder's launch: host-built tables
-            state["fallbacks"] += 1
-            if state.get("host_book") is None:
-                state["host_book"] = mh.Codebook(provider)
-            state["host_book"].update(provider, stream)
-            mh.gpu_encode(d_in.data_ptr(), n, 0x20, state["host_book"], 0, d_payload.data_ptr(), payload_cap, d_res.data_ptr(), ws, stream)
-            h_res[:4].copy_(d_res[:4], non_blocking=True)
-            main.synchronize()
-        bits = int(h_res[0])
-        assert int(h_res[2]) == 0, "encode: capacity"
+        # The payload's size is known before the encoder ends: sum of count x code length (the same arithmetic
+        # that places the shards of a multi-GPU compress). The decoder is queued right behind the encoder - no host wait
+        # between the two; the encoder's own bit count is compared with the prediction after the step.
+        bits = int(np.dot(counts_u64, provider.code_lengths()))
         mh.gpu_decode(d_payload.data_ptr(), 0, bits, 0x20, state["dectab"], d_out.data_ptr(), n, d_res[4:].data_ptr(), ws, stream)
         h_res[4:].copy_(d_res[4:], non_blocking=True)
         ev[2].record()
         main.synchronize()
+        t_a, t_b = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        if int(h_res[3]) != 0:                       # the device-built tables did not fit the encoder's launch: host-built tables
+            state["fallbacks"] += 1
+            if state.get("host_book") is None:
+                state["host_book"] = mh.Codebook(provider)
+            ev[0].record()
+            state["host_book"].update(provider, stream)
+            mh.gpu_encode(d_in.data_ptr(), n, 0x20, state["host_book"], 0, d_payload.data_ptr(), payload_cap, d_res.data_ptr(), ws, stream)
+            h_res[:4].copy_(d_res[:4], non_blocking=True)
+            ev[1].record()
+            mh.gpu_decode(d_payload.data_ptr(), 0, bits, 0x20, state["dectab"], d_out.data_ptr(), n, d_res[4:].data_ptr(), ws, stream)
+            h_res[4:].copy_(d_res[4:], non_blocking=True)
+            ev[2].record()
+            main.synchronize()
+            t_a, t_b = t_a + ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        assert int(h_res[0]) == bits, "encoder wrote %d bits, sum of count x length is %d" % (int(h_res[0]), bits)
+        assert int(h_res[2]) == 0, "encode: capacity"
         assert int(h_res[4]) == n and int(h_res[5]) == 0 and int(h_res[6]) == 0, "decode: %s" % h_res[4:].tolist()
         if timed:   # host work that overlaps the encoder (off the critical path unless it outlasts it)
             host_us["trees"] += (th1 - th0) * 1e6; host_us["dectable"] += (th4 - th3) * 1e6
         state["bits"], state["provider"] = bits, provider
-        return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        return t_a, t_b
 
     for _ in range(args.warmup):
         step(False)
