@@ -106,6 +106,7 @@ const TunableDef kTunables[kTunCount] = {
     {"enc_tma", "MH_ENC_TMA"},
     {"dec_cp_geo", "MH_DEC_CP_GEO"},
     {"enc_warp", "MH_ENC_WARP"},
+    {"enc_spt", "MH_ENC_SPT"},
 };
 std::atomic<long long> g_tunables[kTunCount];
 struct TunableInit {

@@ -138,6 +138,9 @@ struct EncArgs {
 	unsigned long long* result;
 	uint32_t n_tiles;
 	uint32_t full_tiles;   // tiles that are complete (n / tile bytes): computed on the host — in the kernel the 64-bit division was redone every tile
+	uint32_t* fail;                           // SPT = 64 (optimistic launch): raised when the launch declines the tables or a tile's bits do not fit its staging area
+	const uint32_t* gate;                     // launched behind the SPT = 64 variant: run only if *gate != 0, else hand its results over and leave
+	const unsigned long long* alt_result;     // ... the results of the SPT = 64 launch (bits, dropped symbols, capacity error)
 };
 
 // Warp-wide decoupled look-back over a window of kWin x 32 predecessors per poll (one warp-load measured best). All 32 lanes of warp 0 call this.
@@ -318,6 +321,30 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 	const uint32_t bit0 = A.bit_base_dev ? uint32_t(__ldg(A.bit_base_dev) & 7ull) : A.bit0;
 	const uint32_t first_prev = A.prev0_dev ? uint32_t(__ldg(A.prev0_dev) & 255ull) : A.prev0;
 	uint32_t ctx_rows = A.ctx_rows, stage_words = A.stage_words;
+	if(A.gate && ld_relaxed32(A.gate) == 0) {   // the optimistic launch before this one did the work: its results are the call's results
+		if(blockIdx.x == 0 && tid < 3) A.result[tid] = A.alt_result[tid];
+		return;
+	}
+	if constexpr(SPT == 64) {
+		// The optimistic variant (device-built tables only): 64 symbols per thread halve what a tile costs outside the lookups
+		// and the packing (block scan, barriers, tickets, copy-out set-up: a third of the instructions at 32 symbols per thread).
+		// Its staging area is what the launch's shared memory leaves next to the table and the 30 KiB input tile — not the
+		// worst case of 64 x 480 longest codewords — so it declines tables it is not made for (mean codeword above 5.5 bits:
+		// quads longer than 32 bits become common and they take the slow escape path; a staging area below 8 bits per symbol)
+		// and raises *fail when a tile's bits do not fit after all; the SPT = 32 launch queued behind it then does the work.
+		ctx_rows = __ldg(A.meta);
+		const uint32_t status = __ldg(A.meta + 1), longest = __ldg(A.meta + 2);
+		const unsigned long long sum_bits = __ldg(reinterpret_cast<const unsigned long long*>(A.meta + 4)), sum_count = __ldg(reinterpret_cast<const unsigned long long*>(A.meta + 6));
+		const uint32_t worst = (kEncThreads * 2u * (longest ? longest : 1u) + 7u) & ~3u;
+		const uint32_t fixed = ((ctx_table_bytes(ctx_rows, ORDER) + 15u) & ~15u) + kTileBytes + kEncInbufLead + 16u + 8u * 4u;
+		const uint32_t room = A.smem_bytes > fixed ? ((A.smem_bytes - fixed) / 4u) & ~3u : 0u;
+		stage_words = worst < room ? worst : room;
+		if(status != 0 || ctx_rows > uint32_t(kEncCtxMaxRows) || longest > A.launched_bits || (stage_words < worst && stage_words < kEncThreads * 16u + 8u) ||
+		   sum_bits * 2ull > sum_count * 11ull) {
+			if(blockIdx.x == 0 && tid == 0) *A.fail = 1u;
+			return;
+		}
+	} else
 	if(FMT == FMT_CTX && A.meta) {   // device-built tables: check that this launch's shared memory and tile size fit them
 		ctx_rows = __ldg(A.meta);
 		const uint32_t status = __ldg(A.meta + 1), longest = __ldg(A.meta + 2);
@@ -443,9 +470,130 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 		uint32_t tile_bits = 0, pos = 0;
 		uint32_t e32[(FMT == FMT_BOX_SMEM || FMT == FMT_BOX_GLOBAL) ? SPT : 1];
 		unsigned long long e64[FMT == FMT_WIDE ? SPT : 1];
-		uint32_t q_hi[FMT == FMT_CTX ? SPT / 4 : 1], q_lo[FMT == FMT_CTX ? SPT / 4 : 1], q_len[FMT == FMT_CTX ? SPT / 4 : 1];
+		uint32_t q_hi[FMT == FMT_CTX && SPT != 64 ? SPT / 4 : 1], q_lo[FMT == FMT_CTX ? SPT / 4 : 1], q_len[FMT == FMT_CTX && SPT != 64 ? SPT / 4 : 1];
+		uint32_t qlen4[SPT == 64 ? 4 : 1];   // SPT = 64: the quads' lengths, four to a word (a quad longer than 32 bits is escaped, so there is no q_hi)
 		uint32_t esc_mask = 0;   // FMT_CTX: quads of this thread that hold a codeword longer than 16 bits
+		bool overflow = false;   // SPT = 64: this tile's bits do not fit the staging area (the launch fails over to SPT = 32)
 		if(valid) {
+			uint32_t my_bits = 0;
+			if constexpr(SPT == 64) {
+				// The tile is in the input buffer (bulk copy; the stream's ragged last tile is put there by the workers, zero
+				// padded): 4 x 16 bytes per thread from shared memory, one chunk at a time (registers).
+				const bool from_smem = tile < full_tiles;
+				const uint32_t my_sa = inbuf_sa + kEncInbufLead + tid * 64u;
+				int live = 0;
+				uint32_t prev = first_prev;
+				if(from_smem) {
+					mbar_wait(mbar_sa, in_parity);
+					in_parity ^= 1u;
+					live = 64;
+					if(my) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(prev) : "r"(my_sa - 1u) : "memory");
+				} else if(my < A.n) {
+					live = A.n - my >= 64ull ? 64 : int(A.n - my);
+#pragma unroll 1
+					for(int k = 0; k < 16; ++k) {
+						uint32_t x = 0;
+#pragma unroll
+						for(int b = 0; b < 4; ++b)
+							if(4 * k + b < live) x |= uint32_t(A.in[my + 4 * k + b]) << (8 * b);
+						asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_sa + 4u * k), "r"(x) : "memory");
+					}
+					if(my) prev = uint32_t(A.in[my - 1]);
+				}
+				const uint32_t rank_sa = uint32_t(__cvta_generic_to_shared(s_rank));
+				auto row_of = [&](uint32_t byte) -> uint32_t {
+					uint32_t r;
+					asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_sa + byte));
+					return table_sa + r * kCtxPitch;
+				};
+				uint32_t row = table_sa + lane * 4;
+				if(ORDER) row = row_of(prev);
+				uint32_t floor = 0xffffffffu, ceil = 0;
+				auto quads64 = [&](bool checked) {
+					uint32_t lastc = prev;   // the byte before the quad: every quad restarts its lookup chain from that byte's row
+#pragma unroll
+					for(int h = 0; h < 4; ++h) {
+						const uint4 v = lds128(my_sa + 16u * h);
+						const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+						uint32_t packed = 0;
+#pragma unroll
+						for(int k = 0; k < 4; ++k) {
+							const int q = 4 * h + k;
+							if(ORDER && q) row = row_of(lastc);
+							uint32_t e[4];
+#pragma unroll
+							for(int j = 0; j < 4; ++j) {
+								const uint32_t c = __byte_perm(w4[k], 0, 0x4440 + j);
+								uint32_t ent = 0;
+								if(!checked || 4 * q + j < live) {
+									ent = ORDER ? lds32(row + c * 4) : lds32(row + c * 128);
+									if(ORDER) row = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
+									floor = min(floor, ent);
+									ceil = max(ceil, ent);
+								}
+								e[j] = ent;
+							}
+							const uint32_t l1 = e[1] >> 27, l3 = e[3] >> 27;
+							const uint32_t lp0 = (e[0] >> 27) + l1, lp1 = (e[2] >> 27) + l3;
+							const uint32_t p0 = ((e[0] & 0xffffu) << l1) | (e[1] & 0xffffu);
+							const uint32_t p1 = ((e[2] & 0xffffu) << l3) | (e[3] & 0xffffu);
+							uint32_t lo;
+							asm("shl.b32 %0, %1, %2;" : "=r"(lo) : "r"(p0), "r"(lp1));   // lp1 may be 32
+							q_lo[q] = lo | p1;
+							packed |= (lp0 + lp1) << (8 * k);
+							my_bits += lp0 + lp1;
+							lastc = w4[k] >> 24;
+						}
+						qlen4[h] = packed;
+					}
+				};
+				if(live == 64) quads64(false);
+				else quads64(true);
+				// Rare: a quad longer than 32 bits (its low word alone is not the quad), or a codeword longer than 16 bits somewhere
+				// in this thread (length marker 31; only a quad whose merged length reaches 31 can hold one): those quads take
+				// their lengths from the wide table and are packed symbol by symbol below.
+				uint32_t longq = 0;
+#pragma unroll
+				for(int h = 0; h < 4; ++h) longq |= (qlen4[h] + 0x5f5f5f5fu) & 0x80808080u;   // some quad of 33 bits or more (a length is at most 4 x 31)
+				if((ceil >> 27) == 31u || longq) {
+#pragma unroll
+					for(int q = 0; q < 16; ++q) {
+						const uint32_t len = (qlen4[q >> 2] >> (8 * (q & 3))) & 255u;
+						if(len >= 31u) {
+							uint32_t wq;   // the quad's bytes are still in the input buffer (a volatile load: lds32 is a pure function of its address to the compiler, right for the table, wrong for a buffer that is refilled every tile)
+							asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wq) : "r"(my_sa + 4u * q) : "memory");
+							uint32_t p = prev, sum = 0;
+							if(q) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(p) : "r"(my_sa + 4u * q - 1u) : "memory");
+							bool big = false;
+#pragma unroll
+							for(int i = 0; i < 4; ++i) {
+								if(4 * q + i < live) {
+									const uint32_t c = __byte_perm(wq, 0, 0x4440 + i);
+									const uint32_t l = uint32_t(__ldg(A.wide + ((ORDER ? p : 0u) << 8) + c) >> 56);
+									big |= l > 16u;
+									sum += l;
+									p = c;
+								}
+							}
+							if(big || len > 32u) {
+								esc_mask |= 1u << q;
+								my_bits += sum - len;
+							}
+						}
+					}
+				}
+				if(floor < (1u << 27)) {   // rare: some symbol has no codeword; count them exactly (context rows again)
+					uint32_t r2 = table_sa + lane * 4;
+					if(ORDER) r2 = row_of(prev);
+#pragma unroll 1
+					for(int i = 0; i < live; ++i) {
+						const uint32_t c = A.in[my + i];
+						const uint32_t ent = ORDER ? lds32(r2 + c * 4) : lds32(r2 + c * 128);
+						if(ORDER) r2 = table_sa + __byte_perm(ent, 0, 0x4442) * kCtxPitch;
+						dropped += (ent >> 27) == 0 ? 1u : 0u;
+					}
+				}
+			} else {
 			uint32_t w[NWORDS];
 #pragma unroll
 			for(int k = 0; k < NWORDS; ++k) w[k] = 0;
@@ -480,7 +628,6 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 				else if(TMA && tile < full_tiles) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(prev) : "r"(inbuf_sa + kEncInbufLead + tid * SPT - 1u) : "memory");
 				else prev = uint32_t(A.in[my - 1]);
 			}
-			uint32_t my_bits = 0;
 			if constexpr(FMT == FMT_CTX) {
 				// One shared-memory lookup per symbol; the entry names the next context's row, so inside a quad the
 				// dependent chain is lookup -> byte select -> multiply-add -> lookup. Every quad restarts the chain from
@@ -605,8 +752,13 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 					prev = c;
 				}
 			}
+			}   // SPT != 64
 			// block exclusive scan; the tile's bit count is published right away
 			pos = block_exclusive_scan(my_bits, warp_sums, tile_bits);
+			if constexpr(SPT == 64) {
+				overflow = tile_bits > (stage_words - 7u) * 32u;
+				if(overflow && tid == 0) *A.fail = 1u;   // this launch's output is void: the SPT = 32 launch behind it encodes the stream again
+			}
 			if(tid == 0) {
 				st_relaxed(A.agg + tile, kAgg | tile_bits);
 				s_pub_tile[it & 1] = tile;
@@ -659,14 +811,36 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 
 		// ================= phase C: pack tile `tile` into the staging area =================
 		if(valid) {
-			if constexpr(FMT == FMT_CTX) {
+			if constexpr(SPT == 64) {
+				if(!overflow) {
+					Packer32 pk;
+					pk.start(stage_sa, pos);
+#pragma unroll
+					for(int q = 0; q < 16; ++q) {
+						if(esc_mask & (1u << q)) {   // rare: a quad longer than 32 bits or with a codeword of 17..29 bits: one unit per symbol, from the wide table
+							const uint64_t at = my + 4 * q;
+							uint32_t p = at == 0 ? first_prev : uint32_t(A.in[at - 1]);
+#pragma unroll 1
+							for(int i = 0; i < 4 && at + i < A.n; ++i) {
+								const uint32_t c = A.in[at + i];
+								const unsigned long long ent = __ldg(A.wide + ((ORDER ? p : 0u) << 8) + c);
+								pk.put(uint32_t(ent), uint32_t(ent >> 56));
+								p = c;
+							}
+						} else {
+							pk.put(q_lo[q], (qlen4[q >> 2] >> (8 * (q & 3))) & 255u);
+						}
+					}
+					pk.finish();
+				}
+			} else if constexpr(FMT == FMT_CTX) {
 				Packer32 pk;
 				pk.start(stage_sa, pos);
 #pragma unroll
 				for(int q = 0; q < SPT / 4; ++q) {
 					if(esc_mask & (1u << q)) {   // rare: the quad holds a codeword of 17..28 bits: one unit per symbol, from the wide table
 						const uint64_t at = my + 4 * q;
-						uint32_t p = at == 0 ? A.prev0 : uint32_t(A.in[at - 1]);
+						uint32_t p = at == 0 ? first_prev : uint32_t(A.in[at - 1]);
 #pragma unroll 1
 						for(int i = 0; i < 4 && at + i < A.n; ++i) {
 							const uint32_t c = A.in[at + i];
@@ -709,12 +883,12 @@ __global__ void __launch_bounds__(kEncCtaThreads, FMT == FMT_CTX ? 2 : 1) encode
 			bar_workers();   // staged bits visible
 			if(tid == 0) {     // the tail goes out now: successors need it only when they write their first word
 				const uint32_t tcount = tile_bits < 31 ? tile_bits : 31;
-				st_relaxed32(A.tail + tile, kTailValid | stage_bits(stage, tile_bits - tcount, tcount));
+				st_relaxed32(A.tail + tile, kTailValid | (overflow ? 0u : stage_bits(stage, tile_bits - tcount, tcount)));
 				s_head[it & 1] = stage[0];   // for the scanner: the bits that share an output word with the predecessor
 			}
 			pending = true;
 			p_tile = tile;
-			p_bits = tile_bits;
+			p_bits = overflow ? 0u : tile_bits;   // (a tile that did not fit was not packed: nothing to copy out)
 		}
 	}
 	dropped = uint32_t(warp_sum(dropped));
@@ -1127,9 +1301,8 @@ __global__ void __launch_bounds__(kEncWarpThreads, 1) encode_warp_kernel(const E
 	if(lane == 0 && dropped) atomicAdd(A.result + 1, (unsigned long long) dropped);
 }
 
-template <int SPT, int FMT, int ORDER = 1, bool TMA = false>
-int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStream_t st) {
-	auto kern = aligned ? encode_kernel<SPT, FMT, true, ORDER, TMA> : encode_kernel<SPT, FMT, false, ORDER, false>;
+template <typename K>
+int launch_kernel(K kern, const EncArgs& args, size_t smem_bytes, cudaStream_t st, const char* prof_name) {
 	MH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes)));
 	int per_sm = 0;
 	MH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kEncCtaThreads, smem_bytes));
@@ -1137,12 +1310,18 @@ int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStr
 	uint64_t grid = uint64_t(sm_count()) * per_sm;
 	if(grid > args.n_tiles) grid = args.n_tiles;
 	{
-		ProfScope p("encode_kernel", st);
+		ProfScope p(prof_name, st);
 		kern<<<unsigned(grid), kEncCtaThreads, smem_bytes, st>>>(args);
 	}
 	count_launch(1);
 	MH_CUDA(cudaGetLastError());
 	return MH_OK;
+}
+
+template <int SPT, int FMT, int ORDER = 1, bool TMA = false>
+int launch_variant(bool aligned, const EncArgs& args, size_t smem_bytes, cudaStream_t st, const char* prof_name = "encode_kernel") {
+	auto kern = aligned ? encode_kernel<SPT, FMT, true, ORDER, TMA> : encode_kernel<SPT, FMT, false, ORDER, false>;
+	return launch_kernel(kern, args, smem_bytes, st, prof_name);
 }
 
 }  // namespace
@@ -1213,6 +1392,7 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 	a.result = d_result;
 	a.n_tiles = uint32_t(tiles);
 	a.full_tiles = uint32_t(n / tile_bytes);
+	a.fail = nullptr; a.gate = nullptr; a.alt_result = nullptr;
 	const bool aligned = (reinterpret_cast<uint64_t>(d_in) & 15) == 0;
 	size_t smem = ((table_bytes + 15) & ~size_t(15)) + (size_t(stage_words) + 8) * sizeof(uint32_t);
 	// Context rows + aligned input: whole tiles travel into shared memory by bulk copy (TMA), one tile ahead, when the
@@ -1263,7 +1443,32 @@ int launch_encode(const uint8_t* d_in, uint64_t n, uint8_t prev0, const mh_codeb
 		a.stage_words = stage_words;
 		MH_CUDA(cudaMemsetAsync(ws->enc_desc, 0, tiles * (2 * sizeof(uint64_t) + sizeof(uint32_t)), st));
 	}
-	if(fmt == FMT_CTX && tma) return cb->order ? launch_variant<32, FMT_CTX, 1, true>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0, true>(aligned, a, smem, st);
+	const char* name32 = "encode_kernel";
+	if(dev && fmt == FMT_CTX && tma && tunable(kTunEncSpt) != 32) {
+		// Device-built tables: the optimistic 64-symbols-per-thread launch first (its own descriptors, ticket and result
+		// words), then the ordinary launch, which leaves at once unless the first one declined the tables or failed.
+		const uint64_t tile64 = uint64_t(kEncThreads) * 64, tiles64 = (n + tile64 - 1) / tile64;
+		uint8_t* base64 = reinterpret_cast<uint8_t*>(ws->enc_desc) + ((tiles * (2 * sizeof(uint64_t) + sizeof(uint32_t)) + 15) & ~uint64_t(15));
+		MH_CUDA(cudaMemsetAsync(base64, 0, tiles64 * (2 * sizeof(uint64_t) + sizeof(uint32_t)), st));
+		MH_CUDA(cudaMemsetAsync(ws->counters + 2, 0, 2 * sizeof(uint32_t), st));            // the second launch's ticket, the fail flag
+		MH_CUDA(cudaMemsetAsync(ws->counters + 8, 0, 4 * sizeof(unsigned long long), st));   // the first launch's result words
+		EncArgs b = a;
+		b.agg = reinterpret_cast<unsigned long long*>(base64);
+		b.inc = b.agg + tiles64;
+		b.tail = reinterpret_cast<uint32_t*>(b.inc + tiles64);
+		b.result = reinterpret_cast<unsigned long long*>(ws->counters + 8);
+		b.n_tiles = uint32_t(tiles64);
+		b.full_tiles = uint32_t(n / tile64);
+		b.fail = ws->counters + 3;
+		const int rc = cb->order ? launch_kernel(encode_kernel<64, FMT_CTX, true, 1, true>, b, smem, st, "encode_kernel")
+		                         : launch_kernel(encode_kernel<64, FMT_CTX, true, 0, true>, b, smem, st, "encode_kernel");
+		if(rc != MH_OK) return rc;
+		a.ticket = ws->counters + 2;
+		a.gate = ws->counters + 3;
+		a.alt_result = b.result;
+		name32 = "encode_tail_kernel";
+	}
+	if(fmt == FMT_CTX && tma) return cb->order ? launch_variant<32, FMT_CTX, 1, true>(aligned, a, smem, st, name32) : launch_variant<32, FMT_CTX, 0, true>(aligned, a, smem, st, name32);
 	if(fmt == FMT_CTX) return cb->order ? launch_variant<32, FMT_CTX, 1>(aligned, a, smem, st) : launch_variant<32, FMT_CTX, 0>(aligned, a, smem, st);
 	if(fmt == FMT_WIDE) return launch_variant<16, FMT_WIDE>(aligned, a, smem, st);
 	if(fmt == FMT_BOX_SMEM) return spt == 32 ? launch_variant<32, FMT_BOX_SMEM>(aligned, a, smem, st) : launch_variant<16, FMT_BOX_SMEM>(aligned, a, smem, st);

@@ -39,7 +39,7 @@ bool first_use_on_device(std::atomic<uint64_t>& done_mask);
 // MH_DEC_SUB_BITS_MARKOV, MH_DEC_SUB_BITS_HUFFMAN, MH_DEC_PAIR, MH_DEC_WRITE_THREADS, MH_PIPE_MIN_BYTES,
 // MH_PIPE_CHUNK_BYTES, MH_ENC_TMA, MH_ENC_WARP); afterwards only mh_tunable_set changes them. -1 = the documented default.
 enum Tunable { kTunEncFmt = 0, kTunDecSubBitsMarkov, kTunDecSubBitsHuffman, kTunDecPair, kTunDecWriteThreads, kTunPipeMinBytes,
-               kTunPipeChunkBytes, kTunEncPipeChunkBytes, kTunEncTma, kTunDecCpGeo, kTunEncWarp, kTunCount };
+               kTunPipeChunkBytes, kTunEncPipeChunkBytes, kTunEncTma, kTunDecCpGeo, kTunEncWarp, kTunEncSpt, kTunCount };
 long long tunable(Tunable t);
 
 // ---- tunables (env overrides exist for experiments; defaults are what DESIGN.md documents) ------------

@@ -15,7 +15,8 @@
 // reads the counts and writes the table rows together. All contexts run in parallel on different SMs.
 //
 // meta (u32[8], device): [0] context rows incl. the null row, [1] status (0, or a negative mh_status: a live count that
-// wrapped to 0, a codeword longer than 56 bits), [2] longest codeword, [3] live contexts.
+// wrapped to 0, a codeword longer than 56 bits), [2] longest codeword, [3] live contexts, [4..5] u64 sum of count x codeword
+// length (the payload's bits, up to wrapped counts), [6..7] u64 sum of the counts.
 #include "mh_internal.hpp"
 
 namespace mh {
@@ -213,12 +214,23 @@ __global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long lo
 		if(s_status) meta[1] = uint32_t(s_status);
 	}
 	__syncwarp();
+	unsigned long long bits = 0, symbols = 0;   // this context's share of the payload: the encoder sizes itself by the mean codeword
 	for(uint32_t c = lane; c < 256; c += 32) {
 		const uint32_t len = S.len[c];
 		const unsigned long long code = S.code[c];
 		enc_row[c] = len ? (static_cast<unsigned long long>(len) << 56) | code : 0ull;
 		if(ctx_fits)
 			ctx[size_t(my_row) * 256 + c] = len > 16 ? (31u << 27) | (next_of(c) << 16) : (len << 27) | (next_of(c) << 16) | (len ? uint32_t(code) : 0u);
+		bits += row[c] * len;
+		symbols += row[c];
+	}
+	for(int d = 16; d; d >>= 1) {
+		bits += __shfl_xor_sync(0xffffffffu, bits, d);
+		symbols += __shfl_xor_sync(0xffffffffu, symbols, d);
+	}
+	if(lane == 0) {
+		atomicAdd(reinterpret_cast<unsigned long long*>(meta + 4), bits);
+		atomicAdd(reinterpret_cast<unsigned long long*>(meta + 6), symbols);
 	}
 }
 

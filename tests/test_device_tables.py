@@ -41,7 +41,22 @@ def check(counts_u64, order):
     if h_meta[0]:                                    # the host made a context-row table: same rows, same entries
         assert int(d_meta[0]) == int(h_meta[0])
         assert np.array_equal(d_ctx, h_ctx)
+    # the sums the encoder sizes itself by: sum of count x codeword length and sum of the counts, modulo 2^64
+    lens = provider.code_lengths()
+    c = np.ascontiguousarray(counts_u64)[:n].astype(np.uint64)
+    with np.errstate(over="ignore"):
+        assert int(d_meta[4]) | (int(d_meta[5]) << 32) == int(np.sum(c * lens, dtype=np.uint64))
+        assert int(d_meta[6]) | (int(d_meta[7]) << 32) == int(np.sum(np.where(_ctx_live(c, order), c, 0), dtype=np.uint64))
     return provider
+
+
+def _ctx_live(c, order):
+    """Counts that belong to a context with a tree (a context whose counts are all 0 in the reference's 32-bit view has none)."""
+    if not order:
+        return np.ones(c.shape, dtype=bool)
+    rows = c.reshape(256, 256)
+    live_rows = ((rows & np.uint64(0xFFFFFFFF)) != 0).any(axis=1)
+    return np.repeat(live_rows, 256)
 
 
 @pytest.mark.parametrize("name,counts", _count_vectors(), ids=[n for n, _ in _count_vectors()])
