@@ -23,48 +23,57 @@ namespace mh {
 namespace {
 
 struct TreeScratch {
-	int32_t heap_w[256];
-	int16_t heap_n[256];
+	unsigned long long heap[256];   // the array heap: weight << 32 | node; after the heap phase: the paths of the internal nodes
 	int16_t left[512], right[512];
 	int32_t weight[512];
 	int16_t height[512];
 	uint8_t symbol[256];      // of leaf i (leaves are nodes 0 .. n_leaves - 1, in ascending symbol order)
-	int16_t stack_node[260];
-	uint8_t stack_stage[260];
 	uint8_t len[256];
 	unsigned long long code[256];
 };
 
+// The heap's entries are one 64-bit word each — weight (int32, the reference's `int`) in the high half, node in the low
+// half — and an element that moves several levels travels through a hole (one store per level and one at the end)
+// instead of being swapped level by level: the same comparisons in the same order, so the same arrangement as the
+// reference's swaps, at half the shared-memory round trips of the one lane that runs this.
+__device__ __forceinline__ int32_t heap_weight(unsigned long long e) { return int32_t(uint32_t(e >> 32)); }
+
 // min_pq::insert (src/min_pq.tpp:4-8, swim :29-36): move up while the parent is strictly heavier
 __device__ __forceinline__ void heap_push(TreeScratch& S, int& hs, int32_t w, int node) {
 	int i = hs++;
-	S.heap_w[i] = w;
-	S.heap_n[i] = int16_t(node);
+	const unsigned long long me = (static_cast<unsigned long long>(uint32_t(w)) << 32) | uint32_t(node);
 	while(i > 0) {
 		const int up = (i - 1) >> 1;
-		if(!(S.heap_w[up] > S.heap_w[i])) break;
-		const int32_t tw = S.heap_w[up]; S.heap_w[up] = S.heap_w[i]; S.heap_w[i] = tw;
-		const int16_t tn = S.heap_n[up]; S.heap_n[up] = S.heap_n[i]; S.heap_n[i] = tn;
+		const unsigned long long u = S.heap[up];
+		if(!(heap_weight(u) > w)) break;
+		S.heap[i] = u;
 		i = up;
 	}
+	S.heap[i] = me;
 }
 
 // min_pq::pop_min (src/min_pq.tpp:9-27, sink :38-52): the right child only if strictly lighter than the left one, and a
 // swap only if the candidate is strictly lighter than the node
 __device__ __forceinline__ int heap_pop(TreeScratch& S, int& hs) {
-	const int top = S.heap_n[0];
+	const int top = int(uint32_t(S.heap[0]));
 	--hs;
-	S.heap_w[0] = S.heap_w[hs];
-	S.heap_n[0] = S.heap_n[hs];
+	const unsigned long long me = S.heap[hs];
+	const int32_t w = heap_weight(me);
 	int i = 0;
 	for(;;) {
 		const int l = 2 * i + 1, r = l + 1;
-		const int pick = (r < hs && S.heap_w[r] < S.heap_w[l]) ? r : l;
-		if(pick >= hs || !(S.heap_w[pick] < S.heap_w[i])) break;
-		const int32_t tw = S.heap_w[pick]; S.heap_w[pick] = S.heap_w[i]; S.heap_w[i] = tw;
-		const int16_t tn = S.heap_n[pick]; S.heap_n[pick] = S.heap_n[i]; S.heap_n[i] = tn;
+		if(l >= hs) break;
+		unsigned long long pick_e = S.heap[l];
+		int pick = l;
+		if(r < hs) {
+			const unsigned long long right_e = S.heap[r];
+			if(heap_weight(right_e) < heap_weight(pick_e)) { pick = r; pick_e = right_e; }
+		}
+		if(!(heap_weight(pick_e) < w)) break;
+		S.heap[i] = pick_e;
 		i = pick;
 	}
+	S.heap[i] = me;
 	return top;
 }
 
@@ -93,40 +102,32 @@ __device__ int build_tree(TreeScratch& S, int n_leaves, uint32_t& max_len) {
 		max_len = 1;
 		return 0;
 	}
-	// pre-order walk, left edge 0, right edge 1 (src/huffman.cpp:97-123); stage 0 entering, 1 left done, 2 right done
-	int sp = 0, status = 0;
-	unsigned long long path = 0;
+	// Codes: left edge 0, right edge 1 — the reference's pre-order walk (src/huffman.cpp:97-123) gives every leaf the path
+	// from the root, and the order the nodes are visited in does not change a path. A node's children were made before
+	// it, so their indices are smaller: ONE pass from the root down over the internal nodes hands every child its depth
+	// and path — no stack, a fifth of the walk's shared-memory round trips (the tree build is serial work of one lane).
+	// The heap phase is over, so its arrays carry the pass: height[node] <- depth, heap[node - n_leaves] <- path (internal
+	// nodes only: fewer than 256).
+	int status = 0;
 	uint32_t longest = 0;
-	S.stack_node[0] = int16_t(root);
-	S.stack_stage[0] = 0;
-	while(sp >= 0) {
-		const int node = S.stack_node[sp];
-		if(S.left[node] < 0) {
-			const uint32_t depth = uint32_t(sp);
-			S.len[S.symbol[node]] = uint8_t(depth);
-			S.code[S.symbol[node]] = path;
-			if(depth > longest) longest = depth;
-			if(depth > uint32_t(MH_MAX_CODE_BITS)) status = MH_ERR_CODE_TOO_LONG;
-			--sp;
-			path >>= 1;
-			continue;
-		}
-		const int stage = S.stack_stage[sp];
-		if(stage == 0) {
-			S.stack_stage[sp] = 1;
-			path = path << 1;
-			++sp;
-			S.stack_node[sp] = S.left[node];
-			S.stack_stage[sp] = 0;
-		} else if(stage == 1) {
-			S.stack_stage[sp] = 2;
-			path = (path << 1) | 1ull;
-			++sp;
-			S.stack_node[sp] = S.right[node];
-			S.stack_stage[sp] = 0;
-		} else {
-			--sp;
-			path >>= 1;
+	S.height[root] = 0;
+	S.heap[root - n_leaves] = 0;
+	for(int node = root; node >= n_leaves; --node) {
+		const uint32_t depth = uint32_t(S.height[node]) + 1u;
+		const unsigned long long path = S.heap[node - n_leaves];
+#pragma unroll
+		for(int side = 0; side < 2; ++side) {
+			const int child = side ? S.right[node] : S.left[node];
+			const unsigned long long cp = (path << 1) | static_cast<unsigned long long>(side);
+			if(child < n_leaves) {
+				S.len[S.symbol[child]] = uint8_t(depth);
+				S.code[S.symbol[child]] = cp;
+				if(depth > longest) longest = depth;
+				if(depth > uint32_t(MH_MAX_CODE_BITS)) status = MH_ERR_CODE_TOO_LONG;
+			} else {
+				S.height[child] = int16_t(depth);
+				S.heap[child - n_leaves] = cp;
+			}
 		}
 	}
 	max_len = longest;
@@ -202,12 +203,22 @@ __global__ void __launch_bounds__(32) tables_build_kernel(const unsigned long lo
 	const unsigned long long* row = counts + size_t(p) * 256;
 	for(uint32_t c = lane; c < 256; c += 32) { S.len[c] = 0; S.code[c] = 0; }
 	__syncwarp();
-	if(lane == 0) {
-		int n = 0;
-		for(int s = 0; s < 256; ++s) {
-			const int32_t w = int32_t(uint32_t(row[s]));
-			if(w != 0) { S.weight[n] = w; S.symbol[n] = uint8_t(s); ++n; }   // `if(counts[i])`: a wrapped-negative count is still a leaf
+	// the leaves in ascending symbol order (src/huffman.cpp:134-138), gathered by the whole warp: eight coalesced loads per lane
+	// instead of 256 loads by lane 0
+	int n = 0;
+	for(int k = 0; k < 8; ++k) {
+		const int sym = k * 32 + int(lane);
+		const int32_t w = int32_t(uint32_t(row[sym]));
+		const uint32_t m = __ballot_sync(0xffffffffu, w != 0);   // `if(counts[i])`: a wrapped-negative count is still a leaf
+		if(w != 0) {
+			const int at = n + __popc(m & ((1u << lane) - 1u));
+			S.weight[at] = w;
+			S.symbol[at] = uint8_t(sym);
 		}
+		n += __popc(m);
+	}
+	__syncwarp();
+	if(lane == 0) {
 		uint32_t longest = 0;
 		s_status = build_tree(S, n, longest);
 		atomicMax(meta + 2, longest);

@@ -216,6 +216,46 @@ def test_warp_private_encoder_agrees(session, ipsum_counts, tunables):
         assert session.compress_with_table(provider, holes) == want_holes
 
 
+def test_optimistic_64_symbol_encoder_and_its_fail_over(session, ipsum_counts, tunables):
+    """Device-built tables are encoded by an optimistic launch with 64 symbols per thread (30 KiB tiles, a staging area
+    sized by what shared memory leaves, not by the worst case) and an ordinary launch queued behind it that leaves at
+    once unless the first one declined or failed. Same bytes as the oracle: around the 30 KiB tiles, with the optimistic
+    launch switched off (enc_spt = 32), when a tile's bits overflow the staging area (fail-over in mid-stream), and
+    when the tables are declined up front (mean codeword above 5.5 bits)."""
+    text = o.synth_markov(ipsum_counts, 64, 65536, 0, (3 << 20) + 77)
+    sizes = (30719, 30720, 30721, 61440, 61445, 92160 + 63, len(text))
+    want = {(n, order): o.compress_from_input(text[:n], bool(order))[0] for n in sizes for order in (0, 1)}
+    for spt in ("-1", "32"):
+        tunables("enc_spt", spt)
+        for (n, order), stream in want.items():
+            assert session.compress(text[:n], order)[0] == stream, "n=%d order=%d enc_spt=%s" % (n, order, spt)
+    tunables("enc_spt", "-1")
+    # one whole tile of rare symbols (14-bit codewords in -h mode: more than the staging area holds) inside a stream whose
+    # mean codeword is about two bits: the optimistic launch fails in mid-stream
+    rng = np.random.default_rng(15)
+    ladder = np.array([2.0 ** -(i + 1) for i in range(7)])
+    ladder[-1] *= 2
+    body = rng.choice(np.arange(65, 72, dtype=np.uint8), size=4 << 20, p=ladder)   # codewords of 1..7 bits
+    rare = np.tile(np.arange(16, 256, dtype=np.uint8), 128)
+    rare = np.concatenate([rare[rare < 65], rare[rare > 71]])                       # 233 rare values: 14-bit codewords
+    rare = np.tile(rare, 2)[:30720]
+    body[3 * 30720: 4 * 30720] = rare                                               # ... filling the stream's fourth tile
+    data = bytes(body)
+    stream, provider = session.compress(data, 0)
+    lens = provider.code_lengths()
+    assert int(lens[rare].sum()) > (112 * 1024 - 32768 - 30720 - 64) * 8, "the tile was meant to overflow the staging area"
+    assert float(np.dot(np.bincount(body, minlength=256), lens)) / len(data) < 5.5, "the tables were meant to be accepted"
+    want_stream, want_table = o.compress_from_input(data, False)
+    assert provider.write_coding_tree() == want_table
+    assert sha(stream) == sha(want_stream)
+    assert session.decompress(provider, stream) == data
+    stream1, provider1 = session.compress(data, 1)
+    assert sha(stream1) == sha(o.compress_from_input(data, True)[0])
+    # uniform bytes: 8-bit codewords, declined up front
+    noise = bytes(rng.integers(0, 256, 1 << 20, dtype=np.uint8))
+    assert sha(session.compress(noise, 0)[0]) == sha(o.compress_from_input(noise, False)[0])
+
+
 @pytest.mark.parametrize("threads", ["64", "128", "256"])
 def test_small_write_ctas_keep_speculative_lookups_inside_the_table(session, threads, tunables):
     """D4 sizes its CTAs by the number of subsequences (small streams: small CTAs on every SM). With little shared
