@@ -100,9 +100,9 @@ def ncu_traffic(kernel, config, n_bytes):
             cap = json.load(open(path))
             if cap.get("source_hash") != want or cap.get("input_bytes") != n_bytes or cap.get("config", "markov") != config:
                 continue
-            for name, rec in cap["kernels"].items():
-                if kernel.split("<")[0] in name:
-                    return rec["traffic_bytes"]
+            hits = [rec["traffic_bytes"] for name, rec in cap["kernels"].items() if kernel.split("<")[0] in name]
+            if hits:   # (the encoder has two instances in a step: the one that did the work, and the one that left at once)
+                return max(hits)
         except Exception:
             continue
     return None
