@@ -151,14 +151,56 @@ def pin_to_gpu_numa_node(gpu_index):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML from a thread of this process, every 5 ms (a
+    timed region is tens of milliseconds: an nvidia-smi child process needs longer than that to print its first line),
+    falling back to `nvidia-smi -lms 50` when NVML cannot be loaded."""
     FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, threading.Event()
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            try:   # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES reorders the devices: go by UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, handle
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        try:
+            self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            try:
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            for name, bit in (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap)):
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            self._sample()
+            self.stop_flag.wait(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         if shutil.which("nvidia-smi") is None:
             return
         try:
@@ -173,6 +215,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(1.0)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": sorted(self.reasons),
+                    "how": "NVML, every 5 ms inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.1)
@@ -187,7 +235,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons), "how": "nvidia-smi -lms 50"}
 
 
 # ---------------------------------------------------------------------------------------------------------
