@@ -26,6 +26,11 @@
 //   5. one iteration later the workers funnel-shift the staged bits by the tile's global bit phase and write them
 //      with coalesced 32-bit stores, byte-swapped so that stream bit p lands in byte p/8, bit 7 - p%8
 //      (src/bitbuffer.cpp:12); the words just copied are re-zeroed for the next tile.
+// Device-built tables (the compress path of sessions, shards and the bench) are encoded by TWO launches of this kernel: an
+// optimistic instance with SPT = 64 (a third of the 32-symbol kernel's instructions were paid per tile, not per symbol;
+// its quads are one word + a packed length, its staging area is what shared memory leaves, and it declines tables and
+// fails on tiles it is not made for) and the ordinary SPT = 32 instance queued behind it, which reads the first one's
+// flag and either hands its results over and leaves, or encodes the stream itself (launch_encode).
 #include "mh_internal.hpp"
 
 namespace mh {
