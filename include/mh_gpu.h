@@ -51,7 +51,8 @@ int mh_device_memory(int device, uint64_t* free_bytes, uint64_t* total_bytes);
 int mh_version(void);
 /* Experiment / test overrides of the library's tunables ("enc_fmt", "dec_sub_bits_markov", "dec_sub_bits_huffman",
  * "dec_pair", "dec_write_threads", "pipe_min_bytes", "pipe_chunk_bytes", "enc_pipe_chunk_bytes", "enc_tma", "dec_cp_geo",
- * "enc_warp" — 1 selects the encoder with warp-private tiles —); -1 = the documented default. The matching environment variables (MH_ENC_FMT, ...) are read once, when the library is loaded. */
+ * "enc_warp" — 1 selects the encoder with warp-private tiles —, "enc_spt" — 32 switches the optimistic 64-symbols-per-thread
+ * encoder launch for device-built tables off —); -1 = the documented default. The matching environment variables (MH_ENC_FMT, ...) are read once, when the library is loaded. */
 int mh_tunable_set(const char* name, long long value);
 int mh_tunable_get(const char* name, long long* value);
 /* Page-locked host memory for the host-buffer calls below: copies from / to pageable memory cannot overlap with the
